@@ -1,0 +1,675 @@
+// libb2svm.so: C-ABI entry points of the solver (see include/b2svm.h) and the small support
+// kernels around the persistent SMO kernel.  Build: pysvm_b200/build.py (nvcc, sm_100a).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b2svm_internal.h"
+#include "b2svm_smo.cuh"
+
+namespace b2svm {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int chunks_for(int x_dtype, int d) {
+  const int per = x_dtype == B2SVM_F64 ? 2 : 4;
+  const int need = (d + per - 1) / per;
+  for (int ch = 4; ch <= 128; ch *= 2)
+    if (need <= ch) return ch;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// support kernels
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pad_rows_kernel(const T* __restrict__ src, int64_t ld, T* __restrict__ dst, int64_t l, int d, int dp) {
+  const int64_t total = l * dp;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / dp;
+    const int c = (int)(e - r * dp);
+    dst[e] = c < d ? src[r * ld + c] : T(0);
+  }
+}
+
+// |x_r|^2 in T, one warp per row (reference: (x**2).sum(1), svc.py:231)
+template <typename T>
+__global__ void row_norms_kernel(const T* __restrict__ X, int64_t l, int dp, T* __restrict__ norms) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < l; r += nwarps) {
+    T s = 0;
+    for (int c = lane; c < dp; c += 32) {
+      const T v = X[r * dp + c];
+      s += v * v;
+    }
+    s = warp_sum(s);
+    if (lane == 0) norms[r] = s;
+  }
+}
+
+__global__ void refresh_flags_kernel(const double* __restrict__ y, const double* __restrict__ alpha, double C,
+                                     uint8_t* __restrict__ flags, int64_t nv) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x)
+    flags[v] = make_flags(y[v] > 0, alpha[v], C);
+}
+
+// Solver.__init__: alpha = 0, neg_y_grad = -y * p   (solver.py:42-45)
+__global__ void init_state_kernel(const double* __restrict__ y, const double* __restrict__ p,
+                                  double* __restrict__ alpha, double* __restrict__ G, int64_t nv) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    alpha[v] = 0.0;
+    G[v] = -y[v] * p[v];
+  }
+}
+
+// func(i): Q column as float64, out[v] = y_v * K(x_row(v), x_row(i)) * y_i   (svc.py:257-258)
+template <typename T>
+__global__ void column_kernel(const T* __restrict__ X, const T* __restrict__ norms, const double* __restrict__ y,
+                              int64_t l, int64_t nv, int dp, KernelParams<T> kp, int64_t i,
+                              double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t ri = i >= l ? i - l : i;
+  const double yi = y[i];
+  for (int64_t r = warp; r < l; r += nwarps) {
+    T s = 0;
+    for (int c = lane; c < dp; c += 32) s = fma(X[r * dp + c], X[ri * dp + c], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const double k = (double)kernel_value(kp, s, norms[r], norms[ri]);
+      out[r] = y[r] * k * yi;
+      if (nv > l) out[r + l] = y[r + l] * k * yi;
+    }
+  }
+}
+
+// Everything calculate_rho (solver.py:160-177) and calculate_rho_b (solver.py:378-419) need,
+// reduced in a fixed order by one block.
+struct BiasStats {
+  // C variant
+  double sum_free, min_lb, max_ub;
+  long long cnt_free, cnt_lb, cnt_ub;
+  // nu variant, per class (0: y=+1, 1: y=-1); grad = -y * g, bound tests against the literal 1
+  double nsum[2], nmax_hi[2], nmin_lo[2];
+  long long ncnt[2], nhi[2], nlo[2];
+};
+
+__device__ __forceinline__ void merge_stats(BiasStats& a, const BiasStats& b) {
+  a.sum_free += b.sum_free;
+  a.cnt_free += b.cnt_free;
+  if (b.cnt_lb) { a.min_lb = a.cnt_lb ? fmin(a.min_lb, b.min_lb) : b.min_lb; a.cnt_lb += b.cnt_lb; }
+  if (b.cnt_ub) { a.max_ub = a.cnt_ub ? fmax(a.max_ub, b.max_ub) : b.max_ub; a.cnt_ub += b.cnt_ub; }
+  for (int s = 0; s < 2; ++s) {
+    a.nsum[s] += b.nsum[s];
+    a.ncnt[s] += b.ncnt[s];
+    if (b.nhi[s]) { a.nmax_hi[s] = a.nhi[s] ? fmax(a.nmax_hi[s], b.nmax_hi[s]) : b.nmax_hi[s]; a.nhi[s] += b.nhi[s]; }
+    if (b.nlo[s]) { a.nmin_lo[s] = a.nlo[s] ? fmin(a.nmin_lo[s], b.nmin_lo[s]) : b.nmin_lo[s]; a.nlo[s] += b.nlo[s]; }
+  }
+}
+
+__global__ void __launch_bounds__(1024) bias_stats_kernel(const double* __restrict__ y, const double* __restrict__ alpha,
+                                                          const double* __restrict__ G, double C, int64_t nv,
+                                                          BiasStats* __restrict__ out) {
+  __shared__ BiasStats sh[32];
+  BiasStats st;
+  memset(&st, 0, sizeof(st));
+  for (int64_t v = threadIdx.x; v < nv; v += blockDim.x) {
+    const double a = alpha[v], g = G[v], yy = y[v];
+    BiasStats one;
+    memset(&one, 0, sizeof(one));
+    if (a > 0 && a < C) { one.sum_free = g; one.cnt_free = 1; }
+    const bool ub = (a == 0 && yy < 0) || (a == C && yy > 0);
+    const bool lb = (a == 0 && yy > 0) || (a == C && yy < 0);
+    if (ub) { one.max_ub = g; one.cnt_ub = 1; }
+    if (lb) { one.min_lb = g; one.cnt_lb = 1; }
+    const int s = yy == 1.0 ? 0 : (yy == -1.0 ? 1 : -1);
+    if (s >= 0) {
+      const double grad = -yy * g;
+      if (a > 0 && a < 1) { one.nsum[s] = grad; one.ncnt[s] = 1; }
+      if (a == 1) { one.nmax_hi[s] = grad; one.nhi[s] = 1; }
+      if (a == 0) { one.nmin_lo[s] = grad; one.nlo[s] = 1; }
+    }
+    merge_stats(st, one);
+  }
+  // fixed-order tree: lanes, then warps
+  for (int m = 16; m >= 1; m >>= 1) {
+    BiasStats o;
+    const int* src = reinterpret_cast<const int*>(&st);
+    int* dst = reinterpret_cast<int*>(&o);
+    for (int w = 0; w < (int)(sizeof(BiasStats) / 4); ++w) dst[w] = __shfl_down_sync(0xffffffffu, src[w], m);
+    if ((threadIdx.x & 31) + m < 32) merge_stats(st, o);
+  }
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = st;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    BiasStats tot = sh[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) merge_stats(tot, sh[w]);
+    *out = tot;
+  }
+}
+
+// w[r] = sum over the variables that share row r of y_v * alpha_v  (non-mirror: y_r alpha_r;
+// mirror: alpha_r - alpha_{r+l}).  (Q alpha)[t] = y_t * (K w)[row(t)].
+__global__ void row_weights_kernel(const double* __restrict__ y, const double* __restrict__ alpha, int64_t l,
+                                   int64_t nv, double* __restrict__ w) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < l; r += (int64_t)gridDim.x * blockDim.x) {
+    double s = y[r] * alpha[r];
+    if (nv > l) s += y[r + l] * alpha[r + l];
+    w[r] = s;
+  }
+}
+
+// G[t] = -y_t * (y_t * m[row(t)] + p_t)     (solver.py:280 / 470-472, oc_svm.py:95)
+__global__ void finish_gradient_kernel(const double* __restrict__ y, const double* __restrict__ p,
+                                       const double* __restrict__ m, int64_t l, int64_t nv, double* __restrict__ G) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = v >= l ? v - l : v;
+    const double q = y[v] * m[r];
+    G[v] = -y[v] * (q + (p ? p[v] : 0.0));
+  }
+}
+
+}  // namespace b2svm
+
+using namespace b2svm;
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct b2svm_handle {
+  b2svm_problem_desc d;
+  cudaStream_t stream = nullptr;
+  int ch = 0;           // 16-byte chunks per padded row
+  int dp = 0;           // padded feature count
+  bool f64 = false;
+  void* Xown = nullptr;         // padded copy (nullptr when the caller's X is used in place)
+  const void* Xuse = nullptr;
+  void* norms = nullptr;
+  uint8_t* flags = nullptr;
+  CandRec* cand = nullptr;
+  uint32_t* flag = nullptr;
+  int* abort_flag = nullptr;
+  SolveResult* result = nullptr;
+  SolveResult* result_host = nullptr;
+  ProblemDev* prob_dev = nullptr;
+  BiasStats* bias_dev = nullptr;
+  double* scratch = nullptr;    // [2 * n_rows] row weights + mat-vec result
+  double* p_dev = nullptr;      // staging for host-side p
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 0;
+  int ncta = 1, tiles_per_cta = 1, stages = 2;
+  long long ntiles = 0;
+  size_t smem_bytes = 0;
+  int launches = 0;
+};
+
+namespace {
+
+inline int grid_for(int64_t n, int block = 256, int cap = 148 * 8) {
+  int64_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+template <typename T, int CH>
+struct Geometry {
+  using C = Cfg<T, CH>;
+  static size_t smem_for(int stages) {
+    return (size_t)stages * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + 2 * (size_t)C::ROWB +
+           sizeof(Shared<T>) + 128;
+  }
+};
+
+constexpr size_t kSmemBudget = 227 * 1024;   // opt-in maximum per CTA on sm_100
+constexpr size_t kRingBudget = 200 * 1024;
+
+template <typename T, int CH>
+int plan_T(b2svm_handle* h) {
+  using C = Cfg<T, CH>;
+  int stages = (int)std::min<size_t>(MAX_STAGES, kRingBudget / C::TILE_BYTES);
+  if (stages < 2) stages = 2;
+  while (stages > 2 && Geometry<T, CH>::smem_for(stages) > kSmemBudget) --stages;
+  h->stages = stages;
+  h->smem_bytes = Geometry<T, CH>::smem_for(stages);
+  h->ntiles = (h->d.n_rows + C::BR - 1) / C::BR;
+  int min_tiles = 8;
+  if (const char* e = getenv("B2SVM_MIN_TILES_PER_CTA")) min_tiles = std::max(1, atoi(e));
+  int max_ctas = h->d.max_ctas > 0 ? h->d.max_ctas : h->num_sms;
+  if (const char* e = getenv("B2SVM_MAX_CTAS")) max_ctas = std::max(1, atoi(e));
+  max_ctas = std::min(max_ctas, h->num_sms);
+  long long ncta = std::max<long long>(1, std::min<long long>(max_ctas, h->ntiles / min_tiles));
+  const long long tpc = (h->ntiles + ncta - 1) / ncta;
+  ncta = (h->ntiles + tpc - 1) / tpc;
+  h->ncta = (int)ncta;
+  h->tiles_per_cta = (int)tpc;
+  return B2SVM_OK;
+}
+
+template <typename T, int CH>
+int launch_T(const ProblemDev* probs_dev, int nprob, int ncta_pp, int stages, size_t smem, cudaStream_t stream) {
+  auto kern = smo_persistent<T, CH>;
+  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = nprob * ncta_pp;
+  if (ncta_pp > 1) {
+    // CTAs of one problem wait on each other: co-residency must be guaranteed
+    void* args[] = {(void*)&probs_dev, (void*)&ncta_pp, (void*)&stages};
+    B2_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NTHREADS), args, smem, stream));
+  } else {
+    kern<<<grid, NTHREADS, smem, stream>>>(probs_dev, ncta_pp, stages);
+    B2_CUDA(cudaGetLastError());
+  }
+  return B2SVM_OK;
+}
+
+#define B2_DISPATCH_CH(T, ch, CALL)                                                \
+  switch (ch) {                                                                    \
+    case 4: return CALL(T, 4);                                                     \
+    case 8: return CALL(T, 8);                                                     \
+    case 16: return CALL(T, 16);                                                   \
+    case 32: return CALL(T, 32);                                                   \
+    case 64: return CALL(T, 64);                                                   \
+    case 128: return CALL(T, 128);                                                 \
+    default: return fail(B2SVM_E_UNSUPPORTED, "unsupported row width");            \
+  }
+
+int plan(b2svm_handle* h) {
+#define CALL_PLAN(T, CHV) plan_T<T, CHV>(h)
+  if (h->f64) { B2_DISPATCH_CH(double, h->ch, CALL_PLAN) } else { B2_DISPATCH_CH(float, h->ch, CALL_PLAN) }
+#undef CALL_PLAN
+}
+
+int launch(bool f64, int ch, const ProblemDev* probs_dev, int nprob, int ncta_pp, int stages, size_t smem,
+           cudaStream_t stream) {
+#define CALL_LAUNCH(T, CHV) launch_T<T, CHV>(probs_dev, nprob, ncta_pp, stages, smem, stream)
+  if (f64) { B2_DISPATCH_CH(double, ch, CALL_LAUNCH) } else { B2_DISPATCH_CH(float, ch, CALL_LAUNCH) }
+#undef CALL_LAUNCH
+}
+
+void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long long fi, long long fj) {
+  P.X = h->Xuse;
+  P.norms = h->norms;
+  P.alpha = h->d.alpha;
+  P.G = h->d.neg_y_grad;
+  P.flags = h->flags;
+  P.l = h->d.n_rows;
+  P.nv = h->d.n_vars;
+  P.mirror = h->d.n_vars > h->d.n_rows ? 1 : 0;
+  P.nu = h->d.variant == B2SVM_SOLVER_NU ? 1 : 0;
+  P.C = h->d.C;
+  P.tol = h->d.tol;
+  P.kind = h->d.kernel.kind;
+  P.gamma = h->d.kernel.gamma;
+  P.coef0 = h->d.kernel.coef0;
+  P.degree = h->d.kernel.degree;
+  P.ncta = h->ncta;
+  P.tiles_per_cta = h->tiles_per_cta;
+  P.ntiles = h->ntiles;
+  P.cand = h->cand;
+  P.flag = h->flag;
+  P.abort_flag = h->abort_flag;
+  P.result = h->result;
+  P.max_iter = max_iter;
+  P.forced_i = fi;
+  P.forced_j = fj;
+}
+
+// one persistent launch for one handle; fills *res from the device result
+int run_solver(b2svm_handle* h, long long max_iter, long long fi, long long fj, SolveResult* res, float* ms) {
+  B2_CUDA(cudaSetDevice(h->d.device));
+  const int64_t nv = h->d.n_vars;
+  refresh_flags_kernel<<<grid_for(nv), 256, 0, h->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, nv);
+  B2_CUDA(cudaGetLastError());
+  B2_CUDA(cudaMemsetAsync(h->flag, 0, sizeof(uint32_t) * (h->num_sms + 1), h->stream));
+  ProblemDev P;
+  memset(&P, 0, sizeof(P));
+  fill_problem(h, P, max_iter, fi, fj);
+  B2_CUDA(cudaMemcpyAsync(h->prob_dev, &P, sizeof(P), cudaMemcpyHostToDevice, h->stream));
+  B2_CUDA(cudaEventRecord(h->ev0, h->stream));
+  int rc = launch(h->f64, h->ch, h->prob_dev, 1, h->ncta, h->stages, h->smem_bytes, h->stream);
+  if (rc != B2SVM_OK) return rc;
+  B2_CUDA(cudaEventRecord(h->ev1, h->stream));
+  B2_CUDA(cudaMemcpyAsync(h->result_host, h->result, sizeof(SolveResult), cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  h->launches = 2;
+  *res = *h->result_host;
+  if (ms) B2_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  if (res->status != 0) return fail(B2SVM_E_TIMEOUT, "device watchdog: a grid barrier did not complete");
+  return B2SVM_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// exported functions
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int b2svm_abi_version(void) { return B2SVM_ABI_VERSION; }
+const char* b2svm_last_error(void) { return g_last_error.c_str(); }
+
+int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
+  if (!desc || !out) return fail(B2SVM_E_INVALID, "null argument");
+  if (desc->struct_bytes != sizeof(b2svm_problem_desc))
+    return fail(B2SVM_E_INVALID, "b2svm_problem_desc size mismatch (ABI version?)");
+  if (desc->n_rows <= 0 || desc->n_features <= 0) return fail(B2SVM_E_INVALID, "empty problem");
+  if (desc->n_vars != desc->n_rows && desc->n_vars != 2 * desc->n_rows)
+    return fail(B2SVM_E_INVALID, "n_vars must be n_rows or 2*n_rows");
+  if (desc->n_vars >= (1ll << 31)) return fail(B2SVM_E_UNSUPPORTED, "n_vars must be below 2^31");
+  if (!desc->X || !desc->y || !desc->alpha || !desc->neg_y_grad) return fail(B2SVM_E_INVALID, "null device pointer");
+  if (desc->x_dtype != B2SVM_F32 && desc->x_dtype != B2SVM_F64) return fail(B2SVM_E_INVALID, "bad x_dtype");
+  if (desc->kernel.kind < 0 || desc->kernel.kind > 3) return fail(B2SVM_E_INVALID, "bad kernel kind");
+  if (desc->world > 1) return fail(B2SVM_E_UNSUPPORTED, "row-sharded multi-GPU solve not built yet");
+  const int ch = chunks_for(desc->x_dtype, desc->n_features);
+  if (ch == 0) return fail(B2SVM_E_UNSUPPORTED, "n_features above the compiled maximum (512 f32 / 256 f64)");
+
+  B2_CUDA(cudaSetDevice(desc->device));
+  b2svm_handle* h = new b2svm_handle();
+  h->d = *desc;
+  h->stream = (cudaStream_t)desc->stream;
+  h->ch = ch;
+  h->f64 = desc->x_dtype == B2SVM_F64;
+  const int esz = h->f64 ? 8 : 4;
+  h->dp = ch * 16 / esz;
+  cudaDeviceProp prop;
+  B2_CUDA(cudaGetDeviceProperties(&prop, desc->device));
+  h->num_sms = prop.multiProcessorCount;
+  const int64_t l = desc->n_rows, nv = desc->n_vars;
+
+  auto cleanup_fail = [&](int code, const std::string& msg) {
+    b2svm_destroy(h);
+    return fail(code, msg);
+  };
+#define B2_TRY(expr)                                                                              \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) return cleanup_fail(B2SVM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+  const bool in_place = desc->ldx == h->dp && desc->n_features == h->dp && ((uintptr_t)desc->X % 16 == 0);
+  if (in_place) {
+    h->Xuse = desc->X;
+  } else {
+    B2_TRY(cudaMalloc(&h->Xown, (size_t)l * h->dp * esz));
+    if (h->f64)
+      pad_rows_kernel<double><<<grid_for(l * h->dp), 256, 0, h->stream>>>((const double*)desc->X, desc->ldx,
+                                                                          (double*)h->Xown, l, desc->n_features, h->dp);
+    else
+      pad_rows_kernel<float><<<grid_for(l * h->dp), 256, 0, h->stream>>>((const float*)desc->X, desc->ldx,
+                                                                         (float*)h->Xown, l, desc->n_features, h->dp);
+    B2_TRY(cudaGetLastError());
+    h->Xuse = h->Xown;
+  }
+  B2_TRY(cudaMalloc(&h->norms, (size_t)l * esz));
+  if (h->f64)
+    row_norms_kernel<double><<<grid_for(l * 32), 256, 0, h->stream>>>((const double*)h->Xuse, l, h->dp, (double*)h->norms);
+  else
+    row_norms_kernel<float><<<grid_for(l * 32), 256, 0, h->stream>>>((const float*)h->Xuse, l, h->dp, (float*)h->norms);
+  B2_TRY(cudaGetLastError());
+  B2_TRY(cudaMalloc(&h->flags, (size_t)nv));
+  B2_TRY(cudaMalloc(&h->cand, sizeof(CandRec) * 2 * h->num_sms * NCAND));
+  B2_TRY(cudaMalloc(&h->flag, sizeof(uint32_t) * (h->num_sms + 1)));
+  h->abort_flag = reinterpret_cast<int*>(h->flag + h->num_sms);
+  B2_TRY(cudaMalloc(&h->result, sizeof(SolveResult)));
+  B2_TRY(cudaMallocHost(&h->result_host, sizeof(SolveResult)));
+  B2_TRY(cudaMalloc(&h->prob_dev, sizeof(ProblemDev)));
+  B2_TRY(cudaMalloc(&h->bias_dev, sizeof(BiasStats)));
+  B2_TRY(cudaEventCreate(&h->ev0));
+  B2_TRY(cudaEventCreate(&h->ev1));
+#undef B2_TRY
+  int rc = plan(h);
+  if (rc != B2SVM_OK) {
+    b2svm_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return B2SVM_OK;
+}
+
+int b2svm_destroy(b2svm_handle* h) {
+  if (!h) return B2SVM_OK;
+  cudaSetDevice(h->d.device);
+  if (h->stream) cudaStreamSynchronize(h->stream); else cudaDeviceSynchronize();
+  cudaFree(h->Xown);
+  cudaFree(h->norms);
+  cudaFree(h->flags);
+  cudaFree(h->cand);
+  cudaFree(h->flag);
+  cudaFree(h->result);
+  if (h->result_host) cudaFreeHost(h->result_host);
+  cudaFree(h->prob_dev);
+  cudaFree(h->bias_dev);
+  cudaFree(h->scratch);
+  cudaFree(h->p_dev);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+  return B2SVM_OK;
+}
+
+static int stage_p(b2svm_handle* h, const double* p, const double** p_use) {
+  // p may live on the host or the device: stage through a device buffer (UVA-aware copy)
+  if (!p) { *p_use = nullptr; return B2SVM_OK; }
+  if (!h->p_dev) B2_CUDA(cudaMalloc(&h->p_dev, sizeof(double) * h->d.n_vars));
+  B2_CUDA(cudaMemcpyAsync(h->p_dev, p, sizeof(double) * h->d.n_vars, cudaMemcpyDefault, h->stream));
+  *p_use = h->p_dev;
+  return B2SVM_OK;
+}
+
+int b2svm_init_state(b2svm_handle* h, const double* p) {
+  if (!h || !p) return fail(B2SVM_E_INVALID, "null argument");
+  B2_CUDA(cudaSetDevice(h->d.device));
+  const double* pu;
+  int rc = stage_p(h, p, &pu);
+  if (rc) return rc;
+  init_state_kernel<<<grid_for(h->d.n_vars), 256, 0, h->stream>>>(h->d.y, pu, h->d.alpha, h->d.neg_y_grad, h->d.n_vars);
+  B2_CUDA(cudaGetLastError());
+  return B2SVM_OK;
+}
+
+int b2svm_init_gradient(b2svm_handle* h, const double* p) {
+  if (!h) return fail(B2SVM_E_INVALID, "null handle");
+  B2_CUDA(cudaSetDevice(h->d.device));
+  const int64_t l = h->d.n_rows, nv = h->d.n_vars;
+  const double* pu;
+  int rc = stage_p(h, p, &pu);
+  if (rc) return rc;
+  if (!h->scratch) B2_CUDA(cudaMalloc(&h->scratch, sizeof(double) * 2 * l));
+  double* w = h->scratch;
+  double* m = h->scratch + l;
+  row_weights_kernel<<<grid_for(l), 256, 0, h->stream>>>(h->d.y, h->d.alpha, l, nv, w);
+  B2_CUDA(cudaGetLastError());
+  rc = kernel_matvec_impl(h->stream, h->d.kernel, h->d.x_dtype, h->dp, h->Xuse, l, h->dp, h->Xuse, l, h->dp, w, m);
+  if (rc) return rc;
+  finish_gradient_kernel<<<grid_for(nv), 256, 0, h->stream>>>(h->d.y, pu, m, l, nv, h->d.neg_y_grad);
+  B2_CUDA(cudaGetLastError());
+  return B2SVM_OK;
+}
+
+int b2svm_select(b2svm_handle* h, int64_t* i, int64_t* j) {
+  if (!h || !i || !j) return fail(B2SVM_E_INVALID, "null argument");
+  SolveResult r;
+  int rc = run_solver(h, 0, -1, -1, &r, nullptr);
+  if (rc) return rc;
+  *i = r.last_i;
+  *j = r.last_j;
+  return B2SVM_OK;
+}
+
+int b2svm_update(b2svm_handle* h, int64_t i, int64_t j, double* delta_i, double* delta_j) {
+  if (!h) return fail(B2SVM_E_INVALID, "null handle");
+  if (i < 0 || j < 0 || i >= h->d.n_vars || j >= h->d.n_vars) return fail(B2SVM_E_INVALID, "index out of range");
+  SolveResult r;
+  int rc = run_solver(h, 1, i, j, &r, nullptr);
+  if (rc) return rc;
+  if (delta_i) *delta_i = r.di;
+  if (delta_j) *delta_j = r.dj;
+  return B2SVM_OK;
+}
+
+int b2svm_kernel_column(b2svm_handle* h, int64_t i, double* out) {
+  if (!h || !out) return fail(B2SVM_E_INVALID, "null argument");
+  if (i < 0 || i >= h->d.n_vars) return fail(B2SVM_E_INVALID, "index out of range");
+  B2_CUDA(cudaSetDevice(h->d.device));
+  const int64_t l = h->d.n_rows;
+  if (h->f64) {
+    KernelParams<double> kp{h->d.kernel.kind, h->d.kernel.gamma, h->d.kernel.coef0, h->d.kernel.degree};
+    column_kernel<double><<<grid_for(l * 32), 256, 0, h->stream>>>((const double*)h->Xuse, (const double*)h->norms,
+                                                                   h->d.y, l, h->d.n_vars, h->dp, kp, i, out);
+  } else {
+    KernelParams<float> kp{h->d.kernel.kind, (float)h->d.kernel.gamma, (float)h->d.kernel.coef0,
+                           (float)h->d.kernel.degree};
+    column_kernel<float><<<grid_for(l * 32), 256, 0, h->stream>>>((const float*)h->Xuse, (const float*)h->norms,
+                                                                  h->d.y, l, h->d.n_vars, h->dp, kp, i, out);
+  }
+  B2_CUDA(cudaGetLastError());
+  return B2SVM_OK;
+}
+
+int b2svm_solve(b2svm_handle* h, int64_t max_iter, b2svm_solve_stats* stats) {
+  if (!h) return fail(B2SVM_E_INVALID, "null handle");
+  if (max_iter < 0) return fail(B2SVM_E_INVALID, "max_iter < 0");
+  SolveResult r;
+  float ms = 0.f;
+  int rc = run_solver(h, max_iter, -1, -1, &r, &ms);
+  if (rc) return rc;
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->n_iter = r.n_iter;
+    stats->converged = r.converged;
+    stats->n_ctas = h->ncta;
+    stats->last_i = r.last_i;
+    stats->last_j = r.last_j;
+    stats->last_delta_i = r.di;
+    stats->last_delta_j = r.dj;
+    stats->cold_sweeps = r.cold_sweeps;
+    stats->cache_hits = 0;
+    stats->cache_misses = 2 * r.cold_sweeps;
+    const double esz = h->f64 ? 8.0 : 4.0;
+    // DESIGN.md section 4 / SURVEY 8(d): B_cold = l * d * sizeof(T) + n_vars * 18
+    stats->algorithmic_bytes =
+        (double)r.cold_sweeps * ((double)h->d.n_rows * h->d.n_features * esz + (double)h->d.n_vars * 18.0);
+    stats->device_ms = ms;
+    stats->launches = h->launches;
+  }
+  return B2SVM_OK;
+}
+
+static int bias_stats(b2svm_handle* h, BiasStats* host) {
+  B2_CUDA(cudaSetDevice(h->d.device));
+  bias_stats_kernel<<<1, 1024, 0, h->stream>>>(h->d.y, h->d.alpha, h->d.neg_y_grad, h->d.C, h->d.n_vars, h->bias_dev);
+  B2_CUDA(cudaGetLastError());
+  B2_CUDA(cudaMemcpyAsync(host, h->bias_dev, sizeof(BiasStats), cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  return B2SVM_OK;
+}
+
+int b2svm_rho(b2svm_handle* h, double* rho) {
+  if (!h || !rho) return fail(B2SVM_E_INVALID, "null argument");
+  BiasStats s;
+  int rc = bias_stats(h, &s);
+  if (rc) return rc;
+  if (s.cnt_free > 0) {
+    *rho = -(s.sum_free / (double)s.cnt_free);
+  } else {
+    if (s.cnt_lb == 0 || s.cnt_ub == 0)
+      return fail(B2SVM_E_INVALID, "calculate_rho: empty bound set (the reference raises ValueError here)");
+    *rho = -(s.min_lb + s.max_ub) / 2;
+  }
+  return B2SVM_OK;
+}
+
+int b2svm_rho_b(b2svm_handle* h, double* rho, double* b) {
+  if (!h || !rho || !b) return fail(B2SVM_E_INVALID, "null argument");
+  BiasStats s;
+  int rc = bias_stats(h, &s);
+  if (rc) return rc;
+  double r[2];
+  for (int c = 0; c < 2; ++c) {
+    if (s.ncnt[c] > 0) r[c] = s.nsum[c] / (double)s.ncnt[c];
+    else if (s.nhi[c] > 0 && s.nlo[c] > 0) r[c] = (s.nmax_hi[c] + s.nmin_lo[c]) / 2;
+    else r[c] = 0;   // the reference's bare except (solver.py:393-394, 411-412)
+  }
+  *rho = (r[0] + r[1]) / 2;
+  *b = (r[1] - r[0]) / 2;
+  return B2SVM_OK;
+}
+
+int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max_iter, b2svm_solve_stats* stats) {
+  if (!handles || count <= 0) return fail(B2SVM_E_INVALID, "empty batch");
+  b2svm_handle* h0 = handles[0];
+  B2_CUDA(cudaSetDevice(h0->d.device));
+  for (int k = 0; k < count; ++k) {
+    b2svm_handle* h = handles[k];
+    if (!h) return fail(B2SVM_E_INVALID, "null handle in batch");
+    if (h->f64 != h0->f64 || h->ch != h0->ch || h->d.device != h0->d.device || h->stream != h0->stream)
+      return fail(B2SVM_E_INVALID, "batched problems must share dtype, row width, device and stream");
+  }
+  // one CTA per problem, all problems in one launch (no inter-CTA waits -> ordinary launch)
+  std::vector<ProblemDev> P(count);
+  ProblemDev* pd = nullptr;
+  SolveResult* rd = nullptr;
+  B2_CUDA(cudaMalloc(&pd, sizeof(ProblemDev) * count));
+  B2_CUDA(cudaMalloc(&rd, sizeof(SolveResult) * count));
+  for (int k = 0; k < count; ++k) {
+    b2svm_handle* h = handles[k];
+    refresh_flags_kernel<<<grid_for(h->d.n_vars), 256, 0, h0->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, h->d.n_vars);
+    cudaMemsetAsync(h->flag, 0, sizeof(uint32_t) * (h->num_sms + 1), h0->stream);
+    memset(&P[k], 0, sizeof(ProblemDev));
+    fill_problem(h, P[k], max_iter, -1, -1);
+    P[k].ncta = 1;
+    P[k].tiles_per_cta = (int)h->ntiles;
+    P[k].result = rd + k;
+  }
+  B2_CUDA(cudaGetLastError());
+  B2_CUDA(cudaMemcpyAsync(pd, P.data(), sizeof(ProblemDev) * count, cudaMemcpyHostToDevice, h0->stream));
+  B2_CUDA(cudaEventRecord(h0->ev0, h0->stream));
+  int rc = launch(h0->f64, h0->ch, pd, count, 1, h0->stages, h0->smem_bytes, h0->stream);
+  if (rc == B2SVM_OK) {
+    cudaEventRecord(h0->ev1, h0->stream);
+    std::vector<SolveResult> R(count);
+    cudaError_t e = cudaMemcpyAsync(R.data(), rd, sizeof(SolveResult) * count, cudaMemcpyDeviceToHost, h0->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h0->stream);
+    if (e != cudaSuccess) rc = fail(B2SVM_E_CUDA, cudaGetErrorString(e));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h0->ev0, h0->ev1);
+    for (int k = 0; rc == B2SVM_OK && k < count; ++k) {
+      if (R[k].status != 0) rc = fail(B2SVM_E_TIMEOUT, "device watchdog tripped in a batched solve");
+      if (stats) {
+        memset(&stats[k], 0, sizeof(stats[k]));
+        stats[k].n_iter = R[k].n_iter;
+        stats[k].converged = R[k].converged;
+        stats[k].n_ctas = 1;
+        stats[k].last_i = R[k].last_i;
+        stats[k].last_j = R[k].last_j;
+        stats[k].last_delta_i = R[k].di;
+        stats[k].last_delta_j = R[k].dj;
+        stats[k].cold_sweeps = R[k].cold_sweeps;
+        stats[k].cache_misses = 2 * R[k].cold_sweeps;
+        const double esz = handles[k]->f64 ? 8.0 : 4.0;
+        stats[k].algorithmic_bytes = (double)R[k].cold_sweeps * ((double)handles[k]->d.n_rows * handles[k]->d.n_features * esz +
+                                                                 (double)handles[k]->d.n_vars * 18.0);
+        stats[k].device_ms = ms;
+        stats[k].launches = count + 1;
+      }
+    }
+  }
+  cudaFree(pd);
+  cudaFree(rd);
+  return rc;
+}
+
+int b2svm_mailbox_export(b2svm_handle*, void*) { return fail(B2SVM_E_UNSUPPORTED, "row-sharded multi-GPU solve not built yet"); }
+int b2svm_mailbox_attach(b2svm_handle*, const void*) { return fail(B2SVM_E_UNSUPPORTED, "row-sharded multi-GPU solve not built yet"); }
+
+}  // extern "C"

@@ -1,0 +1,337 @@
+// Dense kernel evaluation away from the SMO loop: decision_function / initial gradients (K7) and
+// random Fourier features (K8).  First-generation CUDA-core kernels (FFMA / DFMA with shared-memory
+// tiling); they never materialise the n_a x n_b kernel matrix the reference builds on the host
+// (pysvm/svm/svc.py:269-272).
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "b2svm_device.cuh"
+#include "b2svm_internal.h"
+
+namespace b2svm {
+
+// ------------------------------------------------------------------------------------------
+// ordered compaction of the rows with a non-zero coefficient (support vectors)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) compact_nonzero_kernel(const double* __restrict__ coef, int64_t n,
+                                                               int* __restrict__ idx, int* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_sh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_sh = 0;
+  __syncthreads();
+  for (int64_t start = 0; start < n; start += 1024) {
+    const int64_t e = start + threadIdx.x;
+    const bool nz = e < n && coef[e] != 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+    const int before = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = base_sh;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (nz) idx[off + before] = (int)e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += warp_tot[w];
+      base_sh += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base_sh;
+}
+
+// gather support rows into a dense [nsv][dp] block (zero padded), with norms and coefficients
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ Xa, int64_t lda, int d, int dp, const int* __restrict__ idx,
+                                   int nsv, const double* __restrict__ coef, T* __restrict__ sv, T* __restrict__ svn,
+                                   double* __restrict__ svc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp; k < nsv; k += nwarps) {
+    const int64_t r = idx[k];
+    T s = 0;
+    for (int c = lane; c < dp; c += 32) {
+      const T v = c < d ? Xa[r * lda + c] : T(0);
+      sv[k * dp + c] = v;
+      s += v * v;
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      svn[k] = s;
+      svc[k] = coef[r];
+    }
+  }
+}
+
+// out_partial[y][q] = sum_{s in slice y} coef_s K(sv_s, x_q); one query per thread, TS support rows
+// per shared-memory tile, query tile kept in shared memory chunk-major (conflict-free 16-B reads).
+constexpr int MV_TS = 32;
+
+template <typename T, int TQ>
+__global__ void __launch_bounds__(TQ) matvec_kernel(const T* __restrict__ sv, const T* __restrict__ svn,
+                                                    const double* __restrict__ svc, int nsv, int dp,
+                                                    const T* __restrict__ Xb, int64_t ldb, int d, int64_t nb,
+                                                    KernelParams<T> kp, int slice, double* __restrict__ partial) {
+  using CK = Chunk<T>;
+  using V = typename CK::V;
+  extern __shared__ __align__(16) unsigned char smem_mv[];
+  const int nch = dp / CK::N;
+  V* qs = reinterpret_cast<V*>(smem_mv);            // [nch][TQ]
+  V* ts = qs + (size_t)nch * TQ;                     // [MV_TS][nch]
+  T* tn = reinterpret_cast<T*>(ts + (size_t)MV_TS * nch);
+  double* tc = reinterpret_cast<double*>(tn + MV_TS + (MV_TS & 1));
+  const int tid = threadIdx.x;
+  const int64_t q0 = (int64_t)blockIdx.x * TQ;
+  // stage the query tile (arbitrary d / ldb: scalar, bounds-checked, zero padded)
+  T* qs_s = reinterpret_cast<T*>(qs);
+  for (int e = tid; e < TQ * dp; e += TQ) {
+    const int qq = e / dp, c = e - qq * dp;
+    const int64_t q = q0 + qq;
+    const T v = (q < nb && c < d) ? Xb[q * ldb + c] : T(0);
+    qs_s[((size_t)(c / CK::N) * TQ + qq) * CK::N + (c % CK::N)] = v;
+  }
+  __syncthreads();
+  T nq = 0;
+  for (int c = 0; c < nch; ++c) nq = CK::dot(qs[(size_t)c * TQ + tid], qs[(size_t)c * TQ + tid], nq);
+
+  const int s0 = blockIdx.y * slice;
+  const int s1 = min(nsv, s0 + slice);
+  double sum = 0.0;
+  for (int t0 = s0; t0 < s1; t0 += MV_TS) {
+    __syncthreads();
+    for (int e = tid; e < MV_TS * nch; e += TQ) {
+      const int s = e / nch;
+      ts[e] = (t0 + s < s1) ? reinterpret_cast<const V*>(sv + (size_t)(t0 + s) * dp)[e - s * nch] : CK::zero();
+    }
+    for (int s = tid; s < MV_TS; s += TQ) {
+      tn[s] = (t0 + s < s1) ? svn[t0 + s] : T(0);
+      tc[s] = (t0 + s < s1) ? svc[t0 + s] : 0.0;
+    }
+    __syncthreads();
+    T acc[MV_TS];
+#pragma unroll
+    for (int s = 0; s < MV_TS; ++s) acc[s] = 0;
+    for (int c = 0; c < nch; ++c) {
+      const V vq = qs[(size_t)c * TQ + tid];
+#pragma unroll
+      for (int s = 0; s < MV_TS; ++s) acc[s] = CK::dot(vq, ts[s * nch + c], acc[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < MV_TS; ++s) {
+      if (t0 + s < s1) {
+        const T kv = kernel_value(kp, acc[s], tn[s], nq);
+        sum += tc[s] * (double)kv;
+      }
+    }
+  }
+  const int64_t q = q0 + tid;
+  if (q < nb) partial[(size_t)blockIdx.y * nb + q] = sum;
+}
+
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int ny, int64_t nb, double* __restrict__ out) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nb; q += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int y = 0; y < ny; ++y) s += partial[(size_t)y * nb + q];
+    out[q] = s;
+  }
+}
+
+template <typename T>
+static int matvec_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const T* Xa, int64_t na, int64_t lda,
+                    const T* Xb, int64_t nb, int64_t ldb, const double* coef, double* out) {
+  using CK = Chunk<T>;
+  if (na >= (1ll << 31)) return fail(B2SVM_E_UNSUPPORTED, "too many rows");
+  const int dp = (d + CK::N - 1) / CK::N * CK::N;
+  int* idx = nullptr;
+  int* count_dev = nullptr;
+  B2_CUDA(cudaMalloc(&idx, sizeof(int) * (size_t)na));
+  B2_CUDA(cudaMalloc(&count_dev, sizeof(int)));
+  compact_nonzero_kernel<<<1, 1024, 0, stream>>>(coef, na, idx, count_dev);
+  int nsv = 0;
+  B2_CUDA(cudaMemcpyAsync(&nsv, count_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  B2_CUDA(cudaStreamSynchronize(stream));
+  int rc = B2SVM_OK;
+  T *sv = nullptr, *svn = nullptr;
+  double *svc = nullptr, *partial = nullptr;
+  auto done = [&](int code) {
+    cudaFree(idx); cudaFree(count_dev); cudaFree(sv); cudaFree(svn); cudaFree(svc); cudaFree(partial);
+    return code;
+  };
+  if (nsv == 0) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * (size_t)nb, stream);
+    return done(e == cudaSuccess ? B2SVM_OK : fail(B2SVM_E_CUDA, cudaGetErrorString(e)));
+  }
+#define MV_TRY(expr)                                                                     \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) return done(fail(B2SVM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
+  } while (0)
+  MV_TRY(cudaMalloc(&sv, sizeof(T) * (size_t)nsv * dp));
+  MV_TRY(cudaMalloc(&svn, sizeof(T) * (size_t)nsv));
+  MV_TRY(cudaMalloc(&svc, sizeof(double) * (size_t)nsv));
+  {
+    int g = (int)std::min<int64_t>(148 * 8, ((int64_t)nsv * 32 + 255) / 256);
+    gather_rows_kernel<T><<<std::max(g, 1), 256, 0, stream>>>(Xa, lda, d, dp, idx, nsv, coef, sv, svn, svc);
+    MV_TRY(cudaGetLastError());
+  }
+  KernelParams<T> kp{k.kind, (T)k.gamma, (T)k.coef0, (T)k.degree};
+  const int nch = dp / CK::N;
+  int TQ = 128;
+  auto smem_for = [&](int tq) {
+    return (size_t)nch * tq * 16 + (size_t)MV_TS * nch * 16 + sizeof(T) * (MV_TS + 1) + sizeof(double) * MV_TS + 32;
+  };
+  while (TQ > 32 && smem_for(TQ) > 160 * 1024) TQ /= 2;
+  if (smem_for(TQ) > 200 * 1024) return done(fail(B2SVM_E_UNSUPPORTED, "n_features too large for kernel_matvec"));
+  const int gx = (int)((nb + TQ - 1) / TQ);
+  const int tiles = (nsv + MV_TS - 1) / MV_TS;
+  int ny = std::max(1, std::min(tiles, (2 * 148 + gx - 1) / gx));
+  ny = std::min(ny, 65535);
+  const int slice = ((tiles + ny - 1) / ny) * MV_TS;
+  ny = (nsv + slice - 1) / slice;
+  MV_TRY(cudaMalloc(&partial, sizeof(double) * (size_t)ny * nb));
+  const size_t smem = smem_for(TQ);
+  dim3 grid(gx, ny);
+#define MV_LAUNCH(TQV)                                                                                     \
+  do {                                                                                                     \
+    MV_TRY(cudaFuncSetAttribute(matvec_kernel<T, TQV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    matvec_kernel<T, TQV><<<grid, TQV, smem, stream>>>(sv, svn, svc, nsv, dp, Xb, ldb, d, nb, kp, slice, partial); \
+  } while (0)
+  if (TQ == 128) MV_LAUNCH(128);
+  else if (TQ == 64) MV_LAUNCH(64);
+  else MV_LAUNCH(32);
+  MV_TRY(cudaGetLastError());
+  {
+    int g = (int)std::min<int64_t>(148 * 8, (nb + 255) / 256);
+    reduce_partials_kernel<<<std::max(g, 1), 256, 0, stream>>>(partial, ny, nb, out);
+    MV_TRY(cudaGetLastError());
+  }
+  MV_TRY(cudaStreamSynchronize(stream));
+#undef MV_LAUNCH
+#undef MV_TRY
+  (void)rc;
+  return done(B2SVM_OK);
+}
+
+int kernel_matvec_impl(cudaStream_t stream, const b2svm_kernel_desc& k, int x_dtype, int d, const void* Xa,
+                       int64_t na, int64_t lda, const void* Xb, int64_t nb, int64_t ldb, const double* coef,
+                       double* out) {
+  if (nb <= 0 || na <= 0) return B2SVM_OK;
+  if (x_dtype == B2SVM_F64)
+    return matvec_T<double>(stream, k, d, (const double*)Xa, na, lda, (const double*)Xb, nb, ldb, coef, out);
+  return matvec_T<float>(stream, k, d, (const float*)Xa, na, lda, (const float*)Xb, nb, ldb, coef, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// random Fourier features (rff.py:19-20): float64 like the reference (W, b are float64 there, so
+// X is promoted before the product).  Block: 16 rows x 64 features.
+// ------------------------------------------------------------------------------------------
+constexpr int RF_ROWS = 16, RF_COLS = 64;
+
+template <typename T, bool DECISION>
+__global__ void __launch_bounds__(RF_COLS * 4) rff_kernel(const T* __restrict__ X, int64_t n, int64_t ldx, int d,
+                                                         const double* __restrict__ W, const double* __restrict__ b,
+                                                         int D, const double* __restrict__ wz,
+                                                         double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_rf[];
+  double* xs = reinterpret_cast<double*>(smem_rf);   // [RF_ROWS][d]
+  double* ws = xs + (size_t)RF_ROWS * d;             // [RF_COLS][d + 1]
+  double* red = ws + (size_t)RF_COLS * (d + 1);      // [RF_ROWS][RF_COLS] (decision only)
+  const int tx = threadIdx.x % RF_COLS;              // feature within tile
+  const int ty = threadIdx.x / RF_COLS;              // 0..3 -> rows ty*4 .. ty*4+3
+  const int64_t r0 = (int64_t)blockIdx.x * RF_ROWS;
+  for (int e = threadIdx.x; e < RF_ROWS * d; e += blockDim.x) {
+    const int rr = e / d, c = e - rr * d;
+    xs[e] = (r0 + rr < n) ? (double)X[(r0 + rr) * ldx + c] : 0.0;
+  }
+  const double scale = sqrt(2.0 / (double)D);
+  double dsum[4] = {0, 0, 0, 0};
+  const int k_begin = DECISION ? 0 : blockIdx.y * RF_COLS;
+  const int k_end = DECISION ? D : min(D, k_begin + RF_COLS);
+  for (int k0 = k_begin; k0 < k_end; k0 += RF_COLS) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < RF_COLS * d; e += blockDim.x) {
+      const int kk = e / d, c = e - kk * d;
+      ws[kk * (d + 1) + c] = (k0 + kk < D) ? W[(size_t)(k0 + kk) * d + c] : 0.0;
+    }
+    __syncthreads();
+    const int k = k0 + tx;
+    double acc[4] = {0, 0, 0, 0};
+    for (int c = 0; c < d; ++c) {
+      const double w = ws[tx * (d + 1) + c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fma(xs[(ty * 4 + r) * d + c], w, acc[r]);
+    }
+    if (k < D) {
+      const double bk = b[k];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double z = scale * cos(acc[r] + bk);
+        if (DECISION) dsum[r] += z * wz[k];
+        else if (r0 + ty * 4 + r < n) out[(size_t)(r0 + ty * 4 + r) * D + k] = z;
+      }
+    }
+  }
+  if (DECISION) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) red[(ty * 4 + r) * RF_COLS + tx] = dsum[r];
+    __syncthreads();
+    if (threadIdx.x < RF_ROWS) {
+      double s = 0.0;
+      for (int c = 0; c < RF_COLS; ++c) s += red[threadIdx.x * RF_COLS + c];
+      if (r0 + threadIdx.x < n) out[r0 + threadIdx.x] = s;
+    }
+  }
+}
+
+template <bool DECISION>
+static int rff_launch(int device, void* stream_, int x_dtype, const void* X, int64_t n, int64_t ldx, int d,
+                      const double* W, const double* b, int D, const double* wz, double* out) {
+  if (n <= 0 || D <= 0 || d <= 0) return fail(B2SVM_E_INVALID, "empty RFF problem");
+  B2_CUDA(cudaSetDevice(device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t smem = sizeof(double) * ((size_t)RF_ROWS * d + (size_t)RF_COLS * (d + 1) + (size_t)RF_ROWS * RF_COLS);
+  if (smem > 200 * 1024) return fail(B2SVM_E_UNSUPPORTED, "n_features too large for the RFF kernel");
+  dim3 grid((unsigned)((n + RF_ROWS - 1) / RF_ROWS), DECISION ? 1u : (unsigned)((D + RF_COLS - 1) / RF_COLS));
+  if (x_dtype == B2SVM_F64) {
+    B2_CUDA(cudaFuncSetAttribute(rff_kernel<double, DECISION>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rff_kernel<double, DECISION><<<grid, RF_COLS * 4, smem, stream>>>((const double*)X, n, ldx, d, W, b, D, wz, out);
+  } else {
+    B2_CUDA(cudaFuncSetAttribute(rff_kernel<float, DECISION>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rff_kernel<float, DECISION><<<grid, RF_COLS * 4, smem, stream>>>((const float*)X, n, ldx, d, W, b, D, wz, out);
+  }
+  B2_CUDA(cudaGetLastError());
+  return B2SVM_OK;
+}
+
+}  // namespace b2svm
+
+using namespace b2svm;
+
+extern "C" {
+
+int b2svm_kernel_matvec(int32_t device, void* stream, const b2svm_kernel_desc* k, int32_t x_dtype, int32_t n_features,
+                        const void* Xa, int64_t na, int64_t lda, const void* Xb, int64_t nb, int64_t ldb,
+                        const double* coef, double* out) {
+  if (!k || !Xa || !Xb || !coef || !out) return fail(B2SVM_E_INVALID, "null argument");
+  if (x_dtype != B2SVM_F32 && x_dtype != B2SVM_F64) return fail(B2SVM_E_INVALID, "bad x_dtype");
+  if (n_features <= 0 || lda < n_features || ldb < n_features) return fail(B2SVM_E_INVALID, "bad leading dimension");
+  B2_CUDA(cudaSetDevice(device));
+  return kernel_matvec_impl((cudaStream_t)stream, *k, x_dtype, n_features, Xa, na, lda, Xb, nb, ldb, coef, out);
+}
+
+int b2svm_rff_transform(int32_t device, void* stream, int32_t x_dtype, const void* X, int64_t n, int64_t ldx, int32_t d,
+                        const double* W, const double* b, int32_t D, double* out) {
+  if (!X || !W || !b || !out) return fail(B2SVM_E_INVALID, "null argument");
+  return rff_launch<false>(device, stream, x_dtype, X, n, ldx, d, W, b, D, nullptr, out);
+}
+
+int b2svm_rff_decision(int32_t device, void* stream, int32_t x_dtype, const void* Xq, int64_t nq, int64_t ldx, int32_t d,
+                       const double* W, const double* b, int32_t D, const double* wz, double* out) {
+  if (!Xq || !W || !b || !wz || !out) return fail(B2SVM_E_INVALID, "null argument");
+  return rff_launch<true>(device, stream, x_dtype, Xq, nq, ldx, d, W, b, D, wz, out);
+}
+
+}  // extern "C"

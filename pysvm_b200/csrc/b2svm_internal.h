@@ -1,0 +1,30 @@
+// Host-side internals shared by the translation units of libb2svm.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/b2svm.h"
+
+namespace b2svm {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define B2_CUDA(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return ::b2svm::fail(B2SVM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// number of 16-byte chunks per padded row for (dtype, d); 0 when d exceeds the compiled maximum
+int chunks_for(int x_dtype, int d);
+
+// dense kernel mat-vec (b2svm_dense.cu): out[q] = sum_s coef[s] K(Xa[s], Xb[q])
+int kernel_matvec_impl(cudaStream_t stream, const b2svm_kernel_desc& k, int x_dtype, int d, const void* Xa,
+                       int64_t na, int64_t lda, const void* Xb, int64_t nb, int64_t ldb, const double* coef,
+                       double* out);
+
+}  // namespace b2svm

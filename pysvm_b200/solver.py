@@ -1,0 +1,363 @@
+"""Host-side mirror of ``pysvm/solver.py``: the four solver classes with the reference's
+constructor / method names, backed by the C-ABI library (``include/b2svm.h``).
+
+Differences a PySVM user sees (all additive):
+
+* ``alpha`` / ``neg_y_grad`` are float64 CUDA tensors (the reference holds NumPy arrays); assigning
+  to them copies into the device buffers (OneClassSVM does that, reference ``oc_svm.py:88-95``).
+* ``func`` -- the Q-column callback -- must be a :class:`QColumns` object (it carries X, y and the
+  kernel to the device); an arbitrary Python callable cannot run on the GPU and is rejected.  It can
+  be given at construction (``func=``) or with the first ``update`` / ``solve`` call.
+* ``solve(max_iter)`` runs the estimator's whole ``for n_iter in range(max_iter)`` loop in one
+  persistent kernel (``b2svm_solve``); ``working_set_select`` / ``update`` remain for step-wise use
+  and go through the same device code.
+* The LRU of 256 columns (``solver.py:207,227-229``) is numerically transparent and is not
+  reproduced; ``cache_size`` is accepted for signature compatibility.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+@dataclass
+class KernelSpec:
+    """Resolved kernel (reference ``register_kernel``, svc.py:210-241)."""
+    kind: str = "rbf"
+    gamma: float = 1.0
+    coef0: float = 0.0
+    degree: float = 3.0
+
+    def desc(self) -> N.KernelDesc:
+        return N.KernelDesc(N.KERNEL_IDS[self.kind], 0, float(self.gamma), float(self.coef0), float(self.degree))
+
+
+def default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("pysvm_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _dev_f64(a, device) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+
+
+def to_device_matrix(X, device) -> torch.Tensor:
+    """X as a contiguous float32/float64 CUDA matrix; the dtype of a float input is kept because the
+    reference evaluates kernels in X's dtype."""
+    if isinstance(X, torch.Tensor):
+        t = X
+    else:
+        X = np.asarray(X)
+        if X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(X))
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    return t.to(device).contiguous()
+
+
+class QColumns:
+    """The reference's ``func(i)`` closure (svc.py:257-258, svr.py:174-179, oc_svm.py:72-73) as an
+    object: Q[:, i] = y * K(X, x_{i mod l}) * y_i evaluated on the device."""
+
+    def __init__(self, X, y, kernel: KernelSpec, mirror: bool = False, device=None):
+        self.device = torch.device(device) if device is not None else default_device()
+        self.X = to_device_matrix(X, self.device)
+        self.y = _dev_f64(y, self.device)
+        self.kernel = kernel
+        self.mirror = bool(mirror)
+        l = self.X.shape[0]
+        if self.y.shape[0] != (2 * l if mirror else l):
+            raise ValueError("y must have n_rows entries (2*n_rows in mirror mode)")
+        self._engine = None
+
+    def __call__(self, i: int) -> torch.Tensor:
+        if self._engine is None:
+            raise RuntimeError("QColumns is not bound to a solver yet")
+        return self._engine.column(int(i))
+
+
+class _Engine:
+    """Owns one b2svm handle; keeps every tensor the handle points at alive."""
+
+    def __init__(self, func: QColumns, alpha: torch.Tensor, g: torch.Tensor, Cbox: float, tol: float, variant: int,
+                 max_ctas: int = 0):
+        self.lib = N.load()
+        self.func = func
+        self.alpha, self.g = alpha, g
+        X = func.X
+        d = N.ProblemDesc()
+        d.struct_bytes = C.sizeof(N.ProblemDesc)
+        d.device = func.device.index if func.device.index is not None else torch.cuda.current_device()
+        d.stream = None
+        d.n_rows, d.n_features = X.shape[0], X.shape[1]
+        d.x_dtype = N.F64 if X.dtype == torch.float64 else N.F32
+        d.X = X.data_ptr()
+        d.ldx = X.stride(0)
+        d.n_vars = func.y.shape[0]
+        d.variant = variant
+        d.y = func.y.data_ptr()
+        d.alpha = alpha.data_ptr()
+        d.neg_y_grad = g.data_ptr()
+        d.C, d.tol = float(Cbox), float(tol)
+        d.kernel = func.kernel.desc()
+        d.cache_bytes = 0
+        d.max_ctas = max_ctas
+        d.rank, d.world = 0, 1
+        d.row_offset, d.n_rows_global = 0, X.shape[0]
+        self.desc = d
+        h = C.c_void_p()
+        torch.cuda.synchronize(func.device)          # handle work runs on the legacy default stream
+        N.check(self.lib.b2svm_create(C.byref(d), C.byref(h)))
+        self.h = h
+        func._engine = self
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b2svm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- thin wrappers -----------------------------------------------------------------------
+    def init_state(self, p: torch.Tensor):
+        N.check(self.lib.b2svm_init_state(self.h, p.data_ptr()))
+
+    def init_gradient(self, p: Optional[torch.Tensor]):
+        N.check(self.lib.b2svm_init_gradient(self.h, p.data_ptr() if p is not None else None))
+
+    def select(self):
+        i, j = C.c_int64(), C.c_int64()
+        N.check(self.lib.b2svm_select(self.h, C.byref(i), C.byref(j)))
+        return int(i.value), int(j.value)
+
+    def update(self, i: int, j: int):
+        di, dj = C.c_double(), C.c_double()
+        N.check(self.lib.b2svm_update(self.h, int(i), int(j), C.byref(di), C.byref(dj)))
+        return di.value, dj.value
+
+    def column(self, i: int) -> torch.Tensor:
+        out = torch.empty(self.func.y.shape[0], dtype=torch.float64, device=self.func.device)
+        N.check(self.lib.b2svm_kernel_column(self.h, int(i), out.data_ptr()))
+        return out
+
+    def solve(self, max_iter: int) -> N.SolveStats:
+        st = N.SolveStats()
+        N.check(self.lib.b2svm_solve(self.h, int(max_iter), C.byref(st)))
+        return st
+
+    def rho(self) -> float:
+        r = C.c_double()
+        N.check(self.lib.b2svm_rho(self.h, C.byref(r)))
+        return r.value
+
+    def rho_b(self):
+        r, b = C.c_double(), C.c_double()
+        N.check(self.lib.b2svm_rho_b(self.h, C.byref(r), C.byref(b)))
+        return r.value, b.value
+
+
+class Solver:
+    r"""SMO on  min ½ αᵀQα + pᵀα  s.t. yᵀα = 0, 0 ≤ α ≤ C  (reference ``Solver``, solver.py:5-184).
+
+    ``Q`` must be ``None``: columns come from ``func`` (a :class:`QColumns`).  The dense-Q mode of the
+    reference (``cache_size == 0``) is not built yet.
+    """
+    _variant = N.SOLVER_C
+
+    def __init__(self, Q, p, y, C: float, tol: float = 1e-5, func: Optional[QColumns] = None, device=None):
+        if Q is not None:
+            raise NotImplementedError("dense-Q mode (cache_size == 0) is not built; pass Q=None and a QColumns func")
+        self.device = (func.device if func is not None else
+                       (torch.device(device) if device is not None else default_device()))
+        self.Q = None
+        self.p = _dev_f64(p, self.device)
+        self.y = func.y if func is not None else _dev_f64(y, self.device)
+        n = self.p.shape[0]
+        assert n == self.y.shape[0]
+        self.C = C
+        self.tol = tol
+        self._alpha = torch.zeros(n, dtype=torch.float64, device=self.device)
+        self._g = torch.empty(n, dtype=torch.float64, device=self.device)
+        self._engine: Optional[_Engine] = None
+        self._state_ready = False
+        self.last_stats: Optional[N.SolveStats] = None
+        if func is not None:
+            self.bind(func)
+
+    # -- binding to device data ---------------------------------------------------------------
+    def bind(self, func: QColumns):
+        if self._engine is not None:
+            if func is not None and func is not self._engine.func:
+                raise ValueError("this solver is already bound to another QColumns object")
+            return self._engine
+        if not isinstance(func, QColumns):
+            raise TypeError("func must be a pysvm_b200.solver.QColumns (an arbitrary Python callable cannot "
+                            "run on the GPU; there is no CPU fallback)")
+        self.y = func.y
+        self._engine = _Engine(func, self._alpha, self._g, self.C, self.tol, self._variant)
+        self._init_state()
+        return self._engine
+
+    def _init_state(self):
+        # Solver.__init__: alpha = 0, neg_y_grad = -y * p (solver.py:42-45)
+        self._engine.init_state(self.p)
+        self._state_ready = True
+
+    def _need(self, func=None) -> _Engine:
+        if self._engine is None:
+            if func is None:
+                raise RuntimeError("solver is not bound: pass func=QColumns(...) at construction or call bind()")
+            self.bind(func)
+        return self._engine
+
+    # -- state ------------------------------------------------------------------------------------
+    @property
+    def alpha(self) -> torch.Tensor:
+        return self._alpha
+
+    @alpha.setter
+    def alpha(self, value):
+        self._alpha.copy_(_dev_f64(value, self.device))
+
+    @property
+    def neg_y_grad(self) -> torch.Tensor:
+        self._need()
+        return self._g
+
+    @neg_y_grad.setter
+    def neg_y_grad(self, value):
+        self._g.copy_(_dev_f64(value, self.device))
+
+    # -- the reference's methods --------------------------------------------------------------------
+    def working_set_select(self):
+        """solver.py:47-75."""
+        return self._need().select()
+
+    def update(self, i: int, j: int, func=None):
+        """solver.py:77-147."""
+        return self._need(func).update(i, j)
+
+    def calculate_rho(self) -> float:
+        """solver.py:149-177."""
+        return self._need().rho()
+
+    def get_Q(self, i: int, func=None) -> torch.Tensor:
+        """solver.py:179-184 / 227-229."""
+        return self._need(func).column(i)
+
+    # -- fused driver loop ----------------------------------------------------------------------------
+    def solve(self, max_iter: int, func=None) -> N.SolveStats:
+        """The estimator loop ``for n_iter in range(max_iter): select; break if i < 0; update``
+        (svc.py:260-267) on the device.  ``stats.n_iter`` = number of updates made."""
+        st = self._need(func).solve(max_iter)
+        self.last_stats = st
+        return st
+
+
+class SolverWithCache(Solver):
+    """Reference ``SolverWithCache(p, y, C, tol, cache_size)`` (solver.py:187-229)."""
+    cache_size = 256
+
+    def __init__(self, p, y, C: float, tol: float = 1e-5, cache_size: int = 256, func: Optional[QColumns] = None,
+                 device=None):
+        super().__init__(None, p, y, C, tol, func=func, device=device)
+
+
+def nu_initial_alpha(y: np.ndarray, t: float) -> np.ndarray:
+    """Vectorised form of the sequential fill in solver.py:269-278: per class, in index order, each
+    variable receives min(1., what is left of t/2).  The running remainder after k unit steps is
+    t/2 - k exactly, so alpha_k = clip(t/2 - rank_k, 0, 1)."""
+    y = np.asarray(y)
+    alpha = np.zeros(y.shape[0])
+    for cls in (y == 1, y != 1):
+        rank = np.cumsum(cls) - 1
+        alpha[cls] = np.clip(t / 2 - rank[cls], 0.0, 1.0)
+    return alpha
+
+
+class NuSolver(Solver):
+    r"""ν-variant with the extra constraint eᵀα = t (reference ``NuSolver``, solver.py:232-419)."""
+    _variant = N.SOLVER_NU
+
+    def __init__(self, Q, p, y, t: float, C: float, tol: float = 1e-5, func: Optional[QColumns] = None, device=None):
+        self.t = t
+        self._y_host = np.asarray(y.detach().cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64)
+        super().__init__(Q, p, y, C, tol, func=func, device=device)
+
+    def _init_state(self):
+        # solver.py:269-281 / 456-473: alpha fill, then neg_y_grad = -y * (Q alpha + p)
+        self._alpha.copy_(torch.from_numpy(nu_initial_alpha(self._y_host, self.t)))
+        self._engine.init_gradient(self.p)
+        self._state_ready = True
+
+    def working_set_select(self, func=None):
+        """solver.py:283-339.  Returns (i, j, Qi, Qj) like the reference; the columns are produced on
+        demand (``update`` does not need them -- it recomputes the three kernel values it uses)."""
+        eng = self._need(func)
+        i, j = eng.select()
+        if i < 0:
+            return -1, -1, -1, -1
+        return i, j, _LazyColumn(eng, i), _LazyColumn(eng, j)
+
+    def update(self, i: int, j: int, Qi=None, Qj=None):
+        """solver.py:341-376."""
+        return self._need().update(i, j)
+
+    def calculate_rho_b(self):
+        """solver.py:378-419."""
+        return self._need().rho_b()
+
+
+class NuSolverWithCache(NuSolver):
+    """Reference ``NuSolverWithCache(p, y, t, C, func, tol, cache_size)`` (solver.py:422-486)."""
+    cache_size = 256
+
+    def __init__(self, p, y, t: float, C: float, func: QColumns, tol: float = 1e-5, cache_size: int = 256):
+        super().__init__(None, p, y, t, C, tol, func=func)
+
+
+class _LazyColumn:
+    def __init__(self, engine: _Engine, i: int):
+        self._engine, self._i, self._t = engine, i, None
+
+    def tensor(self) -> torch.Tensor:
+        if self._t is None:
+            self._t = self._engine.column(self._i)
+        return self._t
+
+    def __getitem__(self, k):
+        return self.tensor()[k]
+
+    def __array__(self, dtype=None):
+        a = self.tensor().cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+
+def kernel_matvec(kernel: KernelSpec, Xa: torch.Tensor, coef: torch.Tensor, Xb: torch.Tensor) -> torch.Tensor:
+    """out[q] = sum_s coef[s] K(Xa[s], Xb[q]) as float64 (b2svm_kernel_matvec)."""
+    lib = N.load()
+    assert Xa.dtype == Xb.dtype and Xa.shape[1] == Xb.shape[1]
+    Xa, Xb = Xa.contiguous(), Xb.contiguous()
+    coef = coef.to(dtype=torch.float64).contiguous()
+    out = torch.empty(Xb.shape[0], dtype=torch.float64, device=Xa.device)
+    kd = kernel.desc()
+    torch.cuda.synchronize(Xa.device)
+    N.check(lib.b2svm_kernel_matvec(Xa.device.index or 0, None, C.byref(kd),
+                                    N.F64 if Xa.dtype == torch.float64 else N.F32, Xa.shape[1],
+                                    Xa.data_ptr(), Xa.shape[0], Xa.stride(0), Xb.data_ptr(), Xb.shape[0], Xb.stride(0),
+                                    coef.data_ptr(), out.data_ptr()))
+    return out

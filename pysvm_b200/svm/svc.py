@@ -1,0 +1,249 @@
+"""Classification estimators with PySVM's API (reference ``pysvm/svm/svc.py``), solved on the GPU."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from sklearn.base import BaseEstimator
+from sklearn.metrics import accuracy_score
+from sklearn.multiclass import OneVsOneClassifier, OneVsRestClassifier
+
+from ..rff import NormalRFF, rff_decision_device
+from ..solver import (KernelSpec, NuSolverWithCache, QColumns, SolverWithCache, default_device, kernel_matvec,
+                      to_device_matrix)
+
+
+class _Fitted:
+    """What the reference keeps alive inside the ``decision_function`` closure."""
+
+    def __init__(self, solver, func, spec, coef, rff=None, X_raw=None):
+        self.solver, self.func, self.spec, self.coef, self.rff, self.X_raw = solver, func, spec, coef, rff, X_raw
+        self._wz = None
+
+    def kernel_sum(self, x) -> np.ndarray:
+        """coef . K(X_train, x) as float64 NumPy (svc.py:269-272 without the n x m matrix)."""
+        dev = self.func.device
+        if self.rff is not None:
+            # K(a, b) = z(a).z(b)  =>  coef.K(X, x) = z(x).(Z^T coef)
+            Xq = to_device_matrix(np.array(x), dev).to(self.X_raw.dtype)
+            if self._wz is None:
+                self._wz = self.func.X.t().contiguous() @ self.coef
+            w, b = self.rff._device_params(dev)
+            return rff_decision_device(Xq, w, b, self._wz).cpu().numpy()
+        Xq = to_device_matrix(np.array(x), dev).to(self.func.X.dtype)
+        return kernel_matvec(self.spec, self.func.X, self.coef, Xq).cpu().numpy()
+
+
+class BiLinearSVC(BaseEstimator):
+    """Binary linear C-SVC (reference svc.py:10-94): the linear kernel on the same device solver,
+    with the primal weights recovered as w = sum_i alpha_i y_i x_i."""
+
+    def __init__(self, C: float = 1., max_iter: int = 1000, tol: float = 1e-5, cache_size: int = 256) -> None:
+        super().__init__()
+        self.C = C
+        self.max_iter = max_iter
+        self.tol = tol
+        self.cache_size = cache_size
+
+    _name = "LinearSVC"
+
+    def _report(self, stats):
+        self.n_iter_ = int(stats.n_iter)
+        self.solve_stats_ = stats.as_dict()
+        if stats.n_iter >= self.max_iter:      # the for-loop ran out (svc.py:77-79, 265-267)
+            print("{} not coverage with {} iterations".format(self._name, self.max_iter))
+
+    def fit(self, X, y):
+        X, y = np.array(X), np.array(y, dtype=float)
+        y[y != 1] = -1
+        l, self.n_features = X.shape
+        p = -np.ones(l)
+        func = QColumns(X, y, KernelSpec("linear"))
+        solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func)
+        self._report(solver.solve(self.max_iter))
+        # svc.py:76 accumulates w += delta_i y_i x_i + delta_j y_j x_j; the sum telescopes to X^T (alpha*y)
+        w = (func.X.to(torch.float64).t() @ (solver.alpha * func.y)).cpu().numpy()
+        self.coef_ = (w, solver.calculate_rho())
+        self._fitted = _Fitted(solver, func, func.kernel, solver.alpha * func.y)
+        return self
+
+    def decision_function(self, X) -> np.ndarray:
+        return np.matmul(self.coef_[0], np.array(X).T) - self.coef_[-1]
+
+    def predict(self, X) -> np.ndarray:
+        return (self.decision_function(np.array(X)) >= 0).astype(int)
+
+    def score(self, X, y) -> float:
+        return accuracy_score(y, self.predict(X))
+
+
+class LinearSVC(BiLinearSVC):
+    """Multiclass wrapper (svc.py:97-158).  ``n_jobs`` is accepted but sub-problems are not farmed
+    out to worker processes: they run on the GPU of this process."""
+
+    def __init__(self, C: float = 1., max_iter: int = 1000, tol: float = 1e-5, cache_size: int = 256,
+                 multiclass: str = "ovr", n_jobs=None) -> None:
+        super().__init__(C, max_iter, tol, cache_size)
+        self.multiclass = multiclass
+        self.n_jobs = n_jobs
+        params = {"estimator": BiLinearSVC(C, max_iter, tol, cache_size), "n_jobs": None}
+        self.multiclass_model = {"ovo": OneVsOneClassifier(**params), "ovr": OneVsRestClassifier(**params)}[multiclass]
+
+    def fit(self, X, y):
+        self.multiclass_model.fit(X, y)
+        return self
+
+    def decision_function(self, X):
+        return self.multiclass_model.decision_function(X)
+
+    def predict(self, X):
+        return self.multiclass_model.predict(X)
+
+    def score(self, X, y):
+        return self.multiclass_model.score(X, y)
+
+
+class BiKernelSVC(BiLinearSVC):
+    """Binary kernel C-SVC (svc.py:161-279)."""
+    _name = "KernelSVC"
+
+    def __init__(self, C: float = 1., kernel: str = 'rbf', degree: float = 3, gamma: str = 'scale', coef0: float = 0,
+                 max_iter: int = 1000, rff: bool = False, D: int = 1000, tol: float = 1e-5,
+                 cache_size: int = 256) -> None:
+        super().__init__(C, max_iter, tol, cache_size)
+        self.kernel = kernel
+        self.gamma = gamma
+        self.degree = degree
+        self.coef0 = coef0
+        self.rff = rff
+        self.D = D
+
+    def register_kernel(self, std: float):
+        """svc.py:210-241.  Returns (KernelSpec, NormalRFF or None).  With ``rff=True`` the RBF kernel
+        is replaced by z(a).z(b): the features are computed once and the solver runs a linear kernel on
+        them (the reference recomputes both transforms in every kernel call)."""
+        if type(self.gamma) == str:
+            gamma = {'scale': 1 / (self.n_features * std), 'auto': 1 / self.n_features}[self.gamma]
+        else:
+            gamma = self.gamma
+        rff = None
+        if self.rff:          # drawn whatever the kernel is, exactly like the reference (svc.py:225-226)
+            rff = NormalRFF(gamma, self.D).fit(np.ones((1, self.n_features)))
+        self.gamma_ = gamma
+        spec = KernelSpec(self.kernel, gamma, self.coef0, self.degree)
+        if self.kernel not in ("linear", "poly", "rbf", "sigmoid"):
+            raise KeyError(self.kernel)
+        return spec, (rff if self.kernel == "rbf" else None)
+
+    def _columns(self, X, y, mirror=False):
+        """Device Q-column source for this estimator's kernel (the reference's ``func``)."""
+        spec, rff = self.register_kernel(X.std())
+        if rff is not None:
+            Z = rff.transform_device(to_device_matrix(X, default_device()))
+            return QColumns(Z, y, KernelSpec("linear"), mirror=mirror), spec, rff
+        return QColumns(X, y, spec, mirror=mirror), spec, None
+
+    def fit(self, X, y):
+        X, y = np.array(X), np.array(y, dtype=float)
+        y[y != 1] = -1
+        l, self.n_features = X.shape
+        p = -np.ones(l)
+        func, spec, rff = self._columns(X, y)
+        solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func)
+        self._report(solver.solve(self.max_iter))
+        self._finish(solver, func, spec, rff, X, solver.alpha * func.y)
+        return self
+
+    def _finish(self, solver, func, spec, rff, X, coef):
+        self._fitted = _Fitted(solver, func, func.kernel, coef, rff=rff,
+                               X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None)
+        self.rho_ = solver.calculate_rho()
+        a = solver.alpha.cpu().numpy()
+        self.alpha_ = a
+        self.support_ = np.flatnonzero(a > 0)
+
+    def decision_function(self, x) -> np.ndarray:
+        return self._fitted.kernel_sum(x) - self._fitted.solver.calculate_rho()
+
+    def predict(self, X) -> np.ndarray:
+        return super().predict(X)
+
+    def score(self, X, y) -> float:
+        return super().score(X, y)
+
+
+class KernelSVC(LinearSVC, BiKernelSVC):
+    """Multiclass kernel C-SVC (svc.py:282-354): sklearn's OvO / OvR wrappers around BiKernelSVC."""
+
+    def __init__(self, C: float = 1., kernel: str = 'rbf', degree: float = 3, gamma: float = 'scale',
+                 coef0: float = 0., max_iter: int = 1000, rff: bool = False, D: int = 1000, tol: float = 1e-5,
+                 cache_size: int = 256, multiclass: str = "ovr", n_jobs: int = None) -> None:
+        LinearSVC.__init__(self, C, max_iter, tol, cache_size, multiclass, n_jobs)
+        self.kernel = kernel
+        self.gamma = gamma
+        self.degree = degree
+        self.coef0 = coef0
+        self.rff = rff
+        self.D = D
+        params = {"estimator": BiKernelSVC(C, kernel, degree, gamma, coef0, max_iter, rff, D, tol, cache_size),
+                  "n_jobs": None}
+        self.multiclass_model = {"ovo": OneVsOneClassifier(**params), "ovr": OneVsRestClassifier(**params)}[multiclass]
+
+    def fit(self, X, y):
+        return LinearSVC.fit(self, X, y)
+
+    def decision_function(self, X):
+        return LinearSVC.decision_function(self, X)
+
+    def predict(self, X):
+        return LinearSVC.predict(self, X)
+
+    def score(self, X, y):
+        return LinearSVC.score(self, X, y)
+
+
+class BiNuSVC(BiKernelSVC):
+    """Binary nu-SVC (svc.py:357-446): p = 0, C = 1, e'alpha = nu*l."""
+    _name = "NuSVC"
+
+    def __init__(self, nu: float = 0.5, kernel: str = 'rbf', degree: float = 3, gamma: float = 'scale',
+                 coef0: float = 0., max_iter: int = 1000, rff: bool = False, D: int = 1000, tol: float = 1e-5,
+                 cache_size: int = 256) -> None:
+        super().__init__(1, kernel, degree, gamma, coef0, max_iter, rff, D, tol, cache_size)
+        self.nu = nu
+
+    def fit(self, X, y):
+        X, y = np.array(X), np.array(y, dtype=float)
+        y[y != 1] = -1
+        l, self.n_features = X.shape
+        p = np.zeros(l)
+        func, spec, rff = self._columns(X, y)
+        solver = NuSolverWithCache(p, y, self.nu * l, self.C, func, self.tol, self.cache_size)
+        self._report(solver.solve(self.max_iter))
+        self._finish(solver, func, spec, rff, X, solver.alpha * func.y)
+        self.rho_, self.b_ = solver.calculate_rho_b()
+        return self
+
+    def decision_function(self, x) -> np.ndarray:
+        rho, b = self.rho_, self.b_
+        return self._fitted.kernel_sum(x) / rho + b / rho
+
+    def _finish(self, solver, func, spec, rff, X, coef):
+        self._fitted = _Fitted(solver, func, func.kernel, coef, rff=rff,
+                               X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None)
+        a = solver.alpha.cpu().numpy()
+        self.alpha_ = a
+        self.support_ = np.flatnonzero(a > 0)
+
+
+class NuSVC(KernelSVC, BiNuSVC):
+    """Multiclass nu-SVC (svc.py:449-514)."""
+
+    def __init__(self, nu: float = 0.5, kernel: str = 'rbf', degree: float = 3, gamma: float = 'scale',
+                 coef0: float = 0., max_iter: int = 1000, rff: bool = False, D: int = 1000, tol: float = 1e-5,
+                 cache_size: int = 256, multiclass: str = "ovr", n_jobs: int = None) -> None:
+        KernelSVC.__init__(self, 1, kernel, degree, gamma, coef0, max_iter, rff, D, tol, cache_size, multiclass,
+                           n_jobs)
+        self.nu = nu
+        params = {"estimator": BiNuSVC(nu, kernel, degree, gamma, coef0, max_iter, rff, D, tol, cache_size),
+                  "n_jobs": None}
+        self.multiclass_model = {"ovo": OneVsOneClassifier(**params), "ovr": OneVsRestClassifier(**params)}[multiclass]

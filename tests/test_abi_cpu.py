@@ -1,0 +1,101 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds/loads without a GPU, exports
+every symbol include/b2svm.h declares, and the host-side logic around it is right."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pysvm_b200 import _native as N
+    from pysvm_b200.build import build
+    build()
+    lib = N.load()
+    header = open(os.path.join(ROOT, "include", "b2svm.h")).read()
+    declared = set(re.findall(r"\b(b2svm_[a-z_]+)\s*\(", header))
+    assert declared == set(N.EXPORTS), declared ^ set(N.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.b2svm_abi_version() == N.ABI_VERSION
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors of the ABI structs: sizes pinned so a header edit cannot drift silently."""
+    from pysvm_b200 import _native as N
+    assert ctypes.sizeof(N.KernelDesc) == 32
+    assert ctypes.sizeof(N.ProblemDesc) == 176
+    assert ctypes.sizeof(N.SolveStats) == 88
+
+
+def test_errors_are_reported_not_swallowed():
+    from pysvm_b200 import _native as N
+    lib = N.load()
+    h = ctypes.c_void_p()
+    rc = lib.b2svm_create(None, ctypes.byref(h))
+    assert rc == -1 and b"null" in lib.b2svm_last_error()
+    d = N.ProblemDesc()
+    d.struct_bytes = 7
+    assert lib.b2svm_create(ctypes.byref(d), ctypes.byref(h)) == -1
+    assert b"size mismatch" in lib.b2svm_last_error()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pysvm_b200.svm.svc import BiKernelSVC
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BiKernelSVC().fit(np.zeros((4, 2)), np.array([0, 1, 0, 1]))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pysvm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("the oracle", ""), os.path.join(dirpath, f)
+
+
+def test_nu_initial_alpha_matches_sequential_fill():
+    from pysvm_b200.solver import nu_initial_alpha
+    from oracle.smo_oracle import nu_fill
+    rng = np.random.default_rng(0)
+    for t in (3.0, 7.5, 284.5, 0.3, 1000.0, 221.0):
+        y = np.where(rng.random(700) < 0.4, 1.0, -1.0)
+        np.testing.assert_array_equal(nu_initial_alpha(y, t), nu_fill(y, t))
+
+
+def test_oneclass_initial_alpha_matches_oracle():
+    from pysvm_b200.svm.oc_svm import oneclass_initial_alpha
+    from oracle.smo_oracle import oneclass_alpha0
+    for nu, l in ((0.1, 200), (0.5, 2000), (0.37, 101), (0.999, 10)):
+        np.testing.assert_array_equal(oneclass_initial_alpha(nu, l), oneclass_alpha0(nu, l))
+    with pytest.raises(UnboundLocalError):
+        oneclass_initial_alpha(0.001, 100)
+
+
+def test_estimator_signatures_match_reference_defaults():
+    """Constructor kwargs and defaults of SURVEY 8(b) surface 1."""
+    import inspect
+    import pysvm_b200 as P
+    sig = lambda c: {k: v.default for k, v in inspect.signature(c.__init__).parameters.items() if k != "self"}
+    assert sig(P.KernelSVC) == dict(C=1., kernel='rbf', degree=3, gamma='scale', coef0=0., max_iter=1000, rff=False,
+                                    D=1000, tol=1e-5, cache_size=256, multiclass='ovr', n_jobs=None)
+    assert sig(P.NuSVC) == dict(nu=0.5, kernel='rbf', degree=3, gamma='scale', coef0=0., max_iter=1000, rff=False,
+                                D=1000, tol=1e-5, cache_size=256, multiclass='ovr', n_jobs=None)
+    assert sig(P.KernelSVR) == dict(C=1., eps=0., kernel='rbf', degree=3, gamma='scale', coef0=0., max_iter=1000,
+                                    rff=False, D=1000, tol=1e-5, cache_size=256)
+    assert sig(P.NuSVR) == dict(C=1., nu=0.5, kernel='rbf', degree=3, gamma='scale', coef0=0., max_iter=1000,
+                                rff=False, D=1000, tol=1e-5, cache_size=256)
+    assert sig(P.OneClassSVM) == dict(nu=0.5, kernel='rbf', degree=3, gamma='scale', coef0=0., max_iter=1000,
+                                      rff=False, D=1000, tol=1e-5, cache_size=256)
+    assert sig(P.LinearSVC) == dict(C=1., max_iter=1000, tol=1e-5, cache_size=256, multiclass='ovr', n_jobs=None)
+    assert sig(P.LinearSVR) == dict(C=1., eps=0., max_iter=1000, tol=1e-5, cache_size=256)
+    from sklearn.base import clone
+    est = clone(P.KernelSVC(C=3., multiclass="ovo"))
+    assert est.C == 3. and est.multiclass == "ovo"

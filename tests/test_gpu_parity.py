@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path (through the C-ABI library) against the oracle and the golden
+vectors of the unmodified reference.  Tolerances (BASELINE.json north_star): identical support
+vector sets and labels, alpha / rho / decision values within 1e-4 relative, iteration counts
+within 1 %.  float64 inputs are evaluated in float64 on the device, so they agree far tighter."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import smo_oracle as O
+
+
+def _mods():
+    import torch
+    import pysvm_b200
+    from pysvm_b200 import solver as S
+    from pysvm_b200.svm import svc, svr, oc_svm
+    return torch, pysvm_b200, S, svc, svr, oc_svm
+
+
+def rel_close(a, b, rtol=1e-4, atol=1e-6):
+    np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol)
+
+
+def iters_close(n, ref, frac=0.01):
+    assert abs(n - ref) <= max(1, frac * ref), (n, ref)
+
+
+# ------------------------------------------------------------------------------ kernel columns
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kind", ["rbf", "linear", "poly", "sigmoid"])
+@pytest.mark.parametrize("d", [2, 30, 64, 100])
+def test_kernel_column_matches_oracle(dtype, kind, d):
+    torch, _, S, *_ = _mods()
+    rng = np.random.default_rng(d)
+    n = 333
+    X = rng.standard_normal((n, d)).astype(dtype)
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0)
+    spec = O.KernelSpec(kind=kind, gamma=0.7 / d, coef0=0.25, degree=3)
+    cols = O.ColumnSource(X, y, O.make_kernel(spec), mirror=False, lru=0)
+    func = S.QColumns(X, y, S.KernelSpec(kind, spec.gamma, spec.coef0, spec.degree))
+    solver = S.SolverWithCache(-np.ones(n), y, 1.0, func=func)
+    tol = 2e-5 if dtype == np.float32 else 1e-12
+    for i in (0, 17, n - 1):
+        got = solver.get_Q(i).cpu().numpy()
+        want = cols(i).astype(np.float64)
+        np.testing.assert_allclose(got, want, rtol=tol, atol=tol * max(1.0, np.abs(want).max()))
+
+
+def test_kernel_column_mirror():
+    torch, _, S, *_ = _mods()
+    rng = np.random.default_rng(1)
+    l, d = 200, 16
+    X = rng.standard_normal((l, d)).astype(np.float32)
+    y = np.r_[np.ones(l), -np.ones(l)]
+    spec = O.KernelSpec(kind="rbf", gamma=0.05)
+    cols = O.ColumnSource(X, y, O.make_kernel(spec), mirror=True, lru=0)
+    func = S.QColumns(X, y, S.KernelSpec("rbf", 0.05), mirror=True)
+    solver = S.SolverWithCache(np.zeros(2 * l), y, 1.0, func=func)
+    for i in (3, l + 3, 2 * l - 1):
+        np.testing.assert_allclose(solver.get_Q(i).cpu().numpy(), cols(i), rtol=2e-5, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------ step-wise API
+def test_g4_stepwise_trace(golden):
+    """select / update one step at a time reproduce the reference's (i, j, delta) trace, including
+    the lowest-index tie-break at iteration 0."""
+    torch, _, S, *_ = _mods()
+    g = golden("g4_tiny_trace")
+    X, y01 = g["X"], g["y"]
+    y = np.where(y01 == 1, 1.0, -1.0)
+    func = S.QColumns(X, y, S.KernelSpec("rbf", 0.5))
+    solver = S.SolverWithCache(-np.ones(8), y, 1.0, 1e-5, func=func)
+    trace = g["trace_head"]
+    for k in range(trace.shape[0]):
+        i, j = solver.working_set_select()
+        assert (i, j) == (int(trace[k, 0]), int(trace[k, 1])), k
+        di, dj = solver.update(i, j)
+        np.testing.assert_allclose([di, dj], trace[k, 2:], rtol=0, atol=1e-12)
+    assert solver.working_set_select() == (-1, -1)
+    np.testing.assert_allclose(solver.alpha.cpu().numpy(), g["alpha"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(solver.neg_y_grad.cpu().numpy(), g["g"], rtol=0, atol=1e-12)
+    assert abs(solver.calculate_rho() - float(g["rho"])) < 1e-12
+
+
+def test_stepwise_equals_fused(breast_cancer):
+    torch, _, S, *_ = _mods()
+    X, y01 = breast_cancer
+    y = np.where(y01 == 1, 1.0, -1.0)
+    spec = S.KernelSpec("rbf", 1 / (30 * X.std()))
+    a = S.SolverWithCache(-np.ones(len(y)), y, 1.0, func=S.QColumns(X, y, spec))
+    b = S.SolverWithCache(-np.ones(len(y)), y, 1.0, func=S.QColumns(X, y, spec))
+    for _ in range(40):
+        i, j = a.working_set_select()
+        a.update(i, j)
+    st = b.solve(40)
+    assert st.n_iter == 40 and (st.last_i, st.last_j) == a.working_set_select()
+    np.testing.assert_array_equal(a.alpha.cpu().numpy(), b.alpha.cpu().numpy())
+    np.testing.assert_array_equal(a.neg_y_grad.cpu().numpy(), b.neg_y_grad.cpu().numpy())
+
+
+def test_update_matches_oracle_on_random_state():
+    torch, _, S, *_ = _mods()
+    rng = np.random.default_rng(3)
+    n, d = 1000, 24
+    X = rng.standard_normal((n, d))
+    y = np.where(rng.random(n) < 0.5, 1.0, -1.0)
+    spec = O.KernelSpec(kind="rbf", gamma=0.04)
+    fit = O.fit_csvc(X, (y > 0).astype(int), gamma=0.04, max_iter=150)      # some mid-solve state
+    st = O.DualState(y=y, p=-np.ones(n), C=1.0, tol=1e-5, alpha=fit.alpha.copy(), g=fit.g.copy())
+    cols = O.ColumnSource(X, y, O.make_kernel(spec), mirror=False)
+    solver = S.SolverWithCache(-np.ones(n), y, 1.0, func=S.QColumns(X, y, S.KernelSpec("rbf", 0.04)))
+    solver.alpha = fit.alpha
+    solver.neg_y_grad = fit.g
+    for _ in range(25):
+        i, j = O.select_pair(st)
+        assert solver.working_set_select() == (i, j)
+        want = O.take_step(st, i, j, cols(i), cols(j))
+        got = solver.update(i, j)
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(solver.alpha.cpu().numpy(), st.alpha, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(solver.neg_y_grad.cpu().numpy(), st.g, rtol=0, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------ estimators vs golden
+def test_g1_breast_cancer_csvc(golden, breast_cancer):
+    *_, svc, _, _ = _mods()
+    X, y = breast_cancer
+    g = golden("g1_breast_cancer_csvc")
+    est = svc.BiKernelSVC(max_iter=10 ** 6).fit(X, y)
+    iters_close(est.n_iter_, int(g["n_iter"]))
+    np.testing.assert_array_equal(est.support_, np.flatnonzero(g["alpha"] > 0))
+    rel_close(est.alpha_, g["alpha"])
+    rel_close(est.rho_, float(g["rho"]))
+    rel_close(est.decision_function(X), g["dec"])
+    np.testing.assert_array_equal(est.predict(X), g["pred"])
+    # dual objective 0.5 a.(grad f + p), grad f = -y g      (-59.7613453705)
+    s = est._fitted.solver
+    yv = np.where(y == 1, 1.0, -1.0)
+    obj = 0.5 * float(est.alpha_ @ (-yv * s.neg_y_grad.cpu().numpy() - 1.0))
+    assert abs(obj - (-59.7613453705)) < 1e-4 * 59.76
+
+
+@pytest.mark.parametrize("kernel", ["linear", "poly", "sigmoid"])
+def test_g6_kernels(golden, breast_cancer, kernel):
+    *_, svc, _, _ = _mods()
+    X, y = breast_cancer
+    g = golden(f"g6_breast_cancer_{kernel}")
+    est = svc.BiKernelSVC(kernel=kernel, max_iter=10 ** 6).fit(X, y)
+    iters_close(est.n_iter_, int(g["n_iter"]))
+    np.testing.assert_array_equal(est.support_, np.flatnonzero(g["alpha"] > 0))
+    rel_close(est.alpha_, g["alpha"])
+    rel_close(est.decision_function(X), g["dec"], atol=1e-5)
+    np.testing.assert_array_equal(est.predict(X), g["pred"])
+
+
+def test_g7_nusvc(golden, breast_cancer, capsys):
+    *_, svc, _, _ = _mods()
+    X, y = breast_cancer
+    g = golden("g7_breast_cancer_nusvc")
+    est = svc.BiNuSVC(max_iter=1000).fit(X, y)
+    assert est.n_iter_ == 1000                                  # D3: the nu solver never stops on tol
+    assert "NuSVC not coverage with 1000 iterations" in capsys.readouterr().out
+    rel_close(est.alpha_, g["alpha"])
+    rel_close(est.rho_, float(g["rho"]))
+    rel_close(est.b_, float(g["b"]))
+    rel_close(est.decision_function(X), g["dec"], atol=1e-5)
+    np.testing.assert_array_equal(est.predict(X), g["pred"])
+    assert abs(est.alpha_.sum() - 0.5 * len(y)) < 1e-8
+
+
+def test_g8_svr(golden, diabetes):
+    *_, svr, _ = _mods()
+    X, z = diabetes
+    for tag, kw in (("svr", {}), ("svr_eps10_C100", dict(eps=10, C=100))):
+        g = golden(f"g8_diabetes_{tag}")
+        est = svr.KernelSVR(max_iter=10 ** 6, **kw).fit(X, z)
+        iters_close(est.n_iter_, int(g["n_iter"]))
+        rel_close(est.alpha_, g["alpha"], atol=1e-5 * float(kw.get("C", 1)))
+        rel_close(est.rho_, float(g["rho"]))
+        rel_close(est.predict(X), g["dec"], atol=1e-3)
+    g = golden("g8_diabetes_nusvr")
+    est = svr.NuSVR(max_iter=1000).fit(X, z)
+    assert est.n_iter_ == 1000
+    rel_close(est.alpha_, g["alpha"])
+    rel_close(est.b_, float(g["b"]))
+    rel_close(est.predict(X), g["dec"], atol=1e-3)
+
+
+def test_g5_oneclass(golden):
+    *_, oc = _mods()
+    g = golden("g5_oneclass")
+    est = oc.OneClassSVM(nu=.1, gamma=.1, max_iter=10 ** 5).fit(g["X"])
+    iters_close(est.n_iter_, int(g["n_iter"]))
+    rel_close(est.alpha_, g["alpha"])
+    rel_close(est.rho_, float(g["rho"]))
+    rel_close(est.decision_function(g["X"]), g["dec"], atol=1e-6)
+    np.testing.assert_array_equal(est.predict(g["X"]), g["pred"])
+
+
+def test_linear_estimators(golden, breast_cancer, diabetes):
+    *_, svc, svr, _ = _mods()
+    X, y = breast_cancer
+    g = golden("lin_breast_cancer_svc")
+    est = svc.BiLinearSVC(max_iter=10 ** 6).fit(X, y)
+    iters_close(est.n_iter_, int(g["n_iter"]))
+    rel_close(est.coef_[0], g["w"], atol=1e-6)
+    rel_close(est.decision_function(X), g["dec"], atol=1e-5)
+    X, z = diabetes
+    g = golden("lin_diabetes_svr")
+    est = svr.LinearSVR(max_iter=10 ** 6).fit(X, z)
+    iters_close(est.n_iter_, int(g["n_iter"]))
+    rel_close(est.coef_[0], g["w"], atol=1e-5)
+
+
+def test_g3_digits_ovo(golden, digits):
+    """45 one-vs-one sub-problems: per-sub-problem iteration counts within 1 %, identical
+    support-vector counts, identical predicted labels."""
+    *_, P, S, svc, _, _ = _mods()
+    X, y = digits
+    g = golden("g3_digits_ovo")
+    est = P.KernelSVC(multiclass="ovo", max_iter=10 ** 6).fit(X, y)
+    subs = est.multiclass_model.estimators_
+    iters = np.array([e.n_iter_ for e in subs])
+    nsv = np.array([len(e.support_) for e in subs])
+    assert np.all(np.abs(iters - g["sub_iters"]) <= np.maximum(1, 0.01 * g["sub_iters"])), (iters, g["sub_iters"])
+    np.testing.assert_array_equal(nsv, g["sub_nsv"])
+    np.testing.assert_array_equal(est.predict(X), g["pred"])
+    rel_close(est.decision_function(X[:32]), g["dec_head"], atol=1e-5)
+
+
+# ------------------------------------------------------------------------------ float32 synthetic configs
+def test_s3_synth_classification_converged(golden):
+    """C3-shaped float32 problem at n=2000 to convergence: same SV set, iterations within 1 %."""
+    *_, svc, _, _ = _mods()
+    X, y = O.synth_classification(n=2000, d=128, seed=0)
+    g = golden("s3_synth_cls_n2000")
+    est = svc.BiKernelSVC(max_iter=10 ** 7).fit(X, y)
+    iters_close(est.n_iter_, int(g["n_iter"]))
+    np.testing.assert_array_equal(est.support_, np.flatnonzero(g["alpha"] > 0))
+    rel_close(est.alpha_, g["alpha"], atol=1e-4)
+    rel_close(est.rho_, float(g["rho"]), atol=1e-5)
+    rel_close(est.decision_function(X[:256]), g["dec"], atol=1e-4)
+
+
+def test_s3_synth_classification_capped(golden):
+    """n=20000, max_iter=1000: the early (clipping) phase is reproduced pair for pair."""
+    torch, _, S, svc, _, _ = _mods()
+    X, y = O.synth_classification(n=20000, d=128, seed=0)
+    g = golden("s3_synth_cls_n20000_cap1000")
+    est = svc.BiKernelSVC(max_iter=1000).fit(X, y)
+    assert est.n_iter_ == 1000
+    rel_close(est.alpha_, g["alpha"], atol=1e-4)
+    rel_close(est._fitted.solver.neg_y_grad.cpu().numpy(), g["g"], atol=1e-4)
+
+
+def test_s4_synth_regression(golden):
+    *_, svr, _ = _mods()
+    X, z = O.synth_regression(n=1000, d=64, seed=0)
+    g = golden("s4_synth_svr_n1000")
+    est = svr.KernelSVR(max_iter=10 ** 7).fit(X, z)
+    iters_close(est.n_iter_, int(g["n_iter"]))
+    rel_close(est.alpha_, g["alpha"], atol=1e-4)
+    rel_close(est.predict(X[:256]), g["dec"], atol=1e-4)
+    g = golden("s4_synth_nusvr_n1000")
+    est = svr.NuSVR(max_iter=2000).fit(X, z)
+    assert est.n_iter_ == 2000
+    rel_close(est.alpha_, g["alpha"], atol=1e-4)
+    rel_close(est.b_, float(g["b"]), atol=1e-5)
+
+
+def test_s5_synth_oneclass(golden):
+    *_, oc = _mods()
+    X = O.synth_oneclass(n=2000, d=32, seed=1)
+    g = golden("s5_synth_oneclass_n2000")
+    est = oc.OneClassSVM(max_iter=10 ** 7).fit(X)
+    iters_close(est.n_iter_, int(g["n_iter"]))
+    rel_close(est.alpha_, g["alpha"], atol=1e-4)
+    rel_close(est.rho_, float(g["rho"]))
+    rel_close(est.decision_function(X[:256]), g["dec"], atol=1e-4)
+
+
+# ------------------------------------------------------------------------------ RFF
+def test_rff_vectors(golden):
+    _, P, *_ = _mods()
+    from pysvm_b200.rff import NormalRFF
+    g = golden("rff_vectors")
+    np.random.seed(3)
+    r = NormalRFF(gamma=0.3, D=32).fit(g["X"])
+    np.testing.assert_array_equal(r.w, g["w"])
+    np.testing.assert_array_equal(r.b, g["b"])
+    np.testing.assert_allclose(r.transform(g["X"]), g["Z"], rtol=0, atol=1e-13)
+
+
+# ------------------------------------------------------------------------------ full-size properties
+def test_full_size_invariants():
+    """BASELINE.json configs[2] shape (n=200k, d=128, float32): after 2000 fused iterations the
+    equality constraint and the box hold exactly, and the incrementally updated gradient equals a
+    from-scratch recomputation -y*(Q alpha + p) (size-independent checks; the oracle cannot run here)."""
+    torch, _, S, *_ = _mods()
+    X, y01 = O.synth_classification(n=200_000, d=128, seed=0)
+    y = np.where(y01 == 1, 1.0, -1.0)
+    gamma = 1 / (128 * X.std())
+    func = S.QColumns(X, y, S.KernelSpec("rbf", gamma))
+    solver = S.SolverWithCache(-np.ones(len(y)), y, 1.0, func=func)
+    st = solver.solve(2000)
+    assert st.n_iter == 2000 and st.n_ctas > 100
+    a = solver.alpha.cpu().numpy()
+    assert a.min() >= 0 and a.max() <= 1.0
+    assert abs(float(a @ y)) < 1e-9
+    g_inc = solver.neg_y_grad.clone()
+    solver._engine.init_gradient(solver.p)
+    g_new = solver.neg_y_grad
+    assert float((g_inc - g_new).abs().max()) < 5e-5
+    # the pair the fused kernel would take next is the arg-max / arg-min of the oracle rule
+    stt = O.DualState(y=y, p=-np.ones(len(y)), C=1.0, tol=1e-5, alpha=a, g=g_inc.cpu().numpy())
+    assert O.select_pair(stt) == (st.last_i, st.last_j)
