@@ -196,8 +196,8 @@ struct b2svm_handle {
   const void* Xuse = nullptr;
   void* norms = nullptr;
   uint8_t* flags = nullptr;
-  CandRec* cand = nullptr;
-  uint32_t* flag = nullptr;
+  uint4* cand = nullptr;        // tagged candidate records [2][num_sms][NCAND][2]
+  size_t cand_bytes = 0;
   int* abort_flag = nullptr;
   SolveResult* result = nullptr;
   SolveResult* result_host = nullptr;
@@ -211,6 +211,8 @@ struct b2svm_handle {
   long long ntiles = 0;
   size_t smem_bytes = 0;
   int launches = 0;
+  long long* timeline = nullptr;   // debug: set by B2SVM_TIMELINE=1
+  double* dbg_steps = nullptr;     // debug: set by B2SVM_DEBUG_STEPS=1
 };
 
 namespace {
@@ -226,13 +228,14 @@ template <typename T, int CH>
 struct Geometry {
   using C = Cfg<T, CH>;
   static size_t smem_for(int stages) {
-    return (size_t)stages * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + 2 * (size_t)C::ROWB +
+    return (size_t)stages * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + MAX_STAGES * sizeof(unsigned) +
+           2 * (size_t)C::ROWB +
            sizeof(Shared<T>) + 128;
   }
 };
 
 constexpr size_t kSmemBudget = 227 * 1024;   // opt-in maximum per CTA on sm_100
-constexpr size_t kRingBudget = 200 * 1024;
+constexpr size_t kRingBudget = 204 * 1024;
 
 template <typename T, int CH>
 int plan_T(b2svm_handle* h) {
@@ -243,16 +246,20 @@ int plan_T(b2svm_handle* h) {
   h->stages = stages;
   h->smem_bytes = Geometry<T, CH>::smem_for(stages);
   h->ntiles = (h->d.n_rows + C::BR - 1) / C::BR;
-  int min_tiles = 8;
+  int min_tiles = NW;
   if (const char* e = getenv("B2SVM_MIN_TILES_PER_CTA")) min_tiles = std::max(1, atoi(e));
   int max_ctas = h->d.max_ctas > 0 ? h->d.max_ctas : h->num_sms;
   if (const char* e = getenv("B2SVM_MAX_CTAS")) max_ctas = std::max(1, atoi(e));
   max_ctas = std::min(max_ctas, h->num_sms);
   long long ncta = std::max<long long>(1, std::min<long long>(max_ctas, h->ntiles / min_tiles));
-  const long long tpc = (h->ntiles + ncta - 1) / ncta;
-  ncta = (h->ntiles + tpc - 1) / tpc;
+  // prefer a split whose slices fit the ring, so X stays resident in shared memory for the whole solve
+  const long long fit = (h->ntiles + stages - 1) / stages;
+  if (fit <= max_ctas) ncta = std::max(ncta, fit);
+  // ... and, when the GPU has room, one tile per consumer warp (no intra-CTA imbalance)
+  const long long one_each = (h->ntiles + NW - 1) / NW;
+  if (one_each <= max_ctas) ncta = std::max(ncta, one_each);
   h->ncta = (int)ncta;
-  h->tiles_per_cta = (int)tpc;
+  h->tiles_per_cta = (int)((h->ntiles + ncta - 1) / ncta);   // informational: the kernel deals tiles out evenly
   return B2SVM_OK;
 }
 
@@ -316,12 +323,14 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.tiles_per_cta = h->tiles_per_cta;
   P.ntiles = h->ntiles;
   P.cand = h->cand;
-  P.flag = h->flag;
   P.abort_flag = h->abort_flag;
   P.result = h->result;
   P.max_iter = max_iter;
   P.forced_i = fi;
   P.forced_j = fj;
+  P.timeline = h->timeline;
+  P.dbg_steps = h->dbg_steps;
+  P.debug_flags = getenv("B2SVM_DEBUG_FLAGS") ? atoi(getenv("B2SVM_DEBUG_FLAGS")) : 0;
 }
 
 // one persistent launch for one handle; fills *res from the device result
@@ -330,7 +339,8 @@ int run_solver(b2svm_handle* h, long long max_iter, long long fi, long long fj, 
   const int64_t nv = h->d.n_vars;
   refresh_flags_kernel<<<grid_for(nv), 256, 0, h->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, nv);
   B2_CUDA(cudaGetLastError());
-  B2_CUDA(cudaMemsetAsync(h->flag, 0, sizeof(uint32_t) * (h->num_sms + 1), h->stream));
+  B2_CUDA(cudaMemsetAsync(h->cand, 0, h->cand_bytes, h->stream));
+  B2_CUDA(cudaMemsetAsync(h->abort_flag, 0, sizeof(int), h->stream));
   ProblemDev P;
   memset(&P, 0, sizeof(P));
   fill_problem(h, P, max_iter, fi, fj);
@@ -365,7 +375,7 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
   if (desc->n_rows <= 0 || desc->n_features <= 0) return fail(B2SVM_E_INVALID, "empty problem");
   if (desc->n_vars != desc->n_rows && desc->n_vars != 2 * desc->n_rows)
     return fail(B2SVM_E_INVALID, "n_vars must be n_rows or 2*n_rows");
-  if (desc->n_vars >= (1ll << 31)) return fail(B2SVM_E_UNSUPPORTED, "n_vars must be below 2^31");
+  if (desc->n_vars >= (1ll << 29)) return fail(B2SVM_E_UNSUPPORTED, "n_vars must be below 2^29");
   if (!desc->X || !desc->y || !desc->alpha || !desc->neg_y_grad) return fail(B2SVM_E_INVALID, "null device pointer");
   if (desc->x_dtype != B2SVM_F32 && desc->x_dtype != B2SVM_F64) return fail(B2SVM_E_INVALID, "bad x_dtype");
   if (desc->kernel.kind < 0 || desc->kernel.kind > 3) return fail(B2SVM_E_INVALID, "bad kernel kind");
@@ -417,15 +427,23 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     row_norms_kernel<float><<<grid_for(l * 32), 256, 0, h->stream>>>((const float*)h->Xuse, l, h->dp, (float*)h->norms);
   B2_TRY(cudaGetLastError());
   B2_TRY(cudaMalloc(&h->flags, (size_t)nv));
-  B2_TRY(cudaMalloc(&h->cand, sizeof(CandRec) * 2 * h->num_sms * NCAND));
-  B2_TRY(cudaMalloc(&h->flag, sizeof(uint32_t) * (h->num_sms + 1)));
-  h->abort_flag = reinterpret_cast<int*>(h->flag + h->num_sms);
+  h->cand_bytes = sizeof(uint4) * 2 * h->num_sms * NCAND;
+  B2_TRY(cudaMalloc(&h->cand, h->cand_bytes));
+  B2_TRY(cudaMalloc(&h->abort_flag, sizeof(int)));
   B2_TRY(cudaMalloc(&h->result, sizeof(SolveResult)));
   B2_TRY(cudaMallocHost(&h->result_host, sizeof(SolveResult)));
   B2_TRY(cudaMalloc(&h->prob_dev, sizeof(ProblemDev)));
   B2_TRY(cudaMalloc(&h->bias_dev, sizeof(BiasStats)));
   B2_TRY(cudaEventCreate(&h->ev0));
   B2_TRY(cudaEventCreate(&h->ev1));
+  if (getenv("B2SVM_DEBUG_STEPS")) {
+    B2_TRY(cudaMalloc(&h->dbg_steps, sizeof(double) * DBG_EPOCHS * (h->num_sms * 6 + 2)));
+    B2_TRY(cudaMemset(h->dbg_steps, 0, sizeof(double) * DBG_EPOCHS * (h->num_sms * 6 + 2)));
+  }
+  if (getenv("B2SVM_TIMELINE")) {
+    B2_TRY(cudaMalloc(&h->timeline, sizeof(long long) * TL_TOTAL));
+    B2_TRY(cudaMemset(h->timeline, 0, sizeof(long long) * TL_TOTAL));
+  }
 #undef B2_TRY
   int rc = plan(h);
   if (rc != B2SVM_OK) {
@@ -444,13 +462,15 @@ int b2svm_destroy(b2svm_handle* h) {
   cudaFree(h->norms);
   cudaFree(h->flags);
   cudaFree(h->cand);
-  cudaFree(h->flag);
+  cudaFree(h->abort_flag);
   cudaFree(h->result);
   if (h->result_host) cudaFreeHost(h->result_host);
   cudaFree(h->prob_dev);
   cudaFree(h->bias_dev);
   cudaFree(h->scratch);
   cudaFree(h->p_dev);
+  cudaFree(h->timeline);
+  cudaFree(h->dbg_steps);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -624,7 +644,8 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
   for (int k = 0; k < count; ++k) {
     b2svm_handle* h = handles[k];
     refresh_flags_kernel<<<grid_for(h->d.n_vars), 256, 0, h0->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, h->d.n_vars);
-    cudaMemsetAsync(h->flag, 0, sizeof(uint32_t) * (h->num_sms + 1), h0->stream);
+    cudaMemsetAsync(h->cand, 0, h->cand_bytes, h0->stream);
+    cudaMemsetAsync(h->abort_flag, 0, sizeof(int), h0->stream);
     memset(&P[k], 0, sizeof(ProblemDev));
     fill_problem(h, P[k], max_iter, -1, -1);
     P[k].ncta = 1;
@@ -667,6 +688,21 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
   cudaFree(pd);
   cudaFree(rd);
   return rc;
+}
+
+/* debug only (not part of the ABI header): copy the leader timeline of the last solve to the host */
+int b2svm_debug_timeline(b2svm_handle* h, long long* out, int n) {
+  if (!h || !h->timeline) return fail(B2SVM_E_INVALID, "timeline not enabled (B2SVM_TIMELINE=1)");
+  B2_CUDA(cudaMemcpy(out, h->timeline, sizeof(long long) * std::min(n, TL_TOTAL), cudaMemcpyDeviceToHost));
+  return B2SVM_OK;
+}
+
+int b2svm_debug_steps(b2svm_handle* h, double* out, int epochs) {
+  if (!h || !h->dbg_steps) return fail(B2SVM_E_INVALID, "debug steps not enabled (B2SVM_DEBUG_STEPS=1)");
+  B2_CUDA(cudaMemcpy(out, h->dbg_steps, sizeof(double) * (size_t)std::min(epochs, DBG_EPOCHS) * h->ncta * 6, cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(out + (size_t)std::min(epochs, DBG_EPOCHS) * h->ncta * 6, h->dbg_steps + (size_t)DBG_EPOCHS * h->ncta * 6,
+                     sizeof(double) * (size_t)std::min(epochs, DBG_EPOCHS) * 2, cudaMemcpyDeviceToHost));
+  return B2SVM_OK;
 }
 
 int b2svm_mailbox_export(b2svm_handle*, void*) { return fail(B2SVM_E_UNSUPPORTED, "row-sharded multi-GPU solve not built yet"); }

@@ -64,6 +64,20 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// 16-byte relaxed (L1-bypassing, single-transaction) global accesses: the working-set records carry
+// their own epoch tag in each 16-byte half, so no fence is needed around them (b2svm_smo.cuh).
+__device__ __forceinline__ uint4 ld_relaxed_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_v4(void* p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -90,6 +104,15 @@ struct Chunk<float> {
     acc = fmaf(a.w, b.w, acc);
     return acc;
   }
+  // component-wise accumulation: four independent FMA chains per vector
+  static __device__ __forceinline__ V fma_each(const V& a, const V& b, V acc) {
+    acc.x = fmaf(a.x, b.x, acc.x);
+    acc.y = fmaf(a.y, b.y, acc.y);
+    acc.z = fmaf(a.z, b.z, acc.z);
+    acc.w = fmaf(a.w, b.w, acc.w);
+    return acc;
+  }
+  static __device__ __forceinline__ float hsum(const V& a) { return (a.x + a.y) + (a.z + a.w); }
 };
 template <>
 struct Chunk<double> {
@@ -101,6 +124,12 @@ struct Chunk<double> {
     acc = fma(a.y, b.y, acc);
     return acc;
   }
+  static __device__ __forceinline__ V fma_each(const V& a, const V& b, V acc) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.y = fma(a.y, b.y, acc.y);
+    return acc;
+  }
+  static __device__ __forceinline__ double hsum(const V& a) { return a.x + a.y; }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -141,10 +170,43 @@ __device__ __forceinline__ T kernel_value(const KernelParams<T>& k, T dot, T nor
 // working-set candidates.  Order: value first, then the LOWER index (np.argmax / np.argmin over an
 // index-sorted subset return the first extremum: solver.py:68-69).  idx < 0 = empty set.
 // ------------------------------------------------------------------------------------------
-struct Cand {
+struct Cand {        // lane / warp level: value, variable index, flags byte of that variable
   double g;
   int idx;
+  int flags;
 };
+
+// Order-preserving map double -> uint64 (so arg-max over doubles becomes integer REDUX.MAX), and back.
+__device__ __forceinline__ unsigned long long dkey(double g) {
+  const long long b = __double_as_longlong(g);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+  const long long b = (k >> 63) ? (long long)(k ^ 0x8000000000000000ull) : (long long)~k;
+  return __longlong_as_double(b);
+}
+
+// Arg-max (is_max) / arg-min over the lanes in `mask` with ties going to the lower index: three
+// REDUX instructions (hi word, lo word, packed index) instead of a 5-round shuffle butterfly.
+// Every lane of `mask` must call it with the same mask; all of them receive the winner.
+__device__ __forceinline__ void redux_select(unsigned mask, bool is_max, Cand& c) {
+  unsigned long long key = c.idx >= 0 ? dkey(c.g) : 0ull;      // 0 is below every real value's key
+  if (!is_max && c.idx >= 0) key = ~key;
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned ik = c.idx >= 0 ? (((unsigned)c.idx << 3) | (unsigned)c.flags) : 0xffffffffu;
+  const unsigned mh = __reduce_max_sync(mask, hi);
+  const unsigned ml = __reduce_max_sync(mask, hi == mh ? lo : 0u);
+  const unsigned mi = __reduce_min_sync(mask, (hi == mh && lo == ml) ? ik : 0xffffffffu);
+  if (mi == 0xffffffffu) {
+    c.g = 0.0; c.idx = -1; c.flags = 0;
+  } else {
+    unsigned long long k = ((unsigned long long)mh << 32) | ml;
+    if (!is_max) k = ~k;
+    c.g = dkey_inv(k);
+    c.idx = (int)(mi >> 3);
+    c.flags = (int)(mi & 7u);
+  }
+}
 __device__ __forceinline__ bool better_max(double g, int idx, double bg, int bidx) {
   return idx >= 0 && (bidx < 0 || g > bg || (g == bg && idx < bidx));
 }

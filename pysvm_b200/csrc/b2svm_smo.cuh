@@ -9,30 +9,38 @@
 //   3. sweeps its own slice of X once: both Q columns (dot products + kernel epilogue), the
 //      rank-2 gradient update, and the next iteration's argmax/argmin candidates in the same pass
 //                                                           -> func(i) svc.py:257-258, solver.py:146
-//   4. publishes its candidates; a flag-based grid barrier closes the iteration.
+//   4. publishes its candidates as self-validating records; reading every CTA's record IS the
+//      grid barrier (no atomics, no fences).
 //
 // X rows reach shared memory through a ring of 1-D TMA bulk copies (cp.async.bulk + mbarrier,
 // SASS UBLKCP) issued by a dedicated producer thread that runs ahead of the consumers across
-// iteration boundaries, so HBM keeps streaming while the grid barrier and the serial
+// iteration boundaries, so HBM keeps streaming while the exchange and the serial
 // select -> step chain are in flight.  When a CTA's slice fits in the ring it is loaded once and
 // stays resident in shared memory for the whole solve (small problems, multi-GPU shards).
+//
+// Candidate exchange.  A record is one 16-byte word {g, idx, epoch<<3 | flags}, written and read with
+// one 16-byte relaxed access and double-buffered by epoch parity.  A reader accepts a record only
+// when it carries the epoch it waits for, so data and "flag" travel together and no release/acquire
+// fence (MEMBAR.SC + CCTL.IVALL, ~2-4k cycles each on B200) sits on the per-iteration critical
+// path.  G / flags of a row are only ever read by the CTA (= SM) that writes them.  alpha_i / alpha_j
+// are fetched by every leader straight from L2 together with rows x_i / x_j.  To keep a fast CTA from
+// overwriting alpha_j while a slow leader still reads it, the store of a step's new alphas is
+// deferred to the NEXT sweep (every leader forwards the previous pair's values from registers), and
+// the lane that stores fences it (off the critical path) before its CTA's next record.
 #pragma once
 #include "b2svm_device.cuh"
 
 namespace b2svm {
 
-constexpr int NW = 8;                      // consumer warps per CTA
+constexpr int NW = 11;                     // consumer warps per CTA (+1 producer warp = 384 threads, 168 regs)
 constexpr int NTHREADS = (NW + 1) * 32;    // + one producer warp
 constexpr int MAX_STAGES = 64;
 constexpr int NCAND = 4;                   // up/low (C variant) or up+/low+/up-/low- (nu variant)
-
-struct __align__(16) CandRec {
-  double g;
-  double alpha;
-  int idx;
-  int flags;
-  int pad[2];
-};
+constexpr int TL_ITERS = 64, TL_SLOTS = 8; // debug timeline
+constexpr int DBG_EPOCHS = 2048;
+constexpr int TL_WARP_SLOTS = 4;           // + per-warp {start, end, tiles, wait} of one sweep
+constexpr int TL_CTA_BASE = TL_ITERS * TL_SLOTS + 16 * TL_WARP_SLOTS;   // + per-CTA {sweep cycles, tiles} of one sweep
+constexpr int TL_TOTAL = TL_CTA_BASE + 2 * 160;
 
 struct SolveResult {
   long long n_iter;
@@ -58,26 +66,35 @@ struct ProblemDev {
   int ncta;             // CTAs cooperating on this problem
   int tiles_per_cta;
   long long ntiles;
-  CandRec* cand;        // [2][ncta][NCAND]
-  uint32_t* flag;       // [ncta] epoch counters (zeroed before every launch)
+  uint4* cand;          // [2][ncta][NCAND] tagged records (zeroed before every launch)
   int* abort_flag;
   SolveResult* result;
   long long max_iter;
   long long forced_i, forced_j;   // >= 0: skip the initial selection and take this pair first
+  long long* timeline;            // optional [TL_ITERS][TL_SLOTS] clock64 stamps of CTA 0's leader lane
+  double* dbg_steps;              // optional [DBG_EPOCHS][ncta][6] = si, sj, gi, gj, ai, aj seen by each leader
+  int debug_flags;                // B2SVM_DEBUG_FLAGS: 1 = static tile assignment, 2 = L2 loads for G/flags
 };
 
+// Tile geometry.  A tile is one contiguous bulk copy of BR rows of CH 16-byte chunks.  LPR lanes share
+// a row (lane p of the group owns chunks p, p+LPR, ...: the 8 lanes of a quarter-warp read 128
+// contiguous bytes, conflict-free), a warp-wide load therefore fetches GRP = 32/LPR rows, and a lane
+// group walks RPL rows per tile.  x_i / x_j live in registers (CPL chunks each per lane), so the tile
+// is the only shared-memory traffic.  The RPL*2 partial sums per lane are combined with a transposed
+// reduction (log2(LPR) exchange rounds, NV - FINAL shuffles in total) that leaves lane r of the warp
+// holding both dot products of row r of the tile.
 template <typename T, int CH_>
 struct Cfg {
   using CK = Chunk<T>;
   using V = typename CK::V;
-  static constexpr int CH = CH_;                         // 16-byte chunks per row
-  static constexpr int LPR = CH < 32 ? CH : 32;          // lanes per row
-  static constexpr int CPL = CH / LPR;                   // chunks per lane
-  static constexpr int GRP = 32 / LPR;                   // rows fetched by one warp-wide load
-  static constexpr int FINAL = sizeof(T) == 4 ? 2 : 1;   // sums per lane after the transposed reduce
-  static constexpr int RPL = FINAL == 2 ? LPR : LPR / 2; // rows per lane group per tile
-  static constexpr int BR = GRP * RPL;                   // rows per tile (32 for f32, 16 for f64)
-  static constexpr int NV = 2 * RPL;                     // partial sums per lane
+  static constexpr int CH = CH_;                                   // 16-byte chunks per row
+  static constexpr int LPR = CH <= 8 ? CH : (CH <= 32 ? 8 : CH / 4);   // lanes per row: 4, 8, 8, 8, 16, 32
+  static constexpr int CPL = CH / LPR;                             // chunks per lane: 1, 1, 2, 4, 4, 4
+  static constexpr int GRP = 32 / LPR;                             // rows fetched by one warp-wide load
+  static constexpr int FINAL = (sizeof(T) == 8 && LPR == 32) ? 1 : 2;   // sums per lane after the reduce
+  static constexpr int RPL = FINAL == 2 ? LPR : LPR / 2;           // rows per lane group per tile
+  static constexpr int BR = GRP * RPL;                             // rows per tile (32, or 16)
+  static constexpr int NV = 2 * RPL;                               // partial sums per lane
   static constexpr int ROWB = CH * 16;
   static constexpr int TILE_BYTES = BR * ROWB;
 };
@@ -88,9 +105,12 @@ struct Shared {
   double ai, aj;        // new alpha_i, alpha_j
   T ni, nj;             // |x_i|^2, |x_j|^2
   int i, j, fi, fj;
+  int pi, pj;           // previous pair, whose alphas (pai, paj) are stored during this sweep
+  double pai, paj;
   int stop;
   volatile int producer_stop;
   volatile long long consumed;
+  int ticket;           // next dynamically assigned tile of the current sweep
   Cand wc[NW][NCAND];
 };
 
@@ -98,44 +118,17 @@ __device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (
   const bool second = nu && !(f & F_YPOS);
   if (in_up(f)) {
     if (!second) {
-      if (better_max(g, v, b[0].g, b[0].idx)) { b[0].g = g; b[0].idx = v; }
+      if (better_max(g, v, b[0].g, b[0].idx)) { b[0].g = g; b[0].idx = v; b[0].flags = f; }
     } else {
-      if (better_max(g, v, b[2].g, b[2].idx)) { b[2].g = g; b[2].idx = v; }
+      if (better_max(g, v, b[2].g, b[2].idx)) { b[2].g = g; b[2].idx = v; b[2].flags = f; }
     }
   }
   if (in_low(f)) {
     if (!second) {
-      if (better_min(g, v, b[1].g, b[1].idx)) { b[1].g = g; b[1].idx = v; }
+      if (better_min(g, v, b[1].g, b[1].idx)) { b[1].g = g; b[1].idx = v; b[1].flags = f; }
     } else {
-      if (better_min(g, v, b[3].g, b[3].idx)) { b[3].g = g; b[3].idx = v; }
+      if (better_min(g, v, b[3].g, b[3].idx)) { b[3].g = g; b[3].idx = v; b[3].flags = f; }
     }
-  }
-}
-
-// butterfly reduce of one candidate over the warp; k even = max type, k odd = min type
-__device__ __forceinline__ void warp_reduce_cand(Cand& c, bool is_max) {
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    const double og = __shfl_xor_sync(0xffffffffu, c.g, m);
-    const int oi = __shfl_xor_sync(0xffffffffu, c.idx, m);
-    const bool take = is_max ? better_max(og, oi, c.g, c.idx) : better_min(og, oi, c.g, c.idx);
-    if (take) { c.g = og; c.idx = oi; }
-  }
-}
-
-struct Winner {
-  double g, alpha;
-  int idx, flags;
-};
-__device__ __forceinline__ void warp_reduce_winner(Winner& w, bool is_max) {
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    const double og = __shfl_xor_sync(0xffffffffu, w.g, m);
-    const double oa = __shfl_xor_sync(0xffffffffu, w.alpha, m);
-    const int oi = __shfl_xor_sync(0xffffffffu, w.idx, m);
-    const int of = __shfl_xor_sync(0xffffffffu, w.flags, m);
-    const bool take = is_max ? better_max(og, oi, w.g, w.idx) : better_min(og, oi, w.g, w.idx);
-    if (take) { w.g = og; w.alpha = oa; w.idx = oi; w.flags = of; }
   }
 }
 
@@ -151,12 +144,18 @@ __device__ __forceinline__ void pair_kernels(const ProblemDev& P, const KernelPa
   constexpr int Q = (CH + 31) / 32;
   const V* Xa = reinterpret_cast<const V*>(P.X) + ra * CH;
   const V* Xb = reinterpret_cast<const V*>(P.X) + rb * CH;
-  T daa = 0, dbb = 0, dab = 0;
+  const T* norms = reinterpret_cast<const T*>(P.norms);
+  na = __ldg(norms + ra);
+  nb = __ldg(norms + rb);
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
     const int c = lane + 32 * q;
     xa[q] = (c < CH) ? __ldg(Xa + c) : CK::zero();
     xb[q] = (c < CH) ? __ldg(Xb + c) : CK::zero();
+  }
+  T daa = 0, dbb = 0, dab = 0;
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
     daa = CK::dot(xa[q], xa[q], daa);
     dbb = CK::dot(xb[q], xb[q], dbb);
     dab = CK::dot(xa[q], xb[q], dab);
@@ -164,13 +163,17 @@ __device__ __forceinline__ void pair_kernels(const ProblemDev& P, const KernelPa
   daa = warp_sum(daa);
   dbb = warp_sum(dbb);
   dab = warp_sum(dab);
-  const T* norms = reinterpret_cast<const T*>(P.norms);
-  na = __ldg(norms + ra);
-  nb = __ldg(norms + rb);
   Kaa = kernel_value(kp, daa, na, na);
   Kbb = kernel_value(kp, dbb, nb, nb);
   Kab = kernel_value(kp, dab, na, nb);
 }
+
+template <typename T>
+struct RowState {   // gradient-side state of one row (and its mirror variable), prefetched a tile ahead
+  double g0, g1;
+  int f0, f1;
+  T nt;
+};
 
 template <typename T, int CH>
 __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* __restrict__ probs, int ncta_pp,
@@ -184,78 +187,94 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   unsigned char* ring = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)ring_stages * C::TILE_BYTES);
   uint64_t* empty = full + MAX_STAGES;
-  V* xs = reinterpret_cast<V*>(empty + MAX_STAGES);      // [2][CH]
+  // gen[s] = number of tiles consumed out of stage s so far.  A consumer waits for use u of a stage on
+  // full[s] only once gen[s] == u: mbarrier parity can tell neighbouring phases apart, not phases two
+  // apart, and with dynamically drawn tiles a warp may otherwise run a whole ring ahead of a slow one.
+  volatile unsigned* gen = reinterpret_cast<volatile unsigned*>(empty + MAX_STAGES);
+  V* xs = reinterpret_cast<V*>(const_cast<unsigned*>(gen) + MAX_STAGES);      // [2][CH]
   Shared<T>* sh = reinterpret_cast<Shared<T>*>(xs + 2 * CH);
 
   const ProblemDev& P = probs[blockIdx.x / ncta_pp];
   const int cta = blockIdx.x % ncta_pp;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int S = ring_stages;
+  const unsigned S = (unsigned)ring_stages;
 
-  // this CTA's slice of rows, in whole tiles
-  const long long tile0 = (long long)cta * P.tiles_per_cta;
-  long long tile1 = tile0 + P.tiles_per_cta;
-  if (tile1 > P.ntiles) tile1 = P.ntiles;
-  const int NT = tile1 > tile0 ? (int)(tile1 - tile0) : 0;
+  // this CTA's slice of rows, in whole tiles; tiles are dealt out as evenly as possible
+  const int ncta = P.ncta;
+  const long long tbase = P.ntiles / ncta, trem = P.ntiles % ncta;
+  const long long tile0 = (long long)cta * tbase + (cta < trem ? cta : trem);
+  const int NT = (int)(tbase + (cta < trem ? 1 : 0));
   const long long row0 = tile0 * C::BR;
-  long long row1 = tile1 * C::BR;
+  long long row1 = (tile0 + NT) * C::BR;
   if (row1 > P.l) row1 = P.l;
-  if (row1 < row0) row1 = row0;
-  const bool resident = NT <= S;
+  const bool resident = (unsigned)NT <= S;
   const bool nu = P.nu != 0;
   const bool mirror = P.mirror != 0;
   const long long l = P.l;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
+    for (unsigned s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
+      gen[s] = 0u;
     }
     mbar_fence_init();
     sh->stop = 0;
     sh->producer_stop = 0;
     sh->consumed = 0;
+    sh->ticket = NW;
   }
   __syncthreads();
 
   // ============================== producer warp ==============================================
   if (warp == NW) {
-    if (lane == 0 && NT > 0) {
+    if (NT > 0) {
       const unsigned char* Xb = reinterpret_cast<const unsigned char*>(P.X);
       unsigned long long Tp = 0;
-      auto issue = [&](unsigned long long Tg, int t, int stage) {
-        const long long r0 = row0 + (long long)t * C::BR;
+      unsigned stage = 0, par = 0;   // stage = Tp % S, par = (Tp / S) & 1
+      int t = 0;                     // Tp % NT
+      auto issue = [&](int tt, unsigned st) {
+        const long long r0 = row0 + (long long)tt * C::BR;
         long long nr = row1 - r0;
         if (nr > C::BR) nr = C::BR;
-        const uint32_t bytes = (uint32_t)(nr * C::ROWB);
-        mbar_arrive_expect_tx(&full[stage], bytes);
-        bulk_g2s(ring + (size_t)stage * C::TILE_BYTES, Xb + r0 * C::ROWB, bytes, &full[stage]);
+        unsigned char* dst = ring + (size_t)st * C::TILE_BYTES;
+        if (lane == 0) {
+          const uint32_t bytes = (uint32_t)(nr * C::ROWB);
+          mbar_arrive_expect_tx(&full[st], bytes);
+          bulk_g2s(dst, Xb + r0 * C::ROWB, bytes, &full[st]);
+        }
       };
       if (resident) {
-        for (int t = 0; t < NT; ++t) issue(t, t, t);
+        for (int tt = 0; tt < NT; ++tt) issue(tt, (unsigned)tt);
         Tp = NT;
-        while (!sh->producer_stop) __nanosleep(200);
+        if (lane == 0)
+          while (!sh->producer_stop) __nanosleep(200);
       } else {
-        bool stop = false;
-        while (!stop) {
-          const int stage = (int)(Tp % S);
-          const uint32_t par = (uint32_t)((Tp / S) & 1);
-          while (!mbar_try_wait(&empty[stage], par ^ 1u)) {
-            if (sh->producer_stop) { stop = true; break; }
+        for (;;) {
+          int go = 1;
+          if (lane == 0) {
+            while (!mbar_try_wait(&empty[stage], par ^ 1u)) {
+              if (sh->producer_stop) { go = 0; break; }
+            }
+            if (sh->producer_stop) go = 0;
           }
-          if (stop) break;
-          if (sh->producer_stop) break;
-          issue(Tp, (int)(Tp % NT), stage);
+          go = __shfl_sync(0xffffffffu, go, 0);
+          if (!go) break;
+          issue(t, stage);
           ++Tp;
+          if (++t == NT) t = 0;
+          if (++stage == S) { stage = 0; par ^= 1u; }
         }
       }
       // drain: never leave the CTA with bulk copies still landing in its shared memory
-      const unsigned long long Tc = resident ? 0ull : (unsigned long long)sh->consumed;
-      for (unsigned long long Tg = Tc; Tg < Tp; ++Tg) {
-        const int stage = resident ? (int)Tg : (int)(Tg % S);
-        const uint32_t par = resident ? 0u : (uint32_t)((Tg / S) & 1);
-        while (!mbar_try_wait(&full[stage], par)) {}
+      if (lane == 0) {
+        const unsigned long long Tc = resident ? 0ull : (unsigned long long)sh->consumed;
+        for (unsigned long long Tg = Tc; Tg < Tp; ++Tg) {
+          const unsigned st = resident ? (unsigned)Tg : (unsigned)(Tg % S);
+          const uint32_t pp = resident ? 0u : (uint32_t)((Tg / S) & 1);
+          while (!mbar_try_wait(&full[st], pp)) {}
+        }
       }
     }
     return;
@@ -274,25 +293,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   const int ntypes = nu ? 4 : 2;
   const double Cbox = P.C;
 
-  const int lig = lane % C::LPR;
+  const int lig = lane % C::LPR;      // lane in group = which chunks of the row I own
   const int grp = lane / C::LPR;
-  const int rib = C::FINAL == 2 ? lane : grp * C::RPL + (lig >> 1);   // my row within a tile
+  const int rib = C::FINAL == 2 ? lane : grp * C::RPL + (lig >> 1);   // my row within a tile (epilogue)
   const bool lane_active = C::FINAL == 2 ? true : !(lig & 1);
 
   long long n_iter = 0;
   long long cold = 0;
+  unsigned tb_mod = 0, tb_div = 0;   // (tiles consumed so far) % S and / S, kept incrementally
   unsigned long long Tbase = 0;
   uint32_t epoch = 0;
   int status = 0;
   int converged = 0;
-  // leader-only state (warp 0, replicated in all its lanes)
-  double l_ai = 0, l_aj = 0, l_di = 0, l_dj = 0;
-  int l_i = -1, l_j = -1;
+  double l_di = 0, l_dj = 0;   // leader-only: last step ...
+  int l_i = -1, l_j = -1;      // ... its pair and new alphas (stored one sweep later, forwarded meanwhile)
+  double l_ai = 0, l_aj = 0;
+  long long cta_sweep_start_prev = 0;   // debug
 
   Cand best[NCAND];
   auto reset_best = [&]() {
 #pragma unroll
-    for (int k = 0; k < NCAND; ++k) { best[k].g = 0.0; best[k].idx = -1; }
+    for (int k = 0; k < NCAND; ++k) { best[k].g = 0.0; best[k].idx = -1; best[k].flags = 0; }
+  };
+  auto stamp = [&](int slot) {
+    if (P.timeline && cta == 0 && threadIdx.x == 0 && epoch >= 1 && epoch <= (uint32_t)TL_ITERS)
+      P.timeline[(epoch - 1) * TL_SLOTS + slot] = clock64();
+  };
+  auto load_row_state = [&](int t) {
+    RowState<T> r;
+    r.g0 = r.g1 = 0.0;
+    r.f0 = r.f1 = 0;
+    r.nt = 0;
+    const long long row = row0 + (long long)t * C::BR + rib;
+    if (t < NT && lane_active && row < row1) {
+      if (P.debug_flags & 2) {
+        r.g0 = __ldcg(G + row);
+        r.f0 = __ldcg(flags + row);
+        if (mirror) { r.g1 = __ldcg(G + row + l); r.f1 = __ldcg(flags + row + l); }
+      } else {
+        r.g0 = G[row];
+        r.f0 = flags[row];
+        if (mirror) { r.g1 = G[row + l]; r.f1 = flags[row + l]; }
+      }
+      r.nt = norms[row];
+    }
+    return r;
   };
 
   // ---- initial selection pass over G / flags only (no X) -------------------------------------
@@ -304,86 +349,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       if (mirror) consider(nu, flags[r + l], G[r + l], (int)(r + l), best);
     }
   }
+  RowState<T> pf = load_row_state(warp);   // first tile of the first sweep (tiles 0..NW-1 are static)
 
   for (;;) {
-    // ---- (B) block-level candidate reduce, publish, grid barrier, global reduce (leader) ------
+    // ---- (B) warp -> CTA candidate reduce, publish, exchange, global reduce (leader) ------------
     ++epoch;
+    stamp(0);   // this warp's sweep done
 #pragma unroll
     for (int k = 0; k < NCAND; ++k)
-      if (k < ntypes) warp_reduce_cand(best[k], (k & 1) == 0);
+      if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, best[k]);
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < NCAND; ++k) sh->wc[warp][k] = best[k];
     }
     named_bar_sync(1, NW * 32);
+    stamp(1);   // all warps of this CTA done
 
     if (warp == 0) {
-      // CTA-level winner per type -> record in global memory
-      Cand mine[NCAND];
-#pragma unroll
-      for (int k = 0; k < NCAND; ++k) {
-        if (lane < NW) mine[k] = sh->wc[lane][k];
-        else { mine[k].g = 0.0; mine[k].idx = -1; }
-        if (k < ntypes) warp_reduce_cand(mine[k], (k & 1) == 0);
-      }
-      if (lane < ntypes) {
-        Cand m = mine[0];
-#pragma unroll
-        for (int k = 1; k < NCAND; ++k)
-          if (lane == k) m = mine[k];
-        CandRec rec;
-        rec.g = m.g;
-        rec.idx = m.idx;
-        rec.alpha = 0.0;
-        rec.flags = 0;
-        rec.pad[0] = rec.pad[1] = 0;
-        if (m.idx >= 0) {   // the winner lives in this CTA's slice: same-SM coherent reads
-          rec.alpha = alpha[m.idx];
-          rec.flags = flags[m.idx];
+      // CTA-level winner per type -> tagged record in global memory (two types per pass, 16 lanes each)
+      for (int k0 = 0; k0 < ntypes; k0 += 2) {
+        const int k = k0 + (lane >> 4), src = lane & 15;
+        Cand m;
+        m.g = 0.0; m.idx = -1; m.flags = 0;
+        if (src < NW) m = sh->wc[src][k];
+        redux_select(lane < 16 ? 0x0000ffffu : 0xffff0000u, (k & 1) == 0, m);
+        if (src == 0) {
+          uint4* rp = P.cand + ((size_t)(epoch & 1) * ncta + cta) * NCAND + k;
+          st_relaxed_v4(rp, make_uint4((uint32_t)__double2loint(m.g), (uint32_t)__double2hiint(m.g), (uint32_t)m.idx,
+                                       (epoch << 3) | (uint32_t)m.flags));
         }
-        P.cand[((size_t)(epoch & 1) * P.ncta + cta) * NCAND + lane] = rec;
-        __threadfence();
       }
-      __syncwarp();
-      if (lane == 0) st_release_gpu(P.flag + cta, epoch);
+      if (lane == 0) sh->ticket = NW;   // next sweep: tiles 0..NW-1 are static, the rest are drawn here
+      stamp(2);   // published
+      if (P.timeline && threadIdx.x == 0 && epoch == 11u && cta < 160) {
+        P.timeline[TL_CTA_BASE + 2 * cta] = clock64() - cta_sweep_start_prev;
+        P.timeline[TL_CTA_BASE + 2 * cta + 1] = NT;
+      }
 
-      // wait for every CTA of this problem, fold their records
-      Winner w[NCAND];
-#pragma unroll
-      for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].alpha = 0.0; w[k].idx = -1; w[k].flags = 0; }
+      // read every CTA's record of this epoch (this is the grid barrier)
+      Cand w[NCAND];
       const uint64_t t_start = globaltimer_ns();
-      if (*(volatile int*)P.abort_flag) status = 1;
-      for (int c = lane; c < P.ncta && !status; c += 32) {
-        uint32_t polls = 0;
-        while (ld_acquire_gpu(P.flag + c) < epoch) {
-          if ((++polls & 255u) == 0) {
-            if (*(volatile int*)P.abort_flag) { status = 1; break; }
-            if (globaltimer_ns() - t_start > 4000000000ull) {
-              *(volatile int*)P.abort_flag = 1;
-              status = 1;
-              break;
+      uint32_t rounds = 0;
+      for (;;) {
+        bool all = true;
+#pragma unroll
+        for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; }
+        for (int c = lane; c < ncta; c += 32) {
+          const uint4* rp = P.cand + ((size_t)(epoch & 1) * ncta + c) * NCAND;
+#pragma unroll
+          for (int k = 0; k < NCAND; ++k) {
+            if (k < ntypes) {
+              const uint4 h = ld_relaxed_v4(rp + k);
+              if ((h.w >> 3) != epoch) {
+                all = false;
+              } else {
+                const double g = __hiloint2double((int)h.y, (int)h.x);
+                const int idx = (int)h.z;
+                const bool take = (k & 1) == 0 ? better_max(g, idx, w[k].g, w[k].idx) : better_min(g, idx, w[k].g, w[k].idx);
+                if (take) { w[k].g = g; w[k].idx = idx; w[k].flags = (int)(h.w & 7u); }
+              }
             }
           }
         }
-        if (status) break;
-        const CandRec* rp = P.cand + ((size_t)(epoch & 1) * P.ncta + c) * NCAND;
-#pragma unroll
-        for (int k = 0; k < NCAND; ++k) {
-          if (k < ntypes) {
-            const int4 lo = __ldcg(reinterpret_cast<const int4*>(rp + k));
-            const int4 hi = __ldcg(reinterpret_cast<const int4*>(rp + k) + 1);
-            const double g = __hiloint2double(lo.y, lo.x);
-            const double a = __hiloint2double(lo.w, lo.z);
-            const int idx = hi.x, f = hi.y;
-            const bool take = (k & 1) == 0 ? better_max(g, idx, w[k].g, w[k].idx) : better_min(g, idx, w[k].g, w[k].idx);
-            if (take) { w[k].g = g; w[k].alpha = a; w[k].idx = idx; w[k].flags = f; }
+        if (__all_sync(0xffffffffu, all)) break;
+        if ((++rounds & 63u) == 0) {
+          int bad = *(volatile int*)P.abort_flag;
+          if (!bad && globaltimer_ns() - t_start > 4000000000ull) {
+            *(volatile int*)P.abort_flag = 1;
+            bad = 1;
           }
+          if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
         }
       }
-      status = __any_sync(0xffffffffu, status) ? 1 : 0;
+      stamp(3);   // every CTA's record read
 #pragma unroll
       for (int k = 0; k < NCAND; ++k)
-        if (k < ntypes) warp_reduce_winner(w[k], (k & 1) == 0);
+        if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, w[k]);
+      stamp(4);   // global winners known
 
       // ---- decide the next pair (working_set_select) ------------------------------------------
       int si = -1, sj = -1;
@@ -402,8 +444,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       } else if (!nu) {
         // solver.py:66-75
         si = w[0].idx; sj = w[1].idx;
-        gi = w[0].g; gj = w[1].g; ai = w[0].alpha; aj = w[1].alpha; fi = w[0].flags; fj = w[1].flags;
+        gi = w[0].g; gj = w[1].g; fi = w[0].flags; fj = w[1].flags;
         stop_sel = si < 0 || sj < 0 || (gi - gj < P.tol);
+        if (!stop_sel) {
+          ai = si == l_i ? l_ai : (si == l_j ? l_aj : __ldcg(alpha + si));
+          aj = sj == l_i ? l_ai : (sj == l_j ? l_aj : __ldcg(alpha + sj));
+        }
       } else {
         // solver.py:300-339: no tol test, gain comparison between the class-wise pairs
         const bool pos_ok = w[0].idx >= 0 && w[1].idx >= 0;
@@ -440,18 +486,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           have_k = true;
         }
         if (pick >= 0) {
-          const Winner& a = pick == 0 ? w[0] : w[2];
-          const Winner& b = pick == 0 ? w[1] : w[3];
-          si = a.idx; sj = b.idx; gi = a.g; gj = b.g; ai = a.alpha; aj = b.alpha; fi = a.flags; fj = b.flags;
+          const Cand& a = pick == 0 ? w[0] : w[2];
+          const Cand& b = pick == 0 ? w[1] : w[3];
+          si = a.idx; sj = b.idx; gi = a.g; gj = b.g; fi = a.flags; fj = b.flags;
+          ai = si == l_i ? l_ai : (si == l_j ? l_aj : __ldcg(alpha + si));
+          aj = sj == l_i ? l_ai : (sj == l_j ? l_aj : __ldcg(alpha + sj));
         }
       }
 
+      if (P.dbg_steps && lane == 0 && epoch <= (uint32_t)DBG_EPOCHS) {
+        double* o = P.dbg_steps + ((size_t)(epoch - 1) * ncta + cta) * 6;
+        o[0] = si; o[1] = sj; o[2] = gi; o[3] = gj; o[4] = ai; o[5] = aj;
+      }
       if (stop_sel) converged = 1;
       const bool exit_now = status || stop_sel || n_iter >= P.max_iter;
       if (exit_now) {
         if (lane == 0) {
           sh->stop = 1;
           if (cta == 0) {
+            if (l_i >= 0) {   // the last step's alphas are still pending
+              alpha[l_i] = l_ai;
+              alpha[l_j] = l_aj;
+            }
             SolveResult r;
             r.n_iter = n_iter;
             r.last_i = stop_sel ? -1 : si;
@@ -473,7 +529,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         const double yi = (fi & F_YPOS) ? 1.0 : -1.0;
         const double yj = (fj & F_YPOS) ? 1.0 : -1.0;
         const StepOut so = smo_step(nu, (double)Kii, (double)Kjj, (double)Kij, yi, yj, gi, gj, ai, aj, Cbox);
-        l_ai = so.ai; l_aj = so.aj; l_di = so.di; l_dj = so.dj; l_i = si; l_j = sj;
+        if (lane == 0) {
+          sh->pi = l_i; sh->pj = l_j; sh->pai = l_ai; sh->paj = l_aj;
+        }
+        l_di = so.di; l_dj = so.dj; l_i = si; l_j = sj; l_ai = so.ai; l_aj = so.aj;
+        if (P.dbg_steps && lane == 0 && cta == 0 && epoch <= (uint32_t)DBG_EPOCHS) {
+          double* o = P.dbg_steps + (size_t)DBG_EPOCHS * ncta * 6 + (size_t)(epoch - 1) * 2;
+          o[0] = so.ai; o[1] = so.aj;
+        }
 #pragma unroll
         for (int q = 0; q < QL; ++q) {
           const int c = lane + 32 * q;
@@ -492,14 +555,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           sh->fj = make_flags(yj > 0, so.aj, Cbox);
         }
       }
+      stamp(5);   // leader done: step taken, x_i / x_j staged
     }
     named_bar_sync(2, NW * 32);   // (A) selection + step visible to all consumer warps
     if (sh->stop) break;
+    stamp(6);   // sweep starts
 
     // ---- sweep: both Q columns, gradient update, next candidates --------------------------------
     const double ci = sh->ci, cj = sh->cj;
     const int wi = sh->i, wj = sh->j, nfi = sh->fi, nfj = sh->fj;
-    const double nai = sh->ai, naj = sh->aj;
+    const int pvi = sh->pi, pvj = sh->pj;
+    const double pai = sh->pai, paj = sh->paj;
     const T ni = sh->ni, nj = sh->nj;
     V xi[C::CPL], xj[C::CPL];
 #pragma unroll
@@ -508,28 +574,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       xj[q] = xs[CH + lig + q * C::LPR];
     }
     reset_best();
+    long long cta_sweep_start = 0;
+    if (P.timeline && threadIdx.x == 0 && epoch == 10u) cta_sweep_start = clock64() + (long long)(ci == 123.456);
 
-    for (int t = warp; t < NT; t += NW) {
-      const unsigned long long Tg = Tbase + (unsigned long long)t;
-      const int stage = resident ? t : (int)(Tg % S);
-      const uint32_t par = resident ? 0u : (uint32_t)((Tg / S) & 1);
+    const bool dbg = P.timeline && cta == 0 && epoch == 10u;
+    const long long dbg_start = dbg ? clock64() : 0;
+    long long dbg_wait = 0;
+    int dbg_tiles = 0;
+    int t = warp;                       // first tile is static (its gradient state is already in pf)
+    while (t < NT) {
+      // draw the next tile now so its gradient state can be prefetched a full tile of work ahead
+      int tn = 0;
+      if (P.debug_flags & 1) {
+        tn = t + NW;
+      } else {
+        if (lane == 0) tn = atomicAdd(&sh->ticket, 1);
+        tn = __shfl_sync(0xffffffffu, tn, 0);
+      }
+      const RowState<T> cur = pf;
+      pf = load_row_state(tn);
+
+      unsigned stage, use = 0u;
+      if (resident) {
+        stage = (unsigned)t;
+      } else {
+        const unsigned q = tb_mod + (unsigned)t;
+        stage = q % S;
+        use = tb_div + q / S;
+      }
       const long long row = row0 + (long long)t * C::BR + rib;
       const bool valid = lane_active && row < row1;
-      double g0 = 0, g1 = 0;
-      int f0 = 0, f1 = 0;
-      T nt = 0;
-      if (valid) {
-        g0 = G[row];
-        f0 = flags[row];
-        nt = norms[row];
-        if (mirror) { g1 = G[row + l]; f1 = flags[row + l]; }
-      }
+      const long long dbg_w0 = dbg ? clock64() : 0;
       {
         uint32_t spins = 0;
-        while (!mbar_try_wait(&full[stage], par)) {
-          if ((++spins & 1023u) == 0 && *(volatile int*)P.abort_flag) break;
+        uint64_t t_wait = 0;
+        bool ok = false;
+        while (!ok) {
+          ok = (resident || gen[stage] == use) && mbar_try_wait(&full[stage], use & 1u);
+          if (!ok && (++spins & 1023u) == 0) {
+            if (*(volatile int*)P.abort_flag) break;
+            const uint64_t now = globaltimer_ns();
+            if (t_wait == 0) t_wait = now;
+            else if (now - t_wait > 4000000000ull) { *(volatile int*)P.abort_flag = 1; break; }
+          }
         }
       }
+      if (dbg) { dbg_wait += clock64() - dbg_w0; ++dbg_tiles; }
       const unsigned char* base = ring + (size_t)stage * C::TILE_BYTES + (size_t)grp * C::RPL * C::ROWB + lig * 16;
       T acc[C::NV];
 #pragma unroll
@@ -544,8 +634,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         }
       }
       TransposeReduce<T, C::NV, C::LPR / 2>::run(acc, lig);
-      __syncwarp();
-      if (!resident && lane == 0) mbar_arrive(&empty[stage]);
       T dti, dtj;
       if (C::FINAL == 2) {
         dti = acc[0];
@@ -555,30 +643,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         dti = (lig & 1) ? o : acc[0];
         dtj = (lig & 1) ? acc[0] : o;
       }
+      __syncwarp();
+      if (!resident && lane == 0) {
+        gen[stage] = use + 1u;
+        mbar_arrive(&empty[stage]);
+      }
       if (valid) {
-        const T kti = kernel_value(kp, dti, nt, ni);
-        const T ktj = kernel_value(kp, dtj, nt, nj);
+        const T kti = kernel_value(kp, dti, cur.nt, ni);
+        const T ktj = kernel_value(kp, dtj, cur.nt, nj);
         // y_t * (delta_i Q_i[t] + delta_j Q_j[t]) = (y_i delta_i) K_ti + (y_j delta_j) K_tj   (solver.py:146)
         const double c = ci * (double)kti + cj * (double)ktj;
         {
           const int v = (int)row;
-          const double g = g0 - c;
+          const double g = cur.g0 - c;
           G[v] = g;
-          int f = f0;
-          if (v == wi) { f = nfi; alpha[v] = nai; flags[v] = (uint8_t)nfi; }
-          else if (v == wj) { f = nfj; alpha[v] = naj; flags[v] = (uint8_t)nfj; }
+          int f = cur.f0;
+          if (v == wi) { f = nfi; flags[v] = (uint8_t)nfi; }
+          else if (v == wj) { f = nfj; flags[v] = (uint8_t)nfj; }
+          if (v == pvi) { alpha[v] = pai; __threadfence(); }
+          else if (v == pvj) { alpha[v] = paj; __threadfence(); }
           consider(nu, f, g, v, best);
         }
         if (mirror) {
           const int v = (int)(row + l);
-          const double g = g1 - c;
+          const double g = cur.g1 - c;
           G[v] = g;
-          int f = f1;
-          if (v == wi) { f = nfi; alpha[v] = nai; flags[v] = (uint8_t)nfi; }
-          else if (v == wj) { f = nfj; alpha[v] = naj; flags[v] = (uint8_t)nfj; }
+          int f = cur.f1;
+          if (v == wi) { f = nfi; flags[v] = (uint8_t)nfi; }
+          else if (v == wj) { f = nfj; flags[v] = (uint8_t)nfj; }
+          if (v == pvi) { alpha[v] = pai; __threadfence(); }
+          else if (v == pvj) { alpha[v] = paj; __threadfence(); }
           consider(nu, f, g, v, best);
         }
       }
+      t = tn;
+    }
+    if (cta_sweep_start) cta_sweep_start_prev = cta_sweep_start;
+    if (dbg && lane == 0) {
+      long long* o = P.timeline + TL_ITERS * TL_SLOTS + warp * TL_WARP_SLOTS;
+      o[0] = dbg_start; o[1] = clock64(); o[2] = dbg_tiles; o[3] = dbg_wait;
+    }
+    pf = load_row_state(warp);   // first tile of the next sweep (after this thread's own stores to it)
+    if (!resident) {
+      const unsigned q = tb_mod + (unsigned)NT;
+      tb_mod = q % S;
+      tb_div = tb_div + q / S;
     }
     Tbase += (unsigned long long)NT;
     ++n_iter;
