@@ -143,7 +143,7 @@ class BiKernelSVC(BiLinearSVC):
         return QColumns(X, y, spec, mirror=mirror), spec, None
 
     def fit(self, X, y):
-        X, y = np.array(X), np.array(y, dtype=float)
+        X, y = np.asarray(X), np.array(y, dtype=float)     # X is never written: no host copy needed
         y[y != 1] = -1
         l, self.n_features = X.shape
         p = -np.ones(l)
