@@ -138,6 +138,9 @@ int b2svm_solve(b2svm_handle* h, int64_t max_iter, b2svm_solve_stats* stats);
 /* Solver.calculate_rho (solver.py:149-177) and NuSolver.calculate_rho_b (solver.py:378-419). */
 int b2svm_rho(b2svm_handle* h, double* rho);
 int b2svm_rho_b(b2svm_handle* h, double* rho, double* b);
+/* The same statistics un-combined (host double[18]: sums, counts, extremes), for a row-sharded solve
+ * whose ranks merge them before forming rho / (rho, b). */
+int b2svm_bias_partials(b2svm_handle* h, double* out);
 
 /* decision_function core (svc.py:269-272, :436-439; svr.py:191-194, :297-300; oc_svm.py:108-111):
  *   out[q] = sum_s coef[s] * K(Xa[s], Xb[q])      (no n_a x n_b matrix is materialised)
@@ -167,6 +170,12 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
  * its peers' mailboxes before the first solve. */
 int b2svm_mailbox_export(b2svm_handle* h, void* ipc_handle_out /* 64 bytes */);
 int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles /* world * 64 bytes */);
+/* Multi-GPU only, before EVERY b2svm_solve: clears this rank's mailbox and publishes its alpha slice.
+ * The host then runs a barrier over all ranks (torch.distributed) and calls b2svm_solve on each.
+ * Shards are equal slices of whole 32-row tiles: rank r owns global rows
+ * [r*rpr, min(n, (r+1)*rpr)), rpr = roundup32(ceil(n_rows_global / world)); y, alpha, neg_y_grad of a
+ * mirror problem are laid out [first half | second half] of the LOCAL rows. */
+int b2svm_prepare(b2svm_handle* h);
 
 #ifdef __cplusplus
 }

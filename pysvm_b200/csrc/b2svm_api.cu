@@ -179,6 +179,16 @@ __global__ void finish_gradient_kernel(const double* __restrict__ y, const doubl
   }
 }
 
+// published alpha of a shard: [first half | second half], each rows_per_rank long (the peers index it
+// without knowing this rank's row count)
+__global__ void publish_alpha_kernel(const double* __restrict__ alpha, int64_t l, int64_t nv, int64_t rpr,
+                                     double* __restrict__ pub) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    const bool second = v >= l;
+    pub[(second ? rpr : 0) + (second ? v - l : v)] = alpha[v];
+  }
+}
+
 }  // namespace b2svm
 
 using namespace b2svm;
@@ -211,6 +221,13 @@ struct b2svm_handle {
   long long ntiles = 0;
   size_t smem_bytes = 0;
   int launches = 0;
+  // ---- row-sharded multi-GPU: one IPC-shareable block [mailbox | norms | published alpha | X slice]
+  unsigned char* block = nullptr;
+  size_t block_bytes = 0, off_norms = 0, off_alpha = 0, off_x = 0;
+  long long rows_per_rank = 0;
+  std::vector<void*> peer_blocks;          // opened IPC mappings (nullptr for this rank)
+  void** peer_tables = nullptr;            // device: [4][world] = mbox, X, norms, alpha pointers of every rank
+  bool attached = false, prepared = false;
   long long* timeline = nullptr;   // debug: set by B2SVM_TIMELINE=1
   double* dbg_steps = nullptr;     // debug: set by B2SVM_DEBUG_STEPS=1
 };
@@ -328,19 +345,57 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.max_iter = max_iter;
   P.forced_i = fi;
   P.forced_j = fj;
+  P.world = h->d.world > 1 ? h->d.world : 1;
+  P.rank = h->d.world > 1 ? h->d.rank : 0;
+  P.row_offset = h->d.world > 1 ? h->d.row_offset : 0;
+  P.l_global = h->d.world > 1 ? h->d.n_rows_global : h->d.n_rows;
+  P.rows_per_rank = h->d.world > 1 ? h->rows_per_rank : h->d.n_rows;
+  if (h->d.world > 1) {
+    P.mbox = reinterpret_cast<uint4*>(h->block);
+    P.peer_mbox = reinterpret_cast<uint4* const*>(h->peer_tables);
+    P.peer_X = reinterpret_cast<const void* const*>(h->peer_tables + h->d.world);
+    P.peer_norms = reinterpret_cast<const void* const*>(h->peer_tables + 2 * h->d.world);
+    P.peer_alpha = reinterpret_cast<const double* const*>(h->peer_tables + 3 * h->d.world);
+    P.alpha_pub = reinterpret_cast<double*>(h->block + h->off_alpha);
+  }
   P.timeline = h->timeline;
   P.dbg_steps = h->dbg_steps;
   P.debug_flags = getenv("B2SVM_DEBUG_FLAGS") ? atoi(getenv("B2SVM_DEBUG_FLAGS")) : 0;
 }
 
 // one persistent launch for one handle; fills *res from the device result
-int run_solver(b2svm_handle* h, long long max_iter, long long fi, long long fj, SolveResult* res, float* ms) {
+// everything that must be in place before the persistent kernel starts; with several GPUs the host
+// puts a barrier over all ranks between this and the launch (a peer must not write into a mailbox
+// that is still being cleared, nor read a published alpha that is still being copied)
+int prepare_launch(b2svm_handle* h) {
   B2_CUDA(cudaSetDevice(h->d.device));
   const int64_t nv = h->d.n_vars;
   refresh_flags_kernel<<<grid_for(nv), 256, 0, h->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, nv);
   B2_CUDA(cudaGetLastError());
   B2_CUDA(cudaMemsetAsync(h->cand, 0, h->cand_bytes, h->stream));
   B2_CUDA(cudaMemsetAsync(h->abort_flag, 0, sizeof(int), h->stream));
+  if (h->d.world > 1) {
+    B2_CUDA(cudaMemsetAsync(h->block, 0, h->off_norms, h->stream));
+    publish_alpha_kernel<<<grid_for(nv), 256, 0, h->stream>>>(h->d.alpha, h->d.n_rows, nv, h->rows_per_rank,
+                                                              reinterpret_cast<double*>(h->block + h->off_alpha));
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  h->prepared = true;
+  return B2SVM_OK;
+}
+
+int run_solver(b2svm_handle* h, long long max_iter, long long fi, long long fj, SolveResult* res, float* ms) {
+  B2_CUDA(cudaSetDevice(h->d.device));
+  if (h->d.world > 1) {
+    if (!h->attached) return fail(B2SVM_E_INVALID, "multi-GPU handle: call b2svm_mailbox_attach first");
+    if (!h->prepared) return fail(B2SVM_E_INVALID, "multi-GPU handle: call b2svm_prepare on every rank, then a barrier, before each solve");
+    if (fi >= 0) return fail(B2SVM_E_UNSUPPORTED, "step-wise update is single-GPU only");
+  } else {
+    int rc0 = prepare_launch(h);
+    if (rc0) return rc0;
+  }
+  h->prepared = false;
   ProblemDev P;
   memset(&P, 0, sizeof(P));
   fill_problem(h, P, max_iter, fi, fj);
@@ -379,7 +434,10 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
   if (!desc->X || !desc->y || !desc->alpha || !desc->neg_y_grad) return fail(B2SVM_E_INVALID, "null device pointer");
   if (desc->x_dtype != B2SVM_F32 && desc->x_dtype != B2SVM_F64) return fail(B2SVM_E_INVALID, "bad x_dtype");
   if (desc->kernel.kind < 0 || desc->kernel.kind > 3) return fail(B2SVM_E_INVALID, "bad kernel kind");
-  if (desc->world > 1) return fail(B2SVM_E_UNSUPPORTED, "row-sharded multi-GPU solve not built yet");
+  if (desc->world > 1) {
+    if (desc->world > 8) return fail(B2SVM_E_UNSUPPORTED, "at most 8 ranks (one NVSwitch box)");
+    if (desc->rank < 0 || desc->rank >= desc->world) return fail(B2SVM_E_INVALID, "bad rank");
+  }
   const int ch = chunks_for(desc->x_dtype, desc->n_features);
   if (ch == 0) return fail(B2SVM_E_UNSUPPORTED, "n_features above the compiled maximum (512 f32 / 256 f64)");
 
@@ -406,21 +464,43 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     if (_e != cudaSuccess) return cleanup_fail(B2SVM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
-  const bool in_place = desc->ldx == h->dp && desc->n_features == h->dp && ((uintptr_t)desc->X % 16 == 0);
+  if (desc->world > 1) {
+    // equal slices of whole tiles: rank r owns global rows [r * rpr, min(n, (r + 1) * rpr))
+    const long long rpr = (((desc->n_rows_global + desc->world - 1) / desc->world) + 31) / 32 * 32;
+    h->rows_per_rank = rpr;
+    const long long want = std::min<long long>(rpr, desc->n_rows_global - (long long)desc->rank * rpr);
+    if (desc->row_offset != (long long)desc->rank * rpr || desc->n_rows != want)
+      return cleanup_fail(B2SVM_E_INVALID, "shard must be rows [rank*rpr, min(n,(rank+1)*rpr)), rpr = roundup32(ceil(n/world))");
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    h->off_norms = up(sizeof(uint4) * 2 * desc->world * NCAND);
+    h->off_alpha = h->off_norms + up((size_t)rpr * esz);
+    h->off_x = h->off_alpha + up((size_t)2 * rpr * sizeof(double));
+    h->block_bytes = h->off_x + (size_t)rpr * h->dp * esz;
+    B2_TRY(cudaMalloc(&h->block, h->block_bytes));
+    B2_TRY(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
+  }
+  const bool in_place = desc->world <= 1 && desc->ldx == h->dp && desc->n_features == h->dp && ((uintptr_t)desc->X % 16 == 0);
   if (in_place) {
     h->Xuse = desc->X;
   } else {
-    B2_TRY(cudaMalloc(&h->Xown, (size_t)l * h->dp * esz));
+    void* xdst = nullptr;
+    if (desc->world > 1) {
+      xdst = h->block + h->off_x;
+    } else {
+      B2_TRY(cudaMalloc(&h->Xown, (size_t)l * h->dp * esz));
+      xdst = h->Xown;
+    }
     if (h->f64)
       pad_rows_kernel<double><<<grid_for(l * h->dp), 256, 0, h->stream>>>((const double*)desc->X, desc->ldx,
-                                                                          (double*)h->Xown, l, desc->n_features, h->dp);
+                                                                          (double*)xdst, l, desc->n_features, h->dp);
     else
       pad_rows_kernel<float><<<grid_for(l * h->dp), 256, 0, h->stream>>>((const float*)desc->X, desc->ldx,
-                                                                         (float*)h->Xown, l, desc->n_features, h->dp);
+                                                                         (float*)xdst, l, desc->n_features, h->dp);
     B2_TRY(cudaGetLastError());
-    h->Xuse = h->Xown;
+    h->Xuse = xdst;
   }
-  B2_TRY(cudaMalloc(&h->norms, (size_t)l * esz));
+  if (desc->world > 1) h->norms = h->block + h->off_norms;
+  else B2_TRY(cudaMalloc(&h->norms, (size_t)l * esz));
   if (h->f64)
     row_norms_kernel<double><<<grid_for(l * 32), 256, 0, h->stream>>>((const double*)h->Xuse, l, h->dp, (double*)h->norms);
   else
@@ -459,7 +539,11 @@ int b2svm_destroy(b2svm_handle* h) {
   cudaSetDevice(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream); else cudaDeviceSynchronize();
   cudaFree(h->Xown);
-  cudaFree(h->norms);
+  if (!h->block) cudaFree(h->norms);
+  for (void* pb : h->peer_blocks)
+    if (pb) cudaIpcCloseMemHandle(pb);
+  cudaFree(h->peer_tables);
+  cudaFree(h->block);
   cudaFree(h->flags);
   cudaFree(h->cand);
   cudaFree(h->abort_flag);
@@ -594,6 +678,29 @@ static int bias_stats(b2svm_handle* h, BiasStats* host) {
   return B2SVM_OK;
 }
 
+/* Raw ingredients of calculate_rho / calculate_rho_b over THIS handle's variables, so that a
+ * row-sharded solve can combine them across ranks (sums and counts add, extremes min / max):
+ * out[0..5]  = sum_free, cnt_free, min_lb, cnt_lb, max_ub, cnt_ub            (solver.py:160-177)
+ * out[6+6c..] = nsum, ncnt, nmax_hi, nhi, nmin_lo, nlo for class c = 0 (+1), 1 (-1)   (solver.py:378-419)
+ * Empty extremes are reported as +inf (min) / -inf (max). */
+int b2svm_bias_partials(b2svm_handle* h, double* out /* host [18] */) {
+  if (!h || !out) return fail(B2SVM_E_INVALID, "null argument");
+  BiasStats s;
+  int rc = bias_stats(h, &s);
+  if (rc) return rc;
+  const double inf = INFINITY;
+  out[0] = s.sum_free; out[1] = (double)s.cnt_free;
+  out[2] = s.cnt_lb ? s.min_lb : inf; out[3] = (double)s.cnt_lb;
+  out[4] = s.cnt_ub ? s.max_ub : -inf; out[5] = (double)s.cnt_ub;
+  for (int c = 0; c < 2; ++c) {
+    double* o = out + 6 + 6 * c;
+    o[0] = s.nsum[c]; o[1] = (double)s.ncnt[c];
+    o[2] = s.nhi[c] ? s.nmax_hi[c] : -inf; o[3] = (double)s.nhi[c];
+    o[4] = s.nlo[c] ? s.nmin_lo[c] : inf; o[5] = (double)s.nlo[c];
+  }
+  return B2SVM_OK;
+}
+
 int b2svm_rho(b2svm_handle* h, double* rho) {
   if (!h || !rho) return fail(B2SVM_E_INVALID, "null argument");
   BiasStats s;
@@ -705,7 +812,49 @@ int b2svm_debug_steps(b2svm_handle* h, double* out, int epochs) {
   return B2SVM_OK;
 }
 
-int b2svm_mailbox_export(b2svm_handle*, void*) { return fail(B2SVM_E_UNSUPPORTED, "row-sharded multi-GPU solve not built yet"); }
-int b2svm_mailbox_attach(b2svm_handle*, const void*) { return fail(B2SVM_E_UNSUPPORTED, "row-sharded multi-GPU solve not built yet"); }
+int b2svm_mailbox_export(b2svm_handle* h, void* ipc_handle_out) {
+  if (!h || !ipc_handle_out) return fail(B2SVM_E_INVALID, "null argument");
+  if (h->d.world <= 1 || !h->block) return fail(B2SVM_E_INVALID, "not a multi-GPU handle");
+  B2_CUDA(cudaSetDevice(h->d.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t mh;
+  B2_CUDA(cudaIpcGetMemHandle(&mh, h->block));
+  memcpy(ipc_handle_out, &mh, sizeof(mh));
+  return B2SVM_OK;
+}
+
+int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles) {
+  if (!h || !ipc_handles) return fail(B2SVM_E_INVALID, "null argument");
+  if (h->d.world <= 1 || !h->block) return fail(B2SVM_E_INVALID, "not a multi-GPU handle");
+  if (h->attached) return B2SVM_OK;
+  B2_CUDA(cudaSetDevice(h->d.device));
+  const int world = h->d.world;
+  h->peer_blocks.assign(world, nullptr);
+  std::vector<void*> tab(4 * (size_t)world);
+  for (int r = 0; r < world; ++r) {
+    unsigned char* base = h->block;
+    if (r != h->d.rank) {
+      cudaIpcMemHandle_t mh;
+      memcpy(&mh, reinterpret_cast<const unsigned char*>(ipc_handles) + 64 * (size_t)r, sizeof(mh));
+      void* p = nullptr;
+      B2_CUDA(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_blocks[r] = p;
+      base = reinterpret_cast<unsigned char*>(p);
+    }
+    tab[r] = base;                              // mailbox
+    tab[world + r] = base + h->off_x;           // X slice
+    tab[2 * world + r] = base + h->off_norms;   // norms
+    tab[3 * world + r] = base + h->off_alpha;   // published alpha
+  }
+  B2_CUDA(cudaMalloc(&h->peer_tables, sizeof(void*) * tab.size()));
+  B2_CUDA(cudaMemcpy(h->peer_tables, tab.data(), sizeof(void*) * tab.size(), cudaMemcpyHostToDevice));
+  h->attached = true;
+  return B2SVM_OK;
+}
+
+int b2svm_prepare(b2svm_handle* h) {
+  if (!h) return fail(B2SVM_E_INVALID, "null handle");
+  return prepare_launch(h);
+}
 
 }  // extern "C"

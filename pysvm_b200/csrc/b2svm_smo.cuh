@@ -72,6 +72,15 @@ struct ProblemDev {
   long long max_iter;
   long long forced_i, forced_j;   // >= 0: skip the initial selection and take this pair first
   long long* timeline;            // optional [TL_ITERS][TL_SLOTS] clock64 stamps of CTA 0's leader lane
+  // ---- row-sharded multi-GPU (world > 1): this GPU owns global rows [row_offset, row_offset + l) --------
+  int world, rank;
+  long long row_offset, l_global, rows_per_rank;   // every rank's slice starts at rank * rows_per_rank
+  uint4* mbox;                    // local mailbox [2][world][NCAND], written by the peers over NVLink
+  uint4* const* peer_mbox;        // [world] every rank's mailbox (peer mapping; own entry = local)
+  const void* const* peer_X;      // [world] every rank's padded X slice
+  const void* const* peer_norms;  // [world]
+  const double* const* peer_alpha;   // [world] every rank's published alpha [2][rows_per_rank]
+  double* alpha_pub;              // this rank's published alpha (the peers read it)
   double* dbg_steps;              // optional [DBG_EPOCHS][ncta][6] = si, sj, gi, gj, ai, aj seen by each leader
   int debug_flags;                // B2SVM_DEBUG_FLAGS: 1 = static tile assignment, 2 = L2 loads for G/flags
 };
@@ -132,26 +141,52 @@ __device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (
   }
 }
 
-// Leader warp: load rows ra, rb (16-byte chunks spread over the lanes) and evaluate
+// Where variable `idx` lives: its row in the owner's X slice, its norm, its published alpha.
+template <typename T>
+struct VarRef {
+  const typename Chunk<T>::V* row;
+  const T* norm;
+  const double* alpha;     // nullptr on a single GPU (the caller's alpha array is used)
+  int owner;
+};
+template <typename T, int CH>
+__device__ __forceinline__ VarRef<T> locate(const ProblemDev& P, int idx) {
+  using V = typename Chunk<T>::V;
+  VarRef<T> r;
+  const bool second = P.mirror && idx >= P.l_global;
+  const long long grow = second ? idx - P.l_global : idx;
+  if (P.world == 1) {
+    r.owner = 0;
+    r.row = reinterpret_cast<const V*>(P.X) + grow * CH;
+    r.norm = reinterpret_cast<const T*>(P.norms) + grow;
+    r.alpha = nullptr;
+  } else {
+    const int rk = (int)(grow / P.rows_per_rank);
+    const long long lrow = grow - (long long)rk * P.rows_per_rank;
+    r.owner = rk;
+    r.row = reinterpret_cast<const V*>(P.peer_X[rk]) + lrow * CH;
+    r.norm = reinterpret_cast<const T*>(P.peer_norms[rk]) + lrow;
+    r.alpha = P.peer_alpha[rk] + (second ? P.rows_per_rank : 0) + lrow;
+  }
+  return r;
+}
+
+// Leader warp: load rows a, b (16-byte chunks spread over the lanes) and evaluate
 // K(a,a), K(b,b), K(a,b) in T.  Chunks stay in xa / xb for the caller.
 template <typename T, int CH>
-__device__ __forceinline__ void pair_kernels(const ProblemDev& P, const KernelParams<T>& kp, long long ra,
-                                             long long rb, int lane, typename Chunk<T>::V (&xa)[(CH + 31) / 32],
+__device__ __forceinline__ void pair_kernels(const KernelParams<T>& kp, const VarRef<T>& A, const VarRef<T>& B,
+                                             int lane, typename Chunk<T>::V (&xa)[(CH + 31) / 32],
                                              typename Chunk<T>::V (&xb)[(CH + 31) / 32], T& na, T& nb, T& Kaa,
                                              T& Kbb, T& Kab) {
   using CK = Chunk<T>;
-  using V = typename CK::V;
   constexpr int Q = (CH + 31) / 32;
-  const V* Xa = reinterpret_cast<const V*>(P.X) + ra * CH;
-  const V* Xb = reinterpret_cast<const V*>(P.X) + rb * CH;
-  const T* norms = reinterpret_cast<const T*>(P.norms);
-  na = __ldg(norms + ra);
-  nb = __ldg(norms + rb);
+  na = *A.norm;
+  nb = *B.norm;
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
     const int c = lane + 32 * q;
-    xa[q] = (c < CH) ? __ldg(Xa + c) : CK::zero();
-    xb[q] = (c < CH) ? __ldg(Xb + c) : CK::zero();
+    xa[q] = (c < CH) ? A.row[c] : CK::zero();
+    xb[q] = (c < CH) ? B.row[c] : CK::zero();
   }
   T daa = 0, dbb = 0, dab = 0;
 #pragma unroll
@@ -212,6 +247,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   const bool nu = P.nu != 0;
   const bool mirror = P.mirror != 0;
   const long long l = P.l;
+  const long long goff = P.row_offset, lg = P.l_global;   // global variable index = goff + row (+ lg)
+  const int world = P.world;
 
   if (threadIdx.x == 0) {
     for (unsigned s = 0; s < S; ++s) {
@@ -319,6 +356,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     if (P.timeline && cta == 0 && threadIdx.x == 0 && epoch >= 1 && epoch <= (uint32_t)TL_ITERS)
       P.timeline[(epoch - 1) * TL_SLOTS + slot] = clock64();
   };
+  // alpha of any variable: the caller's array on one GPU, the owner's published copy otherwise
+  auto read_alpha = [&](int idx) -> double {
+    if (world == 1) return __ldcg(alpha + idx);
+    return ld_relaxed_sys_f64(locate<T, CH>(P, idx).alpha);
+  };
+  // deferred store of a step's new alpha by the lane that owns the variable (local index lv)
+  auto store_alpha = [&](long long lv, bool second, long long lrow, double a) {
+    alpha[lv] = a;
+    if (world > 1) {
+      P.alpha_pub[(second ? P.rows_per_rank : 0) + lrow] = a;
+      __threadfence_system();
+    } else {
+      __threadfence();
+    }
+  };
   auto load_row_state = [&](int t) {
     RowState<T> r;
     r.g0 = r.g1 = 0.0;
@@ -345,8 +397,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   const bool forced = P.forced_i >= 0;
   if (!forced) {
     for (long long r = row0 + warp * 32 + lane; r < row1; r += NW * 32) {
-      consider(nu, flags[r], G[r], (int)r, best);
-      if (mirror) consider(nu, flags[r + l], G[r + l], (int)(r + l), best);
+      consider(nu, flags[r], G[r], (int)(r + goff), best);
+      if (mirror) consider(nu, flags[r + l], G[r + l], (int)(r + goff + lg), best);
     }
   }
   RowState<T> pf = load_row_state(warp);   // first tile of the first sweep (tiles 0..NW-1 are static)
@@ -425,6 +477,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
 #pragma unroll
       for (int k = 0; k < NCAND; ++k)
         if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, w[k]);
+      if (world > 1) {
+        // ---- cross-GPU exchange over NVLink: CTA 0 pushes this GPU's winners into every rank's mailbox
+        // (16-byte tagged records again), every leader polls the local mailbox, same reduction.
+        if (cta == 0 && lane < world * ntypes) {
+          const int r = lane / ntypes, k = lane - r * ntypes;
+          Cand m = w[0];
+#pragma unroll
+          for (int kk = 1; kk < NCAND; ++kk)
+            if (k == kk) m = w[kk];
+          uint4* rp = const_cast<uint4*>(P.peer_mbox[r]) + ((size_t)(epoch & 1) * world + P.rank) * NCAND + k;
+          st_relaxed_sys_v4(rp, make_uint4((uint32_t)__double2loint(m.g), (uint32_t)__double2hiint(m.g), (uint32_t)m.idx,
+                                           (epoch << 3) | (uint32_t)m.flags));
+        }
+        uint32_t rounds2 = 0;
+        for (;;) {
+          bool all = true;
+#pragma unroll
+          for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; }
+          for (int r = lane; r < world; r += 32) {
+            const uint4* rp = P.mbox + ((size_t)(epoch & 1) * world + r) * NCAND;
+#pragma unroll
+            for (int k = 0; k < NCAND; ++k) {
+              if (k < ntypes) {
+                const uint4 h = ld_relaxed_sys_v4(rp + k);
+                if ((h.w >> 3) != epoch) {
+                  all = false;
+                } else {
+                  const double g = __hiloint2double((int)h.y, (int)h.x);
+                  const int idx = (int)h.z;
+                  const bool take = (k & 1) == 0 ? better_max(g, idx, w[k].g, w[k].idx) : better_min(g, idx, w[k].g, w[k].idx);
+                  if (take) { w[k].g = g; w[k].idx = idx; w[k].flags = (int)(h.w & 7u); }
+                }
+              }
+            }
+          }
+          if (__all_sync(0xffffffffu, all)) break;
+          if ((++rounds2 & 63u) == 0) {
+            int bad = *(volatile int*)P.abort_flag;
+            if (!bad && globaltimer_ns() - t_start > 8000000000ull) {
+              *(volatile int*)P.abort_flag = 1;
+              bad = 1;
+            }
+            if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < NCAND; ++k)
+          if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, w[k]);
+      }
       stamp(4);   // global winners known
 
       // ---- decide the next pair (working_set_select) ------------------------------------------
@@ -436,7 +537,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       T ni = 0, nj = 0, Kii = 0, Kjj = 0, Kij = 0;
       bool have_k = false;
       if (forced && epoch == 1) {
-        si = (int)P.forced_i;
+        si = (int)P.forced_i;     // single GPU only (checked on the host)
         sj = (int)P.forced_j;
         gi = __ldcg(G + si); gj = __ldcg(G + sj);
         ai = __ldcg(alpha + si); aj = __ldcg(alpha + sj);
@@ -447,8 +548,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         gi = w[0].g; gj = w[1].g; fi = w[0].flags; fj = w[1].flags;
         stop_sel = si < 0 || sj < 0 || (gi - gj < P.tol);
         if (!stop_sel) {
-          ai = si == l_i ? l_ai : (si == l_j ? l_aj : __ldcg(alpha + si));
-          aj = sj == l_i ? l_ai : (sj == l_j ? l_aj : __ldcg(alpha + sj));
+          ai = si == l_i ? l_ai : (si == l_j ? l_aj : read_alpha(si));
+          aj = sj == l_i ? l_ai : (sj == l_j ? l_aj : read_alpha(sj));
         }
       } else {
         // solver.py:300-339: no tol test, gain comparison between the class-wise pairs
@@ -461,16 +562,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         else {
           V xa[QL], xb[QL];
           T na, nb, Kaa, Kbb, Kab;
-          const long long rpa = w[0].idx >= l && mirror ? w[0].idx - l : w[0].idx;
-          const long long rpb = w[1].idx >= l && mirror ? w[1].idx - l : w[1].idx;
-          pair_kernels<T, CH>(P, kp, rpa, rpb, lane, xa, xb, na, nb, Kaa, Kbb, Kab);
+          pair_kernels<T, CH>(kp, locate<T, CH>(P, w[0].idx), locate<T, CH>(P, w[1].idx), lane, xa, xb, na, nb, Kaa, Kbb,
+                              Kab);
           double quad_p = ((double)Kaa + (double)Kbb) - 2.0 * (double)Kab;
           if (quad_p <= 0) quad_p = 1e-12;
           const double dp = w[0].g - w[1].g;
           const double gain_p = -(dp * dp) / quad_p;
-          const long long rna = w[2].idx >= l && mirror ? w[2].idx - l : w[2].idx;
-          const long long rnb = w[3].idx >= l && mirror ? w[3].idx - l : w[3].idx;
-          pair_kernels<T, CH>(P, kp, rna, rnb, lane, xi, xj, ni, nj, Kii, Kjj, Kij);
+          pair_kernels<T, CH>(kp, locate<T, CH>(P, w[2].idx), locate<T, CH>(P, w[3].idx), lane, xi, xj, ni, nj, Kii, Kjj,
+                              Kij);
           double quad_n = ((double)Kii + (double)Kjj) - 2.0 * (double)Kij;
           if (quad_n <= 0) quad_n = 1e-12;
           const double dn = w[2].g - w[3].g;
@@ -489,8 +588,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           const Cand& a = pick == 0 ? w[0] : w[2];
           const Cand& b = pick == 0 ? w[1] : w[3];
           si = a.idx; sj = b.idx; gi = a.g; gj = b.g; fi = a.flags; fj = b.flags;
-          ai = si == l_i ? l_ai : (si == l_j ? l_aj : __ldcg(alpha + si));
-          aj = sj == l_i ? l_ai : (sj == l_j ? l_aj : __ldcg(alpha + sj));
+          ai = si == l_i ? l_ai : (si == l_j ? l_aj : read_alpha(si));
+          aj = sj == l_i ? l_ai : (sj == l_j ? l_aj : read_alpha(sj));
         }
       }
 
@@ -504,9 +603,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         if (lane == 0) {
           sh->stop = 1;
           if (cta == 0) {
-            if (l_i >= 0) {   // the last step's alphas are still pending
-              alpha[l_i] = l_ai;
-              alpha[l_j] = l_aj;
+            if (l_i >= 0) {   // the last step's alphas are still pending: each rank flushes what it owns
+              const int pend[2] = {l_i, l_j};
+              const double pval[2] = {l_ai, l_aj};
+              for (int q = 0; q < 2; ++q) {
+                const bool second = mirror && pend[q] >= lg;
+                const long long lrow = (second ? pend[q] - lg : pend[q]) - goff;
+                if (lrow >= 0 && lrow < l) {
+                  alpha[(second ? l : 0) + lrow] = pval[q];
+                  if (world > 1) P.alpha_pub[(second ? P.rows_per_rank : 0) + lrow] = pval[q];
+                }
+              }
             }
             SolveResult r;
             r.n_iter = n_iter;
@@ -523,9 +630,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         }
       } else {
         // ---- Solver.update / NuSolver.update: the analytic step (solver.py:82-145, 342-373) ----
-        const long long ri = (mirror && si >= l) ? si - l : si;
-        const long long rj = (mirror && sj >= l) ? sj - l : sj;
-        if (!have_k) pair_kernels<T, CH>(P, kp, ri, rj, lane, xi, xj, ni, nj, Kii, Kjj, Kij);
+        if (!have_k)
+          pair_kernels<T, CH>(kp, locate<T, CH>(P, si), locate<T, CH>(P, sj), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
         const double yi = (fi & F_YPOS) ? 1.0 : -1.0;
         const double yj = (fj & F_YPOS) ? 1.0 : -1.0;
         const StepOut so = smo_step(nu, (double)Kii, (double)Kjj, (double)Kij, yi, yj, gi, gj, ai, aj, Cbox);
@@ -654,25 +760,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         // y_t * (delta_i Q_i[t] + delta_j Q_j[t]) = (y_i delta_i) K_ti + (y_j delta_j) K_tj   (solver.py:146)
         const double c = ci * (double)kti + cj * (double)ktj;
         {
-          const int v = (int)row;
+          const int v = (int)(row + goff);
           const double g = cur.g0 - c;
-          G[v] = g;
+          G[row] = g;
           int f = cur.f0;
-          if (v == wi) { f = nfi; flags[v] = (uint8_t)nfi; }
-          else if (v == wj) { f = nfj; flags[v] = (uint8_t)nfj; }
-          if (v == pvi) { alpha[v] = pai; __threadfence(); }
-          else if (v == pvj) { alpha[v] = paj; __threadfence(); }
+          if (v == wi) { f = nfi; flags[row] = (uint8_t)nfi; }
+          else if (v == wj) { f = nfj; flags[row] = (uint8_t)nfj; }
+          if (v == pvi) store_alpha(row, false, row, pai);
+          else if (v == pvj) store_alpha(row, false, row, paj);
           consider(nu, f, g, v, best);
         }
         if (mirror) {
-          const int v = (int)(row + l);
+          const int v = (int)(row + goff + lg);
           const double g = cur.g1 - c;
-          G[v] = g;
+          G[row + l] = g;
           int f = cur.f1;
-          if (v == wi) { f = nfi; flags[v] = (uint8_t)nfi; }
-          else if (v == wj) { f = nfj; flags[v] = (uint8_t)nfj; }
-          if (v == pvi) { alpha[v] = pai; __threadfence(); }
-          else if (v == pvj) { alpha[v] = paj; __threadfence(); }
+          if (v == wi) { f = nfi; flags[row + l] = (uint8_t)nfi; }
+          else if (v == wj) { f = nfj; flags[row + l] = (uint8_t)nfj; }
+          if (v == pvi) store_alpha(row + l, true, row, pai);
+          else if (v == pvj) store_alpha(row + l, true, row, paj);
           consider(nu, f, g, v, best);
         }
       }

@@ -1,0 +1,229 @@
+"""Row-sharded SMO over the GPUs of one NVLink / NVSwitch box.
+
+One process per GPU (``torch.distributed``).  Each rank owns a contiguous slice of the training rows
+and the matching slices of ``alpha`` / ``neg_y_grad``; per SMO iteration the persistent kernels of all
+ranks exchange their working-set candidates through 16-byte tagged records written straight into
+each other's memory over NVLink (CUDA IPC peer mappings), and read the two winning rows from the
+owner's published block.  ``torch.distributed`` is used for plumbing only: the one-off exchange of
+IPC handles, a barrier before each solve, and the final gather / reduction of results.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .solver import KernelSpec, QColumns, SolverWithCache, kernel_matvec, to_device_matrix
+
+
+@dataclass(frozen=True)
+class Shard:
+    rank: int
+    world: int
+    n_global: int
+    rows_per_rank: int      # roundup32(ceil(n / world)); the same formula as b2svm_create
+
+    @property
+    def row_offset(self) -> int:
+        return self.rank * self.rows_per_rank
+
+    @property
+    def n_local(self) -> int:
+        return max(0, min(self.rows_per_rank, self.n_global - self.row_offset))
+
+    def rows(self) -> slice:
+        return slice(self.row_offset, self.row_offset + self.n_local)
+
+
+def plan(n_global: int, world: int, rank: int) -> Shard:
+    """Equal slices of whole 32-row tiles: rank r owns rows [r*rpr, min(n, (r+1)*rpr))."""
+    rpr = (-(-n_global // world) + 31) // 32 * 32
+    s = Shard(rank, world, n_global, rpr)
+    if s.n_local <= 0:
+        raise ValueError(f"rank {rank} of {world} would own no rows of {n_global}")
+    return s
+
+
+def local_vector(v: np.ndarray, shard: Shard, mirror: bool) -> np.ndarray:
+    """The slice of a per-variable vector this rank owns; mirror problems keep [first | second] halves."""
+    r = shard.rows()
+    if not mirror:
+        return np.ascontiguousarray(v[r])
+    n = shard.n_global
+    return np.concatenate([v[r], v[n + r.start:n + r.stop]])
+
+
+def combine_bias_partials(parts: np.ndarray) -> np.ndarray:
+    """Merge per-rank b2svm_bias_partials rows [world][18]: sums / counts add, extremes min / max."""
+    out = parts.sum(axis=0)
+    out[2] = parts[:, 2].min()
+    out[4] = parts[:, 4].max()
+    for c in range(2):
+        o = 6 + 6 * c
+        out[o + 2] = parts[:, o + 2].max()
+        out[o + 4] = parts[:, o + 4].min()
+    return out
+
+
+def rho_from_partials(p: np.ndarray) -> float:
+    """Solver.calculate_rho (solver.py:160-177) from merged partials."""
+    if p[1] > 0:
+        return -(p[0] / p[1])
+    if p[3] == 0 or p[5] == 0:
+        raise ValueError("calculate_rho: empty bound set")
+    return -(p[2] + p[4]) / 2
+
+
+def rho_b_from_partials(p: np.ndarray):
+    """NuSolver.calculate_rho_b (solver.py:378-419) from merged partials."""
+    r = []
+    for c in range(2):
+        o = 6 + 6 * c
+        if p[o + 1] > 0:
+            r.append(p[o] / p[o + 1])
+        elif p[o + 3] > 0 and p[o + 5] > 0:
+            r.append((p[o + 2] + p[o + 4]) / 2)
+        else:
+            r.append(0.0)
+    return (r[0] + r[1]) / 2, (r[1] - r[0]) / 2
+
+
+def _group_device(group) -> torch.device:
+    backend = dist.get_backend(group)
+    return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+
+def all_gather_bytes(payload: bytes, group=None) -> bytes:
+    """Concatenation over ranks of a fixed-size byte string (IPC handles)."""
+    dev = _group_device(group)
+    world = dist.get_world_size(group)
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(dev)
+    out = torch.empty(world * len(payload), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return bytes(out.cpu().numpy().tobytes())
+
+
+def all_gather_array(a: np.ndarray, group=None) -> np.ndarray:
+    dev = _group_device(group)
+    world = dist.get_world_size(group)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    t = torch.from_numpy(a.reshape(-1)).to(dev)
+    out = torch.empty(world * t.numel(), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, t, group=group)
+    return out.cpu().numpy().reshape((world,) + a.shape)
+
+
+class ShardedColumns(QColumns):
+    """QColumns over this rank's rows only; carries the shard geometry to b2svm_create."""
+
+    def __init__(self, X_local, y_local, kernel: KernelSpec, shard: Shard, mirror: bool = False, device=None):
+        super().__init__(X_local, y_local, kernel, mirror=mirror, device=device)
+        self.shard = shard
+        assert self.X.shape[0] == shard.n_local
+
+
+class ShardedSolver(SolverWithCache):
+    """``SolverWithCache`` whose ``solve`` runs row-sharded over the process group."""
+
+    def __init__(self, p_local, y_local, C, tol, func: ShardedColumns, group=None):
+        self.group = group
+        super().__init__(p_local, y_local, C, tol, func=func)
+        handles = all_gather_bytes(self._engine.export_mailbox(), group)
+        self._engine.attach_mailboxes(handles)
+
+    def solve(self, max_iter: int, func=None):
+        eng = self._need(func)
+        eng.prepare()                          # clear mailbox, publish alpha slice (synchronises the stream)
+        dist.barrier(group=self.group)         # no peer may start before every mailbox is clean
+        st = eng.solve(max_iter)
+        self.last_stats = st
+        return st
+
+    def calculate_rho(self) -> float:
+        parts = all_gather_array(self._engine.bias_partials(), self.group)
+        return rho_from_partials(combine_bias_partials(parts))
+
+
+_ENABLED = {"on": False, "group": None}
+
+
+def enable(group=None):
+    """Route ``BiKernelSVC.fit`` / ``KernelSVR.fit`` through the row-sharded solve of the current
+    ``torch.distributed`` process group (every rank must call ``fit`` with the same host arrays)."""
+    _ENABLED["on"], _ENABLED["group"] = True, group
+
+
+def disable():
+    _ENABLED["on"], _ENABLED["group"] = False, None
+
+
+def active() -> bool:
+    return _ENABLED["on"] and dist.is_available() and dist.is_initialized() and dist.get_world_size(_ENABLED["group"]) > 1
+
+
+def gather_variables(v_local: np.ndarray, shard: Shard, mirror: bool, group=None) -> np.ndarray:
+    """All ranks' slices of a per-variable vector, reassembled in global variable order."""
+    rpr, n = shard.rows_per_rank, shard.n_global
+    halves = 2 if mirror else 1
+    pad = np.zeros((halves, rpr))
+    for h in range(halves):
+        pad[h, :shard.n_local] = v_local[h * shard.n_local:(h + 1) * shard.n_local]
+    allp = all_gather_array(pad, group)                      # [world][halves][rpr]
+    return np.concatenate([allp[:, h, :].reshape(-1)[:n] for h in range(halves)])
+
+
+class ShardedFit:
+    """What a sharded estimator keeps after ``fit`` (the counterpart of svc._Fitted)."""
+
+    def __init__(self, solver: "ShardedSolver", shard: Shard, coef_local: torch.Tensor, mirror: bool, group=None):
+        self.solver, self.shard, self.coef_local, self.mirror, self.group = solver, shard, coef_local, mirror, group
+        self.func = solver._engine.func
+
+    def kernel_sum(self, x) -> np.ndarray:
+        return decision_sharded(self.solver, self.coef_local, x, self.group)
+
+
+def fit_csvc_sharded(X: np.ndarray, y01: np.ndarray, C: float, kernel: KernelSpec, tol: float, max_iter: int,
+                     group=None):
+    """Row-sharded BiKernelSVC solve.  Every rank passes the full host arrays and keeps its slice.
+    Returns (solver, shard, stats); ``solver.alpha`` is this rank's slice."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    y = np.array(y01, dtype=float)
+    y[y != 1] = -1
+    shard = plan(X.shape[0], world, rank)
+    func = ShardedColumns(np.ascontiguousarray(X[shard.rows()]), local_vector(y, shard, False), kernel, shard)
+    solver = ShardedSolver(local_vector(-np.ones(X.shape[0]), shard, False), func.y, C, tol, func, group)
+    stats = solver.solve(max_iter)
+    return solver, shard, stats
+
+
+def fit_svr_sharded(X: np.ndarray, z: np.ndarray, C: float, eps: float, kernel: KernelSpec, tol: float,
+                    max_iter: int, group=None):
+    """Row-sharded KernelSVR solve (2l variables, variables t and t+l share row t)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    l = X.shape[0]
+    y = np.empty(2 * l)
+    y[:l], y[l:] = 1., -1.
+    p = np.ones(2 * l) * eps
+    p[:l] -= z
+    p[l:] += z
+    shard = plan(l, world, rank)
+    func = ShardedColumns(np.ascontiguousarray(X[shard.rows()]), local_vector(y, shard, True), kernel, shard,
+                          mirror=True)
+    solver = ShardedSolver(local_vector(p, shard, True), func.y, C, tol, func, group)
+    stats = solver.solve(max_iter)
+    return solver, shard, stats
+
+
+def decision_sharded(solver: ShardedSolver, coef_local: torch.Tensor, Xq: np.ndarray, group=None) -> np.ndarray:
+    """sum over ALL support rows of coef K(x_s, x_q): each rank sums its slice, one all-reduce adds them."""
+    func = solver._engine.func
+    q = to_device_matrix(np.asarray(Xq), func.device).to(func.X.dtype)
+    part = kernel_matvec(func.kernel, func.X, coef_local, q)
+    if dist.get_backend(group) != "nccl":
+        part = part.cpu()
+    dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    return part.cpu().numpy()

@@ -91,6 +91,7 @@ class _Engine:
 
     def __init__(self, func: QColumns, alpha: torch.Tensor, g: torch.Tensor, Cbox: float, tol: float, variant: int,
                  max_ctas: int = 0):
+        shard = getattr(func, "shard", None)
         self.lib = N.load()
         self.func = func
         self.alpha, self.g = alpha, g
@@ -112,8 +113,12 @@ class _Engine:
         d.kernel = func.kernel.desc()
         d.cache_bytes = 0
         d.max_ctas = max_ctas
-        d.rank, d.world = 0, 1
-        d.row_offset, d.n_rows_global = 0, X.shape[0]
+        if shard is None:
+            d.rank, d.world = 0, 1
+            d.row_offset, d.n_rows_global = 0, X.shape[0]
+        else:
+            d.rank, d.world = shard.rank, shard.world
+            d.row_offset, d.n_rows_global = shard.row_offset, shard.n_global
         self.desc = d
         h = C.c_void_p()
         torch.cuda.synchronize(func.device)          # handle work runs on the legacy default stream
@@ -168,6 +173,22 @@ class _Engine:
         r, b = C.c_double(), C.c_double()
         N.check(self.lib.b2svm_rho_b(self.h, C.byref(r), C.byref(b)))
         return r.value, b.value
+
+    def bias_partials(self) -> np.ndarray:
+        out = (C.c_double * 18)()
+        N.check(self.lib.b2svm_bias_partials(self.h, out))
+        return np.array(out[:], dtype=np.float64)
+
+    def prepare(self):
+        N.check(self.lib.b2svm_prepare(self.h))
+
+    def export_mailbox(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        N.check(self.lib.b2svm_mailbox_export(self.h, buf))
+        return buf.raw
+
+    def attach_mailboxes(self, handles: bytes):
+        N.check(self.lib.b2svm_mailbox_attach(self.h, handles))
 
 
 class Solver:

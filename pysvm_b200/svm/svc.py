@@ -147,6 +147,9 @@ class BiKernelSVC(BiLinearSVC):
         y[y != 1] = -1
         l, self.n_features = X.shape
         p = -np.ones(l)
+        from .. import sharded
+        if sharded.active() and not self.rff:
+            return self._fit_sharded(X, y, sharded)
         func, spec, rff = self._columns(X, y)
         solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func)
         self._report(solver.solve(self.max_iter))
@@ -161,8 +164,21 @@ class BiKernelSVC(BiLinearSVC):
         self.alpha_ = a
         self.support_ = np.flatnonzero(a > 0)
 
+    def _fit_sharded(self, X, y, sharded):
+        """The same fit, row-sharded over the GPUs of the current process group (sharded.enable())."""
+        group = sharded._ENABLED["group"]
+        spec, _ = self.register_kernel(X.std())
+        solver, shard, stats = sharded.fit_csvc_sharded(X, (y == 1).astype(int), self.C, spec, self.tol,
+                                                        self.max_iter, group)
+        self._report(stats)
+        self._fitted = sharded.ShardedFit(solver, shard, solver.alpha * solver._engine.func.y, False, group)
+        self.rho_ = solver.calculate_rho()
+        self.alpha_ = sharded.gather_variables(solver.alpha.cpu().numpy(), shard, False, group)
+        self.support_ = np.flatnonzero(self.alpha_ > 0)
+        return self
+
     def decision_function(self, x) -> np.ndarray:
-        return self._fitted.kernel_sum(x) - self._fitted.solver.calculate_rho()
+        return self._fitted.kernel_sum(x) - self.rho_
 
     def predict(self, X) -> np.ndarray:
         return super().predict(X)
