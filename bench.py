@@ -171,12 +171,12 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- value: inputs resident in HBM, K fresh fits of ITERS iterations each -------------------------
     if world == 1:
-        func = S.QColumns(X, y, S.KernelSpec("rbf", gamma), device=dev)
+        func = S.QColumns(X, y, S.KernelSpec("rbf", gamma), device=dev, cache_bytes=0)   # cold path
         sol = S.SolverWithCache(p, y, 1.0, 1e-5, func=func)
     else:
         # row-sharded over the GPUs of the box: one problem, every rank owns n/world rows (strong scaling)
         from pysvm_b200 import sharded
-        sol, shard, _ = sharded.fit_csvc_sharded(X, y01, 1.0, S.KernelSpec("rbf", gamma), 1e-5, 8)
+        sol, shard, _ = sharded.fit_csvc_sharded(X, y01, 1.0, S.KernelSpec("rbf", gamma), 1e-5, 8, cache_bytes=0)
         sharded.enable()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 

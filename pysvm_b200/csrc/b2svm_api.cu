@@ -228,6 +228,9 @@ struct b2svm_handle {
   std::vector<void*> peer_blocks;          // opened IPC mappings (nullptr for this rank)
   void** peer_tables = nullptr;            // device: [4][world] = mbox, X, norms, alpha pointers of every rank
   bool attached = false, prepared = false;
+  void* cache = nullptr;          // Q-column cache [cache_slots][n_rows] in the input dtype
+  int* slot_of = nullptr;
+  long long cache_slots = 0, cache_used = 0;
   long long* timeline = nullptr;   // debug: set by B2SVM_TIMELINE=1
   double* dbg_steps = nullptr;     // debug: set by B2SVM_DEBUG_STEPS=1
 };
@@ -345,6 +348,10 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.max_iter = max_iter;
   P.forced_i = fi;
   P.forced_j = fj;
+  P.cache = h->cache;
+  P.slot_of = h->slot_of;
+  P.cache_slots = h->cache_slots;
+  P.cache_used = h->cache_used;
   P.world = h->d.world > 1 ? h->d.world : 1;
   P.rank = h->d.world > 1 ? h->d.rank : 0;
   P.row_offset = h->d.world > 1 ? h->d.row_offset : 0;
@@ -408,6 +415,7 @@ int run_solver(b2svm_handle* h, long long max_iter, long long fi, long long fj, 
   B2_CUDA(cudaStreamSynchronize(h->stream));
   h->launches = 2;
   *res = *h->result_host;
+  h->cache_used = res->cache_used;
   if (ms) B2_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   if (res->status != 0) return fail(B2SVM_E_TIMEOUT, "device watchdog: a grid barrier did not complete");
   return B2SVM_OK;
@@ -507,6 +515,19 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     row_norms_kernel<float><<<grid_for(l * 32), 256, 0, h->stream>>>((const float*)h->Xuse, l, h->dp, (float*)h->norms);
   B2_TRY(cudaGetLastError());
   B2_TRY(cudaMalloc(&h->flags, (size_t)nv));
+  if (desc->cache_bytes > 0) {
+    // device-resident Q-column cache: as many whole columns (this GPU's rows) as the budget holds
+    const size_t col_bytes = (size_t)l * esz;
+    long long slots = (long long)(desc->cache_bytes / col_bytes);
+    const long long lglob = desc->world > 1 ? desc->n_rows_global : l;
+    slots = std::min<long long>(slots, lglob);
+    if (slots > 0) {
+      B2_TRY(cudaMalloc(&h->cache, (size_t)slots * col_bytes));
+      B2_TRY(cudaMalloc(&h->slot_of, sizeof(int) * (size_t)lglob));
+      B2_TRY(cudaMemsetAsync(h->slot_of, 0xff, sizeof(int) * (size_t)lglob, h->stream));
+      h->cache_slots = slots;
+    }
+  }
   h->cand_bytes = sizeof(uint4) * 2 * h->num_sms * NCAND;
   B2_TRY(cudaMalloc(&h->cand, h->cand_bytes));
   B2_TRY(cudaMalloc(&h->abort_flag, sizeof(int)));
@@ -545,6 +566,8 @@ int b2svm_destroy(b2svm_handle* h) {
   cudaFree(h->peer_tables);
   cudaFree(h->block);
   cudaFree(h->flags);
+  cudaFree(h->cache);
+  cudaFree(h->slot_of);
   cudaFree(h->cand);
   cudaFree(h->abort_flag);
   cudaFree(h->result);
@@ -657,12 +680,15 @@ int b2svm_solve(b2svm_handle* h, int64_t max_iter, b2svm_solve_stats* stats) {
     stats->last_delta_i = r.di;
     stats->last_delta_j = r.dj;
     stats->cold_sweeps = r.cold_sweeps;
-    stats->cache_hits = 0;
-    stats->cache_misses = 2 * r.cold_sweeps;
+    stats->cache_hits = 2 * r.warm_sweeps;                 // both columns read from the cache
+    stats->cache_misses = 2 * r.cold_sweeps;               // cold sweep: both columns recomputed in one pass over X
     const double esz = h->f64 ? 8.0 : 4.0;
-    // DESIGN.md section 4 / SURVEY 8(d): B_cold = l * d * sizeof(T) + n_vars * 18
+    // DESIGN.md section 4 / SURVEY 8(d): B_cold = l d sizeof(T) + n_vars 18 (+ sizeof(T) l per stored column);
+    // B_warm = n_vars 18 + 2 sizeof(T) l
     stats->algorithmic_bytes =
-        (double)r.cold_sweeps * ((double)h->d.n_rows * h->d.n_features * esz + (double)h->d.n_vars * 18.0);
+        (double)r.cold_sweeps * ((double)h->d.n_rows * h->d.n_features * esz + (double)h->d.n_vars * 18.0) +
+        (double)r.cols_stored * (double)h->d.n_rows * esz +
+        (double)r.warm_sweeps * ((double)h->d.n_vars * 18.0 + 2.0 * (double)h->d.n_rows * esz);
     stats->device_ms = ms;
     stats->launches = h->launches;
   }

@@ -46,6 +46,7 @@ struct SolveResult {
   long long n_iter;
   long long last_i, last_j;
   long long cold_sweeps;
+  long long warm_sweeps, cols_stored, cache_used;
   double di, dj;
   int converged;
   int status;   // 0 ok, 1 watchdog
@@ -72,6 +73,11 @@ struct ProblemDev {
   long long max_iter;
   long long forced_i, forced_j;   // >= 0: skip the initial selection and take this pair first
   long long* timeline;            // optional [TL_ITERS][TL_SLOTS] clock64 stamps of CTA 0's leader lane
+  // ---- device-resident Q-column cache (replaces the LRU of solver.py:207,227-229) -------------------
+  void* cache;                    // T [cache_slots][l]: K(x_t, x_r) for this GPU's rows t, one slot per cached row r
+  int* slot_of;                   // [l_global] slot of global row r, -1 = not cached (replicated per GPU)
+  long long cache_slots;          // 0 = cache off
+  long long cache_used;           // slots already filled by earlier solves on this handle
   // ---- row-sharded multi-GPU (world > 1): this GPU owns global rows [row_offset, row_offset + l) --------
   int world, rank;
   long long row_offset, l_global, rows_per_rank;   // every rank's slice starts at rank * rows_per_rank
@@ -114,6 +120,9 @@ struct Shared {
   double ai, aj;        // new alpha_i, alpha_j
   T ni, nj;             // |x_i|^2, |x_j|^2
   int i, j, fi, fj;
+  int slot_i, slot_j;   // cache slots of rows i, j (-1 = none); store_* = fill the slot during this sweep
+  int store_i, store_j, warm;
+  int p_ri, p_rj, p_si, p_sj;   // previous pair's rows / slots: slot_of[] is updated one sweep late, like alpha
   int pi, pj;           // previous pair, whose alphas (pai, paj) are stored during this sweep
   double pai, paj;
   int stop;
@@ -208,6 +217,7 @@ struct RowState {   // gradient-side state of one row (and its mirror variable),
   double g0, g1;
   int f0, f1;
   T nt;
+  T ki, kj;   // cached kernel values of this row against x_i, x_j (warm sweeps only)
 };
 
 template <typename T, int CH>
@@ -344,6 +354,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   int converged = 0;
   double l_di = 0, l_dj = 0;   // leader-only: last step ...
   int l_i = -1, l_j = -1;      // ... its pair and new alphas (stored one sweep later, forwarded meanwhile)
+  int l_ri = -1, l_rj = -1, l_si = -1, l_sj = -1;   // ... and its rows / cache slots (same deferral)
+  int n_cached = (int)P.cache_used;   // slots handed out so far (identical in every leader)
+  long long warm_cnt = 0, stored_cnt = 0;
   double l_ai = 0, l_aj = 0;
   long long cta_sweep_start_prev = 0;   // debug
 
@@ -371,11 +384,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       __threadfence();
     }
   };
+  // cache columns in use by the current / next sweep (set after bar (A))
+  bool sweep_warm = false;
+  const T* cache_i = nullptr;
+  const T* cache_j = nullptr;
   auto load_row_state = [&](int t) {
     RowState<T> r;
     r.g0 = r.g1 = 0.0;
     r.f0 = r.f1 = 0;
     r.nt = 0;
+    r.ki = r.kj = 0;
     const long long row = row0 + (long long)t * C::BR + rib;
     if (t < NT && lane_active && row < row1) {
       if (P.debug_flags & 2) {
@@ -388,6 +406,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         if (mirror) { r.g1 = G[row + l]; r.f1 = flags[row + l]; }
       }
       r.nt = norms[row];
+      if (sweep_warm) {
+        r.ki = cache_i[row];
+        r.kj = cache_j[row];
+      }
     }
     return r;
   };
@@ -620,6 +642,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             r.last_i = stop_sel ? -1 : si;
             r.last_j = stop_sel ? -1 : sj;
             r.cold_sweeps = cold;
+            r.warm_sweeps = warm_cnt;
+            r.cols_stored = stored_cnt;
+            r.cache_used = n_cached;
+            if (P.cache_slots > 0 && l_ri >= 0) {   // pending slot-table entries of the last step
+              if (l_si >= 0) P.slot_of[l_ri] = l_si;
+              if (l_sj >= 0) P.slot_of[l_rj] = l_sj;
+            }
             r.di = l_di;
             r.dj = l_dj;
             r.converged = converged;
@@ -635,9 +664,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         const double yi = (fi & F_YPOS) ? 1.0 : -1.0;
         const double yj = (fj & F_YPOS) ? 1.0 : -1.0;
         const StepOut so = smo_step(nu, (double)Kii, (double)Kjj, (double)Kij, yi, yj, gi, gj, ai, aj, Cbox);
+        // ---- Q-column cache: which of the two columns are already resident, which get stored now --------
+        int slot_i = -1, slot_j = -1, store_i = 0, store_j = 0;
+        const int gri = (int)((mirror && si >= lg) ? si - lg : si), grj = (int)((mirror && sj >= lg) ? sj - lg : sj);
+        if (P.cache_slots > 0) {
+          slot_i = gri == l_ri ? l_si : (gri == l_rj ? l_sj : __ldcg(P.slot_of + gri));
+          slot_j = grj == l_ri ? l_si : (grj == l_rj ? l_sj : __ldcg(P.slot_of + grj));
+          if (slot_i < 0 && n_cached < P.cache_slots) { slot_i = n_cached++; store_i = 1; }
+          if (grj == gri) { slot_j = slot_i; }
+          else if (slot_j < 0 && n_cached < P.cache_slots) { slot_j = n_cached++; store_j = 1; }
+        }
+        const int warm = (P.cache_slots > 0 && slot_i >= 0 && slot_j >= 0 && !store_i && !store_j) ? 1 : 0;
         if (lane == 0) {
+          sh->slot_i = slot_i; sh->slot_j = slot_j; sh->store_i = store_i; sh->store_j = store_j; sh->warm = warm;
+          sh->p_ri = l_ri; sh->p_rj = l_rj; sh->p_si = l_si; sh->p_sj = l_sj;
           sh->pi = l_i; sh->pj = l_j; sh->pai = l_ai; sh->paj = l_aj;
         }
+        l_ri = gri; l_rj = grj; l_si = slot_i; l_sj = slot_j;
+        if (warm) ++warm_cnt;
+        stored_cnt += store_i + store_j;
         l_di = so.di; l_dj = so.dj; l_i = si; l_j = sj; l_ai = so.ai; l_aj = so.aj;
         if (P.dbg_steps && lane == 0 && cta == 0 && epoch <= (uint32_t)DBG_EPOCHS) {
           double* o = P.dbg_steps + (size_t)DBG_EPOCHS * ncta * 6 + (size_t)(epoch - 1) * 2;
@@ -680,6 +725,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       xj[q] = xs[CH + lig + q * C::LPR];
     }
     reset_best();
+    // ---- Q-column cache plan of this sweep ---------------------------------------------------------
+    const bool warm = sh->warm != 0;
+    const int store_i = sh->store_i, store_j = sh->store_j;
+    T* const cache_base = reinterpret_cast<T*>(P.cache);
+    T* const col_i = sh->slot_i >= 0 ? cache_base + (size_t)sh->slot_i * (size_t)l : nullptr;
+    T* const col_j = sh->slot_j >= 0 ? cache_base + (size_t)sh->slot_j * (size_t)l : nullptr;
+    sweep_warm = warm;
+    cache_i = col_i;
+    cache_j = col_j;
+    if (P.cache_slots > 0 && cta == 0 && warp == NW - 1 && lane == 0 && sh->p_ri >= 0) {
+      // the previous step's slot-table entries, one sweep late (a slow leader may still have been reading them)
+      if (sh->p_si >= 0) P.slot_of[sh->p_ri] = sh->p_si;
+      if (sh->p_sj >= 0) P.slot_of[sh->p_rj] = sh->p_sj;
+      __threadfence();
+    }
+    if (warm) {   // the first tile's state was prefetched before this sweep's plan was known
+      const long long r0w = row0 + (long long)warp * C::BR + rib;
+      if (warp < NT && lane_active && r0w < row1) { pf.ki = col_i[r0w]; pf.kj = col_j[r0w]; }
+    }
     long long cta_sweep_start = 0;
     if (P.timeline && threadIdx.x == 0 && epoch == 10u) cta_sweep_start = clock64() + (long long)(ci == 123.456);
 
@@ -700,63 +764,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       const RowState<T> cur = pf;
       pf = load_row_state(tn);
 
-      unsigned stage, use = 0u;
-      if (resident) {
-        stage = (unsigned)t;
-      } else {
-        const unsigned q = tb_mod + (unsigned)t;
-        stage = q % S;
-        use = tb_div + q / S;
-      }
       const long long row = row0 + (long long)t * C::BR + rib;
       const bool valid = lane_active && row < row1;
-      const long long dbg_w0 = dbg ? clock64() : 0;
-      {
-        uint32_t spins = 0;
-        uint64_t t_wait = 0;
-        bool ok = false;
-        while (!ok) {
-          ok = (resident || gen[stage] == use) && mbar_try_wait(&full[stage], use & 1u);
-          if (!ok && (++spins & 1023u) == 0) {
-            if (*(volatile int*)P.abort_flag) break;
-            const uint64_t now = globaltimer_ns();
-            if (t_wait == 0) t_wait = now;
-            else if (now - t_wait > 4000000000ull) { *(volatile int*)P.abort_flag = 1; break; }
+      T dti = 0, dtj = 0;
+      if (!warm) {
+        unsigned stage, use = 0u;
+        if (resident) {
+          stage = (unsigned)t;
+        } else {
+          const unsigned q = tb_mod + (unsigned)t;
+          stage = q % S;
+          use = tb_div + q / S;
+        }
+        const long long dbg_w0 = dbg ? clock64() : 0;
+        {
+          uint32_t spins = 0;
+          uint64_t t_wait = 0;
+          bool ok = false;
+          while (!ok) {
+            ok = (resident || gen[stage] == use) && mbar_try_wait(&full[stage], use & 1u);
+            if (!ok && (++spins & 1023u) == 0) {
+              if (*(volatile int*)P.abort_flag) break;
+              const uint64_t now = globaltimer_ns();
+              if (t_wait == 0) t_wait = now;
+              else if (now - t_wait > 4000000000ull) { *(volatile int*)P.abort_flag = 1; break; }
+            }
           }
         }
-      }
-      if (dbg) { dbg_wait += clock64() - dbg_w0; ++dbg_tiles; }
-      const unsigned char* base = ring + (size_t)stage * C::TILE_BYTES + (size_t)grp * C::RPL * C::ROWB + lig * 16;
-      T acc[C::NV];
+        if (dbg) { dbg_wait += clock64() - dbg_w0; ++dbg_tiles; }
+        const unsigned char* base = ring + (size_t)stage * C::TILE_BYTES + (size_t)grp * C::RPL * C::ROWB + lig * 16;
+        T acc[C::NV];
 #pragma unroll
-      for (int k = 0; k < C::NV; ++k) acc[k] = 0;
+        for (int k = 0; k < C::NV; ++k) acc[k] = 0;
 #pragma unroll
-      for (int k = 0; k < C::RPL; ++k) {
+        for (int k = 0; k < C::RPL; ++k) {
 #pragma unroll
-        for (int q = 0; q < C::CPL; ++q) {
-          const V v = *reinterpret_cast<const V*>(base + k * C::ROWB + q * C::LPR * 16);
-          acc[2 * k] = CK::dot(v, xi[q], acc[2 * k]);
-          acc[2 * k + 1] = CK::dot(v, xj[q], acc[2 * k + 1]);
+          for (int q = 0; q < C::CPL; ++q) {
+            const V v = *reinterpret_cast<const V*>(base + k * C::ROWB + q * C::LPR * 16);
+            acc[2 * k] = CK::dot(v, xi[q], acc[2 * k]);
+            acc[2 * k + 1] = CK::dot(v, xj[q], acc[2 * k + 1]);
+          }
+        }
+        TransposeReduce<T, C::NV, C::LPR / 2>::run(acc, lig);
+        if (C::FINAL == 2) {
+          dti = acc[0];
+          dtj = acc[1];
+        } else {
+          const T o = __shfl_xor_sync(0xffffffffu, acc[0], 1);
+          dti = (lig & 1) ? o : acc[0];
+          dtj = (lig & 1) ? acc[0] : o;
+        }
+        __syncwarp();
+        if (!resident && lane == 0) {
+          gen[stage] = use + 1u;
+          mbar_arrive(&empty[stage]);
         }
       }
-      TransposeReduce<T, C::NV, C::LPR / 2>::run(acc, lig);
-      T dti, dtj;
-      if (C::FINAL == 2) {
-        dti = acc[0];
-        dtj = acc[1];
-      } else {
-        const T o = __shfl_xor_sync(0xffffffffu, acc[0], 1);
-        dti = (lig & 1) ? o : acc[0];
-        dtj = (lig & 1) ? acc[0] : o;
-      }
-      __syncwarp();
-      if (!resident && lane == 0) {
-        gen[stage] = use + 1u;
-        mbar_arrive(&empty[stage]);
-      }
       if (valid) {
-        const T kti = kernel_value(kp, dti, cur.nt, ni);
-        const T ktj = kernel_value(kp, dtj, cur.nt, nj);
+        // a cached value is bit-identical to the recomputed one (same code, same summation order)
+        const T kti = warm ? cur.ki : kernel_value(kp, dti, cur.nt, ni);
+        const T ktj = warm ? cur.kj : kernel_value(kp, dtj, cur.nt, nj);
+        if (store_i) col_i[row] = kti;
+        if (store_j) col_j[row] = ktj;
         // y_t * (delta_i Q_i[t] + delta_j Q_j[t]) = (y_i delta_i) K_ti + (y_j delta_j) K_tj   (solver.py:146)
         const double c = ci * (double)kti + cj * (double)ktj;
         {
@@ -789,15 +858,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       long long* o = P.timeline + TL_ITERS * TL_SLOTS + warp * TL_WARP_SLOTS;
       o[0] = dbg_start; o[1] = clock64(); o[2] = dbg_tiles; o[3] = dbg_wait;
     }
+    sweep_warm = false;
     pf = load_row_state(warp);   // first tile of the next sweep (after this thread's own stores to it)
-    if (!resident) {
-      const unsigned q = tb_mod + (unsigned)NT;
-      tb_mod = q % S;
-      tb_div = tb_div + q / S;
+    if (!warm) {
+      if (!resident) {
+        const unsigned q = tb_mod + (unsigned)NT;
+        tb_mod = q % S;
+        tb_div = tb_div + q / S;
+      }
+      Tbase += (unsigned long long)NT;
+      ++cold;
     }
-    Tbase += (unsigned long long)NT;
     ++n_iter;
-    ++cold;
   }
 
   // ---- exit: tell the producer how far the consumers got, let it drain --------------------------

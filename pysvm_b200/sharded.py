@@ -119,8 +119,9 @@ def all_gather_array(a: np.ndarray, group=None) -> np.ndarray:
 class ShardedColumns(QColumns):
     """QColumns over this rank's rows only; carries the shard geometry to b2svm_create."""
 
-    def __init__(self, X_local, y_local, kernel: KernelSpec, shard: Shard, mirror: bool = False, device=None):
-        super().__init__(X_local, y_local, kernel, mirror=mirror, device=device)
+    def __init__(self, X_local, y_local, kernel: KernelSpec, shard: Shard, mirror: bool = False, device=None,
+                 cache_bytes=None):
+        super().__init__(X_local, y_local, kernel, mirror=mirror, device=device, cache_bytes=cache_bytes)
         self.shard = shard
         assert self.X.shape[0] == shard.n_local
 
@@ -187,14 +188,15 @@ class ShardedFit:
 
 
 def fit_csvc_sharded(X: np.ndarray, y01: np.ndarray, C: float, kernel: KernelSpec, tol: float, max_iter: int,
-                     group=None):
+                     group=None, cache_bytes=None):
     """Row-sharded BiKernelSVC solve.  Every rank passes the full host arrays and keeps its slice.
     Returns (solver, shard, stats); ``solver.alpha`` is this rank's slice."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     y = np.array(y01, dtype=float)
     y[y != 1] = -1
     shard = plan(X.shape[0], world, rank)
-    func = ShardedColumns(np.ascontiguousarray(X[shard.rows()]), local_vector(y, shard, False), kernel, shard)
+    func = ShardedColumns(np.ascontiguousarray(X[shard.rows()]), local_vector(y, shard, False), kernel, shard,
+                          cache_bytes=cache_bytes)
     solver = ShardedSolver(local_vector(-np.ones(X.shape[0]), shard, False), func.y, C, tol, func, group)
     stats = solver.solve(max_iter)
     return solver, shard, stats

@@ -17,6 +17,7 @@ Differences a PySVM user sees (all additive):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -69,7 +70,12 @@ class QColumns:
     """The reference's ``func(i)`` closure (svc.py:257-258, svr.py:174-179, oc_svm.py:72-73) as an
     object: Q[:, i] = y * K(X, x_{i mod l}) * y_i evaluated on the device."""
 
-    def __init__(self, X, y, kernel: KernelSpec, mirror: bool = False, device=None):
+    def __init__(self, X, y, kernel: KernelSpec, mirror: bool = False, device=None, cache_bytes=None):
+        """``cache_bytes``: HBM budget of the device-resident Q-column cache (the reference's LRU,
+        solver.py:207,227-229, at B200 scale).  ``None`` = automatic (up to 70 % of the free memory, never
+        more than the full kernel matrix; ``B2SVM_CACHE_GB`` overrides), ``0`` = off (every iteration
+        sweeps X: the cold path)."""
+        self.cache_bytes = cache_bytes
         self.device = torch.device(device) if device is not None else default_device()
         self.X = to_device_matrix(X, self.device)
         self.y = _dev_f64(y, self.device)
@@ -111,7 +117,18 @@ class _Engine:
         d.neg_y_grad = g.data_ptr()
         d.C, d.tol = float(Cbox), float(tol)
         d.kernel = func.kernel.desc()
-        d.cache_bytes = 0
+        esz = 8 if X.dtype == torch.float64 else 4
+        n_glob = shard.n_global if shard is not None else X.shape[0]
+        full_q = int(n_glob) * int(X.shape[0]) * esz
+        cb = func.cache_bytes
+        if cb is None:
+            env = os.environ.get("B2SVM_CACHE_GB")
+            if env is not None:
+                cb = int(float(env) * (1 << 30))
+            else:
+                free, _total = torch.cuda.mem_get_info(func.device)
+                cb = int(free * 0.7)
+        d.cache_bytes = max(0, min(int(cb), full_q))
         d.max_ctas = max_ctas
         if shard is None:
             d.rank, d.world = 0, 1

@@ -325,3 +325,38 @@ def test_full_size_invariants():
     # the pair the fused kernel would take next is the arg-max / arg-min of the oracle rule
     stt = O.DualState(y=y, p=-np.ones(len(y)), C=1.0, tol=1e-5, alpha=a, g=g_inc.cpu().numpy())
     assert O.select_pair(stt) == (st.last_i, st.last_j)
+
+
+# ------------------------------------------------------------------------------ Q-column cache
+def test_column_cache_is_numerically_transparent():
+    """The HBM column cache must not change a single bit (the reference's LRU is transparent too,
+    SURVEY D2): same iterations, same alpha / gradient, and a large share of warm iterations."""
+    torch, _, S, *_ = _mods()
+    X, y01 = O.synth_classification(n=6000, d=128, seed=2)
+    y = np.where(y01 == 1, 1.0, -1.0)
+    spec = S.KernelSpec("rbf", 1 / (128 * X.std()))
+    runs = {}
+    for tag, cb in (("off", 0), ("on", None), ("tiny", 40 * 6000 * 4)):
+        sol = S.SolverWithCache(-np.ones(len(y)), y, 1.0, func=S.QColumns(X, y, spec, cache_bytes=cb))
+        st = sol.solve(10 ** 7)
+        runs[tag] = (st.n_iter, sol.alpha.cpu().numpy(), sol.neg_y_grad.cpu().numpy(), st.cache_hits, st.cold_sweeps)
+    assert runs["off"][3] == 0 and runs["off"][4] == runs["off"][0]
+    for tag in ("on", "tiny"):
+        assert runs[tag][0] == runs["off"][0]
+        np.testing.assert_array_equal(runs[tag][1], runs["off"][1])
+        np.testing.assert_array_equal(runs[tag][2], runs["off"][2])
+    assert runs["on"][3] > runs["on"][0]              # > 50 % of the iterations were warm (2 hits each)
+    assert 0 < runs["tiny"][3] < runs["on"][3]        # a 40-column cache still helps, but less
+
+
+def test_column_cache_survives_a_refit_on_the_same_handle():
+    torch, _, S, *_ = _mods()
+    X, y01 = O.synth_classification(n=4000, d=64, seed=4)
+    y = np.where(y01 == 1, 1.0, -1.0)
+    sol = S.SolverWithCache(-np.ones(len(y)), y, 1.0, func=S.QColumns(X, y, S.KernelSpec("rbf", 0.01)))
+    a = sol.solve(10 ** 7)
+    alpha1 = sol.alpha.clone()
+    sol._engine.init_state(sol.p)
+    b = sol.solve(10 ** 7)
+    assert a.n_iter == b.n_iter and torch.equal(alpha1, sol.alpha)
+    assert b.cold_sweeps < a.cold_sweeps          # columns computed by the first fit are reused
