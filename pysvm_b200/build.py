@@ -18,8 +18,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libb2svm.so")
-SOURCES = ["b2svm_api.cu", "b2svm_dense.cu"]
-HEADERS = ["b2svm_device.cuh", "b2svm_smo.cuh", "b2svm_internal.h", os.path.join("..", "..", "include", "b2svm.h")]
+SOURCES = ["b2svm_api.cu", "b2svm_dense.cu", "b2svm_launch_f32_plain.cu", "b2svm_launch_f32_generic.cu",
+           "b2svm_launch_f64_plain.cu", "b2svm_launch_f64_generic.cu"]
+HEADERS = ["b2svm_device.cuh", "b2svm_smo.cuh", "b2svm_launch.cuh", "b2svm_internal.h", os.path.join("..", "..", "include", "b2svm.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -29,6 +30,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
+if os.environ.get("B2SVM_TIMELINE"):      # per-phase clock stamps inside the persistent kernel (scripts/gpu_timeline.py)
+    NVCC_FLAGS.append("-DB2SVM_TIMELINE")
 
 
 def _nvcc() -> str:

@@ -283,44 +283,29 @@ int plan_T(b2svm_handle* h) {
   return B2SVM_OK;
 }
 
-template <typename T, int CH>
-int launch_T(const ProblemDev* probs_dev, int nprob, int ncta_pp, int stages, size_t smem, cudaStream_t stream) {
-  auto kern = smo_persistent<T, CH>;
-  B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = nprob * ncta_pp;
-  if (ncta_pp > 1) {
-    // CTAs of one problem wait on each other: co-residency must be guaranteed
-    void* args[] = {(void*)&probs_dev, (void*)&ncta_pp, (void*)&stages};
-    B2_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(NTHREADS), args, smem, stream));
-  } else {
-    kern<<<grid, NTHREADS, smem, stream>>>(probs_dev, ncta_pp, stages);
-    B2_CUDA(cudaGetLastError());
-  }
-  return B2SVM_OK;
-}
-
-#define B2_DISPATCH_CH(T, ch, CALL)                                                \
-  switch (ch) {                                                                    \
-    case 4: return CALL(T, 4);                                                     \
-    case 8: return CALL(T, 8);                                                     \
-    case 16: return CALL(T, 16);                                                   \
-    case 32: return CALL(T, 32);                                                   \
-    case 64: return CALL(T, 64);                                                   \
-    case 128: return CALL(T, 128);                                                 \
-    default: return fail(B2SVM_E_UNSUPPORTED, "unsupported row width");            \
-  }
-
 int plan(b2svm_handle* h) {
-#define CALL_PLAN(T, CHV) plan_T<T, CHV>(h)
-  if (h->f64) { B2_DISPATCH_CH(double, h->ch, CALL_PLAN) } else { B2_DISPATCH_CH(float, h->ch, CALL_PLAN) }
-#undef CALL_PLAN
+#define B2_PLAN_CASE(CHV) case CHV: return h->f64 ? plan_T<double, CHV>(h) : plan_T<float, CHV>(h);
+  switch (h->ch) {
+    B2_PLAN_CASE(4) B2_PLAN_CASE(8) B2_PLAN_CASE(16) B2_PLAN_CASE(32) B2_PLAN_CASE(64) B2_PLAN_CASE(128)
+    default: return fail(B2SVM_E_UNSUPPORTED, "unsupported row width");
+  }
+#undef B2_PLAN_CASE
 }
 
-int launch(bool f64, int ch, const ProblemDev* probs_dev, int nprob, int ncta_pp, int stages, size_t smem,
-           cudaStream_t stream) {
-#define CALL_LAUNCH(T, CHV) launch_T<T, CHV>(probs_dev, nprob, ncta_pp, stages, smem, stream)
-  if (f64) { B2_DISPATCH_CH(double, ch, CALL_LAUNCH) } else { B2_DISPATCH_CH(float, ch, CALL_LAUNCH) }
-#undef CALL_LAUNCH
+// The 48 instantiations of the persistent kernel are compiled in four translation units
+// (b2svm_launch_{f32,f64}_{plain,generic}.cu) so the build parallelises.
+int launch(bool f64, int ch, bool cache, bool generic, const ProblemDev* probs_dev, int nprob, int ncta_pp, int stages,
+           size_t smem, cudaStream_t stream) {
+  if (f64) return generic ? launch_f64_generic(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream)
+                          : launch_f64_plain(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream);
+  return generic ? launch_f32_generic(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream)
+                 : launch_f32_plain(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream);
+}
+
+inline bool needs_generic(const b2svm_handle* h);
+
+inline bool needs_generic(const b2svm_handle* h) {
+  return h->d.variant == B2SVM_SOLVER_NU || h->d.n_vars > h->d.n_rows;
 }
 
 void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long long fi, long long fj) {
@@ -408,7 +393,8 @@ int run_solver(b2svm_handle* h, long long max_iter, long long fi, long long fj, 
   fill_problem(h, P, max_iter, fi, fj);
   B2_CUDA(cudaMemcpyAsync(h->prob_dev, &P, sizeof(P), cudaMemcpyHostToDevice, h->stream));
   B2_CUDA(cudaEventRecord(h->ev0, h->stream));
-  int rc = launch(h->f64, h->ch, h->prob_dev, 1, h->ncta, h->stages, h->smem_bytes, h->stream);
+  int rc = launch(h->f64, h->ch, h->cache_slots > 0, needs_generic(h), h->prob_dev, 1, h->ncta, h->stages, h->smem_bytes,
+                  h->stream);
   if (rc != B2SVM_OK) return rc;
   B2_CUDA(cudaEventRecord(h->ev1, h->stream));
   B2_CUDA(cudaMemcpyAsync(h->result_host, h->result, sizeof(SolveResult), cudaMemcpyDeviceToHost, h->stream));
@@ -528,7 +514,7 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
       h->cache_slots = slots;
     }
   }
-  h->cand_bytes = sizeof(uint4) * 2 * h->num_sms * NCAND;
+  h->cand_bytes = sizeof(uint4) * 2 * h->num_sms * NCAND * REC_STRIDE;
   B2_TRY(cudaMalloc(&h->cand, h->cand_bytes));
   B2_TRY(cudaMalloc(&h->abort_flag, sizeof(int)));
   B2_TRY(cudaMalloc(&h->result, sizeof(SolveResult)));
@@ -788,7 +774,11 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
   B2_CUDA(cudaGetLastError());
   B2_CUDA(cudaMemcpyAsync(pd, P.data(), sizeof(ProblemDev) * count, cudaMemcpyHostToDevice, h0->stream));
   B2_CUDA(cudaEventRecord(h0->ev0, h0->stream));
-  int rc = launch(h0->f64, h0->ch, pd, count, 1, h0->stages, h0->smem_bytes, h0->stream);
+  bool any_cache = false;
+  for (int k = 0; k < count; ++k) any_cache = any_cache || handles[k]->cache_slots > 0;
+  bool any_generic = false;
+  for (int k = 0; k < count; ++k) any_generic = any_generic || needs_generic(handles[k]);
+  int rc = launch(h0->f64, h0->ch, any_cache, any_generic, pd, count, 1, h0->stages, h0->smem_bytes, h0->stream);
   if (rc == B2SVM_OK) {
     cudaEventRecord(h0->ev1, h0->stream);
     std::vector<SolveResult> R(count);

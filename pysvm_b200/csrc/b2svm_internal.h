@@ -27,4 +27,13 @@ int kernel_matvec_impl(cudaStream_t stream, const b2svm_kernel_desc& k, int x_dt
                        int64_t na, int64_t lda, const void* Xb, int64_t nb, int64_t ldb, const double* coef,
                        double* out);
 
+struct ProblemDev;
+#define B2_DECL_LAUNCH(name)                                                                                  \
+  int name(int ch, bool cache, const ProblemDev* p, int nprob, int ncta_pp, int stages, size_t smem, cudaStream_t stream)
+B2_DECL_LAUNCH(launch_f32_plain);
+B2_DECL_LAUNCH(launch_f32_generic);
+B2_DECL_LAUNCH(launch_f64_plain);
+B2_DECL_LAUNCH(launch_f64_generic);
+#undef B2_DECL_LAUNCH
+
 }  // namespace b2svm

@@ -36,6 +36,7 @@ constexpr int NW = 11;                     // consumer warps per CTA (+1 produce
 constexpr int NTHREADS = (NW + 1) * 32;    // + one producer warp
 constexpr int MAX_STAGES = 64;
 constexpr int NCAND = 4;                   // up/low (C variant) or up+/low+/up-/low- (nu variant)
+constexpr int REC_STRIDE = 1;              // one 128-byte line per record (uint4 units): spreads the polling over L2 slices
 constexpr int TL_ITERS = 64, TL_SLOTS = 8; // debug timeline
 constexpr int DBG_EPOCHS = 2048;
 constexpr int TL_WARP_SLOTS = 4;           // + per-warp {start, end, tiles, wait} of one sweep
@@ -114,6 +115,18 @@ struct Cfg {
   static constexpr int TILE_BYTES = BR * ROWB;
 };
 
+// State only the leader warp needs between iterations.  It lives in shared memory and is loaded into
+// registers for the duration of the leader block only, so it costs the sweep loop no registers.
+struct LeaderState {
+  double di, dj;          // last step
+  double ai, aj;          // ... its new alphas (stored one sweep later, forwarded meanwhile)
+  int i, j;               // ... its pair
+  int ri, rj, si, sj;     // ... its rows / cache slots (same deferral)
+  int n_cached;           // cache slots handed out so far (identical in every leader)
+  int converged;
+  long long warm_cnt, stored_cnt;
+};
+
 template <typename T>
 struct Shared {
   double ci, cj;        // y_i * delta_i, y_j * delta_j
@@ -128,6 +141,7 @@ struct Shared {
   int stop;
   volatile int producer_stop;
   volatile long long consumed;
+  LeaderState leader;
   int ticket;           // next dynamically assigned tile of the current sweep
   Cand wc[NW][NCAND];
 };
@@ -220,7 +234,10 @@ struct RowState {   // gradient-side state of one row (and its mirror variable),
   T ki, kj;   // cached kernel values of this row against x_i, x_j (warm sweeps only)
 };
 
-template <typename T, int CH>
+// CACHE: the Q-column cache code is compiled in.  GENERIC: nu variant and mirror (2l-variable) problems
+// are handled at run time; GENERIC = false is the plain C-SVC / one-class shape (two candidate types,
+// one variable per row), which frees enough registers to keep the sweep loop spill-free.
+template <typename T, int CH, bool CACHE, bool GENERIC>
 __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* __restrict__ probs, int ncta_pp,
                                                               int ring_stages) {
   using C = Cfg<T, CH>;
@@ -254,8 +271,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   long long row1 = (tile0 + NT) * C::BR;
   if (row1 > P.l) row1 = P.l;
   const bool resident = (unsigned)NT <= S;
-  const bool nu = P.nu != 0;
-  const bool mirror = P.mirror != 0;
+  const bool nu = GENERIC && P.nu != 0;
+  const bool mirror = GENERIC && P.mirror != 0;
   const long long l = P.l;
   const long long goff = P.row_offset, lg = P.l_global;   // global variable index = goff + row (+ lg)
   const int world = P.world;
@@ -271,6 +288,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     sh->producer_stop = 0;
     sh->consumed = 0;
     sh->ticket = NW;
+    LeaderState L0;
+    L0.di = L0.dj = L0.ai = L0.aj = 0.0;
+    L0.i = L0.j = L0.ri = L0.rj = L0.si = L0.sj = -1;
+    L0.n_cached = (int)P.cache_used;
+    L0.converged = 0;
+    L0.warm_cnt = L0.stored_cnt = 0;
+    sh->leader = L0;
   }
   __syncthreads();
 
@@ -337,7 +361,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   double* __restrict__ G = P.G;
   double* __restrict__ alpha = P.alpha;
   uint8_t* __restrict__ flags = P.flags;
-  const int ntypes = nu ? 4 : 2;
+  const int ntypes = (GENERIC && nu) ? 4 : 2;
   const double Cbox = P.C;
 
   const int lig = lane % C::LPR;      // lane in group = which chunks of the row I own
@@ -345,30 +369,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   const int rib = C::FINAL == 2 ? lane : grp * C::RPL + (lig >> 1);   // my row within a tile (epilogue)
   const bool lane_active = C::FINAL == 2 ? true : !(lig & 1);
 
-  long long n_iter = 0;
-  long long cold = 0;
   unsigned tb_mod = 0, tb_div = 0;   // (tiles consumed so far) % S and / S, kept incrementally
-  unsigned long long Tbase = 0;
-  uint32_t epoch = 0;
-  int status = 0;
-  int converged = 0;
-  double l_di = 0, l_dj = 0;   // leader-only: last step ...
-  int l_i = -1, l_j = -1;      // ... its pair and new alphas (stored one sweep later, forwarded meanwhile)
-  int l_ri = -1, l_rj = -1, l_si = -1, l_sj = -1;   // ... and its rows / cache slots (same deferral)
-  int n_cached = (int)P.cache_used;   // slots handed out so far (identical in every leader)
-  long long warm_cnt = 0, stored_cnt = 0;
-  double l_ai = 0, l_aj = 0;
-  long long cta_sweep_start_prev = 0;   // debug
+#ifdef B2SVM_TIMELINE
+  long long cta_sweep_start_prev = 0;
+#endif
+  long long cold = 0;                // cold sweeps so far (every warp counts; the producer drains cold * NT tiles)
+  uint32_t epoch = 0;                // exchanges so far; sweeps completed = epoch - 1
 
   Cand best[NCAND];
   auto reset_best = [&]() {
 #pragma unroll
     for (int k = 0; k < NCAND; ++k) { best[k].g = 0.0; best[k].idx = -1; best[k].flags = 0; }
   };
+#ifdef B2SVM_TIMELINE
   auto stamp = [&](int slot) {
     if (P.timeline && cta == 0 && threadIdx.x == 0 && epoch >= 1 && epoch <= (uint32_t)TL_ITERS)
       P.timeline[(epoch - 1) * TL_SLOTS + slot] = clock64();
   };
+#else
+  auto stamp = [&](int) {};
+#endif
   // alpha of any variable: the caller's array on one GPU, the owner's published copy otherwise
   auto read_alpha = [&](int idx) -> double {
     if (world == 1) return __ldcg(alpha + idx);
@@ -406,7 +426,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         if (mirror) { r.g1 = G[row + l]; r.f1 = flags[row + l]; }
       }
       r.nt = norms[row];
-      if (sweep_warm) {
+      if (CACHE && sweep_warm) {
         r.ki = cache_i[row];
         r.kj = cache_j[row];
       }
@@ -440,6 +460,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     stamp(1);   // all warps of this CTA done
 
     if (warp == 0) {
+      LeaderState L = sh->leader;
+      int status = 0;
+      const long long n_iter = (long long)epoch - 1;
       // CTA-level winner per type -> tagged record in global memory (two types per pass, 16 lanes each)
       for (int k0 = 0; k0 < ntypes; k0 += 2) {
         const int k = k0 + (lane >> 4), src = lane & 15;
@@ -448,17 +471,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         if (src < NW) m = sh->wc[src][k];
         redux_select(lane < 16 ? 0x0000ffffu : 0xffff0000u, (k & 1) == 0, m);
         if (src == 0) {
-          uint4* rp = P.cand + ((size_t)(epoch & 1) * ncta + cta) * NCAND + k;
+          uint4* rp = P.cand + (((size_t)(epoch & 1) * ncta + cta) * NCAND + k) * REC_STRIDE;
           st_relaxed_v4(rp, make_uint4((uint32_t)__double2loint(m.g), (uint32_t)__double2hiint(m.g), (uint32_t)m.idx,
                                        (epoch << 3) | (uint32_t)m.flags));
         }
       }
       if (lane == 0) sh->ticket = NW;   // next sweep: tiles 0..NW-1 are static, the rest are drawn here
       stamp(2);   // published
+#ifdef B2SVM_TIMELINE
       if (P.timeline && threadIdx.x == 0 && epoch == 11u && cta < 160) {
         P.timeline[TL_CTA_BASE + 2 * cta] = clock64() - cta_sweep_start_prev;
         P.timeline[TL_CTA_BASE + 2 * cta + 1] = NT;
       }
+#endif
 
       // read every CTA's record of this epoch (this is the grid barrier)
       Cand w[NCAND];
@@ -468,19 +493,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         bool all = true;
 #pragma unroll
         for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; }
-        for (int c = lane; c < ncta; c += 32) {
-          const uint4* rp = P.cand + ((size_t)(epoch & 1) * ncta + c) * NCAND;
+        // all loads of a pass are issued before any is looked at: one L2 round trip per pass, not one per record
+        constexpr int MAXC = 5;   // ceil(160 CTAs / 32 lanes)
+        const uint4* rbase = P.cand + (size_t)(epoch & 1) * ncta * NCAND * REC_STRIDE;
+        for (int k0 = 0; k0 < ntypes; k0 += 2) {
+          uint4 h[MAXC][2];
 #pragma unroll
-          for (int k = 0; k < NCAND; ++k) {
-            if (k < ntypes) {
-              const uint4 h = ld_relaxed_v4(rp + k);
-              if ((h.w >> 3) != epoch) {
-                all = false;
-              } else {
-                const double g = __hiloint2double((int)h.y, (int)h.x);
-                const int idx = (int)h.z;
-                const bool take = (k & 1) == 0 ? better_max(g, idx, w[k].g, w[k].idx) : better_min(g, idx, w[k].g, w[k].idx);
-                if (take) { w[k].g = g; w[k].idx = idx; w[k].flags = (int)(h.w & 7u); }
+          for (int m = 0; m < MAXC; ++m) {
+            const int c = lane + 32 * m;
+            if (c < ncta) {
+              h[m][0] = ld_relaxed_v4(rbase + ((size_t)c * NCAND + k0) * REC_STRIDE);
+              h[m][1] = ld_relaxed_v4(rbase + ((size_t)c * NCAND + k0 + 1) * REC_STRIDE);
+            }
+          }
+#pragma unroll
+          for (int m = 0; m < MAXC; ++m) {
+            const int c = lane + 32 * m;
+            if (c < ncta) {
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint4 hh = h[m][kk];
+                if ((hh.w >> 3) != epoch) {
+                  all = false;
+                } else {
+                  const double g = __hiloint2double((int)hh.y, (int)hh.x);
+                  const int idx = (int)hh.z;
+                  Cand& wk = (k0 == 0) ? w[kk] : w[2 + kk];
+                  const bool take = kk == 0 ? better_max(g, idx, wk.g, wk.idx) : better_min(g, idx, wk.g, wk.idx);
+                  if (take) { wk.g = g; wk.idx = idx; wk.flags = (int)(hh.w & 7u); }
+                }
               }
             }
           }
@@ -570,8 +611,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         gi = w[0].g; gj = w[1].g; fi = w[0].flags; fj = w[1].flags;
         stop_sel = si < 0 || sj < 0 || (gi - gj < P.tol);
         if (!stop_sel) {
-          ai = si == l_i ? l_ai : (si == l_j ? l_aj : read_alpha(si));
-          aj = sj == l_i ? l_ai : (sj == l_j ? l_aj : read_alpha(sj));
+          ai = si == L.i ? L.ai : (si == L.j ? L.aj : read_alpha(si));
+          aj = sj == L.i ? L.ai : (sj == L.j ? L.aj : read_alpha(sj));
         }
       } else {
         // solver.py:300-339: no tol test, gain comparison between the class-wise pairs
@@ -610,24 +651,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           const Cand& a = pick == 0 ? w[0] : w[2];
           const Cand& b = pick == 0 ? w[1] : w[3];
           si = a.idx; sj = b.idx; gi = a.g; gj = b.g; fi = a.flags; fj = b.flags;
-          ai = si == l_i ? l_ai : (si == l_j ? l_aj : read_alpha(si));
-          aj = sj == l_i ? l_ai : (sj == l_j ? l_aj : read_alpha(sj));
+          ai = si == L.i ? L.ai : (si == L.j ? L.aj : read_alpha(si));
+          aj = sj == L.i ? L.ai : (sj == L.j ? L.aj : read_alpha(sj));
         }
       }
 
+#ifdef B2SVM_TIMELINE
       if (P.dbg_steps && lane == 0 && epoch <= (uint32_t)DBG_EPOCHS) {
         double* o = P.dbg_steps + ((size_t)(epoch - 1) * ncta + cta) * 6;
         o[0] = si; o[1] = sj; o[2] = gi; o[3] = gj; o[4] = ai; o[5] = aj;
       }
-      if (stop_sel) converged = 1;
+#endif
+      if (stop_sel) L.converged = 1;
       const bool exit_now = status || stop_sel || n_iter >= P.max_iter;
       if (exit_now) {
         if (lane == 0) {
           sh->stop = 1;
           if (cta == 0) {
-            if (l_i >= 0) {   // the last step's alphas are still pending: each rank flushes what it owns
-              const int pend[2] = {l_i, l_j};
-              const double pval[2] = {l_ai, l_aj};
+            if (L.i >= 0) {   // the last step's alphas are still pending: each rank flushes what it owns
+              const int pend[2] = {L.i, L.j};
+              const double pval[2] = {L.ai, L.aj};
               for (int q = 0; q < 2; ++q) {
                 const bool second = mirror && pend[q] >= lg;
                 const long long lrow = (second ? pend[q] - lg : pend[q]) - goff;
@@ -641,17 +684,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             r.n_iter = n_iter;
             r.last_i = stop_sel ? -1 : si;
             r.last_j = stop_sel ? -1 : sj;
-            r.cold_sweeps = cold;
-            r.warm_sweeps = warm_cnt;
-            r.cols_stored = stored_cnt;
-            r.cache_used = n_cached;
-            if (P.cache_slots > 0 && l_ri >= 0) {   // pending slot-table entries of the last step
-              if (l_si >= 0) P.slot_of[l_ri] = l_si;
-              if (l_sj >= 0) P.slot_of[l_rj] = l_sj;
+            r.cold_sweeps = n_iter - L.warm_cnt;
+            r.warm_sweeps = L.warm_cnt;
+            r.cols_stored = L.stored_cnt;
+            r.cache_used = L.n_cached;
+            if (CACHE && P.cache_slots > 0 && L.ri >= 0) {   // pending slot-table entries of the last step
+              if (L.si >= 0) P.slot_of[L.ri] = L.si;
+              if (L.sj >= 0) P.slot_of[L.rj] = L.sj;
             }
-            r.di = l_di;
-            r.dj = l_dj;
-            r.converged = converged;
+            r.di = L.di;
+            r.dj = L.dj;
+            r.converged = L.converged;
             r.status = status;
             r.pad[0] = r.pad[1] = 0;
             *P.result = r;
@@ -667,27 +710,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         // ---- Q-column cache: which of the two columns are already resident, which get stored now --------
         int slot_i = -1, slot_j = -1, store_i = 0, store_j = 0;
         const int gri = (int)((mirror && si >= lg) ? si - lg : si), grj = (int)((mirror && sj >= lg) ? sj - lg : sj);
-        if (P.cache_slots > 0) {
-          slot_i = gri == l_ri ? l_si : (gri == l_rj ? l_sj : __ldcg(P.slot_of + gri));
-          slot_j = grj == l_ri ? l_si : (grj == l_rj ? l_sj : __ldcg(P.slot_of + grj));
-          if (slot_i < 0 && n_cached < P.cache_slots) { slot_i = n_cached++; store_i = 1; }
+        if (CACHE && P.cache_slots > 0) {
+          slot_i = gri == L.ri ? L.si : (gri == L.rj ? L.sj : __ldcg(P.slot_of + gri));
+          slot_j = grj == L.ri ? L.si : (grj == L.rj ? L.sj : __ldcg(P.slot_of + grj));
+          if (slot_i < 0 && L.n_cached < P.cache_slots) { slot_i = L.n_cached++; store_i = 1; }
           if (grj == gri) { slot_j = slot_i; }
-          else if (slot_j < 0 && n_cached < P.cache_slots) { slot_j = n_cached++; store_j = 1; }
+          else if (slot_j < 0 && L.n_cached < P.cache_slots) { slot_j = L.n_cached++; store_j = 1; }
         }
-        const int warm = (P.cache_slots > 0 && slot_i >= 0 && slot_j >= 0 && !store_i && !store_j) ? 1 : 0;
+        const int warm = (CACHE && P.cache_slots > 0 && slot_i >= 0 && slot_j >= 0 && !store_i && !store_j) ? 1 : 0;
         if (lane == 0) {
           sh->slot_i = slot_i; sh->slot_j = slot_j; sh->store_i = store_i; sh->store_j = store_j; sh->warm = warm;
-          sh->p_ri = l_ri; sh->p_rj = l_rj; sh->p_si = l_si; sh->p_sj = l_sj;
-          sh->pi = l_i; sh->pj = l_j; sh->pai = l_ai; sh->paj = l_aj;
+          sh->p_ri = L.ri; sh->p_rj = L.rj; sh->p_si = L.si; sh->p_sj = L.sj;
+          sh->pi = L.i; sh->pj = L.j; sh->pai = L.ai; sh->paj = L.aj;
         }
-        l_ri = gri; l_rj = grj; l_si = slot_i; l_sj = slot_j;
-        if (warm) ++warm_cnt;
-        stored_cnt += store_i + store_j;
-        l_di = so.di; l_dj = so.dj; l_i = si; l_j = sj; l_ai = so.ai; l_aj = so.aj;
+        L.ri = gri; L.rj = grj; L.si = slot_i; L.sj = slot_j;
+        if (warm) ++L.warm_cnt;
+        L.stored_cnt += store_i + store_j;
+        L.di = so.di; L.dj = so.dj; L.i = si; L.j = sj; L.ai = so.ai; L.aj = so.aj;
+#ifdef B2SVM_TIMELINE
         if (P.dbg_steps && lane == 0 && cta == 0 && epoch <= (uint32_t)DBG_EPOCHS) {
           double* o = P.dbg_steps + (size_t)DBG_EPOCHS * ncta * 6 + (size_t)(epoch - 1) * 2;
           o[0] = so.ai; o[1] = so.aj;
         }
+#endif
 #pragma unroll
         for (int q = 0; q < QL; ++q) {
           const int c = lane + 32 * q;
@@ -706,6 +751,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           sh->fj = make_flags(yj > 0, so.aj, Cbox);
         }
       }
+      __syncwarp();
+      if (lane == 0) sh->leader = L;
       stamp(5);   // leader done: step taken, x_i / x_j staged
     }
     named_bar_sync(2, NW * 32);   // (A) selection + step visible to all consumer warps
@@ -726,15 +773,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     }
     reset_best();
     // ---- Q-column cache plan of this sweep ---------------------------------------------------------
-    const bool warm = sh->warm != 0;
-    const int store_i = sh->store_i, store_j = sh->store_j;
+    const bool warm = CACHE && sh->warm != 0;
+    const int store_i = CACHE ? sh->store_i : 0, store_j = CACHE ? sh->store_j : 0;
     T* const cache_base = reinterpret_cast<T*>(P.cache);
     T* const col_i = sh->slot_i >= 0 ? cache_base + (size_t)sh->slot_i * (size_t)l : nullptr;
     T* const col_j = sh->slot_j >= 0 ? cache_base + (size_t)sh->slot_j * (size_t)l : nullptr;
     sweep_warm = warm;
     cache_i = col_i;
     cache_j = col_j;
-    if (P.cache_slots > 0 && cta == 0 && warp == NW - 1 && lane == 0 && sh->p_ri >= 0) {
+    if (CACHE && P.cache_slots > 0 && cta == 0 && warp == NW - 1 && lane == 0 && sh->p_ri >= 0) {
       // the previous step's slot-table entries, one sweep late (a slow leader may still have been reading them)
       if (sh->p_si >= 0) P.slot_of[sh->p_ri] = sh->p_si;
       if (sh->p_sj >= 0) P.slot_of[sh->p_rj] = sh->p_sj;
@@ -744,13 +791,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       const long long r0w = row0 + (long long)warp * C::BR + rib;
       if (warp < NT && lane_active && r0w < row1) { pf.ki = col_i[r0w]; pf.kj = col_j[r0w]; }
     }
+#ifdef B2SVM_TIMELINE
     long long cta_sweep_start = 0;
     if (P.timeline && threadIdx.x == 0 && epoch == 10u) cta_sweep_start = clock64() + (long long)(ci == 123.456);
-
     const bool dbg = P.timeline && cta == 0 && epoch == 10u;
     const long long dbg_start = dbg ? clock64() : 0;
     long long dbg_wait = 0;
     int dbg_tiles = 0;
+#endif
     int t = warp;                       // first tile is static (its gradient state is already in pf)
     while (t < NT) {
       // draw the next tile now so its gradient state can be prefetched a full tile of work ahead
@@ -776,7 +824,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           stage = q % S;
           use = tb_div + q / S;
         }
+#ifdef B2SVM_TIMELINE
         const long long dbg_w0 = dbg ? clock64() : 0;
+#endif
         {
           uint32_t spins = 0;
           uint64_t t_wait = 0;
@@ -791,7 +841,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             }
           }
         }
+#ifdef B2SVM_TIMELINE
         if (dbg) { dbg_wait += clock64() - dbg_w0; ++dbg_tiles; }
+#endif
         const unsigned char* base = ring + (size_t)stage * C::TILE_BYTES + (size_t)grp * C::RPL * C::ROWB + lig * 16;
         T acc[C::NV];
 #pragma unroll
@@ -853,11 +905,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       }
       t = tn;
     }
+#ifdef B2SVM_TIMELINE
     if (cta_sweep_start) cta_sweep_start_prev = cta_sweep_start;
     if (dbg && lane == 0) {
       long long* o = P.timeline + TL_ITERS * TL_SLOTS + warp * TL_WARP_SLOTS;
       o[0] = dbg_start; o[1] = clock64(); o[2] = dbg_tiles; o[3] = dbg_wait;
     }
+#endif
     sweep_warm = false;
     pf = load_row_state(warp);   // first tile of the next sweep (after this thread's own stores to it)
     if (!warm) {
@@ -866,15 +920,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         tb_mod = q % S;
         tb_div = tb_div + q / S;
       }
-      Tbase += (unsigned long long)NT;
       ++cold;
     }
-    ++n_iter;
   }
 
   // ---- exit: tell the producer how far the consumers got, let it drain --------------------------
   if (threadIdx.x == 0) {
-    sh->consumed = (long long)Tbase;
+    sh->consumed = cold * (long long)NT;
     __threadfence_block();
     sh->producer_stop = 1;
   }

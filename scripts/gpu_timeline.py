@@ -13,7 +13,7 @@ def run(n, d, iters, dtype=np.float32):
     Xs, ys = O.synth_classification(n=n, d=d, seed=0)
     Xs = Xs.astype(dtype)
     yv = np.where(ys == 1, 1.0, -1.0)
-    func = S.QColumns(Xs, yv, S.KernelSpec("rbf", 1 / (d * Xs.std())))
+    func = S.QColumns(Xs, yv, S.KernelSpec("rbf", 1 / (d * Xs.std())), cache_bytes=int(os.environ.get("CACHE_BYTES", "0")))
     sol = S.SolverWithCache(-np.ones(n), yv, 1.0, func=func)
     sol.solve(iters)
     st = sol.solve(iters)
