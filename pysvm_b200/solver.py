@@ -399,3 +399,25 @@ def kernel_matvec(kernel: KernelSpec, Xa: torch.Tensor, coef: torch.Tensor, Xb: 
                                     Xa.data_ptr(), Xa.shape[0], Xa.stride(0), Xb.data_ptr(), Xb.shape[0], Xb.stride(0),
                                     coef.data_ptr(), out.data_ptr()))
     return out
+
+
+def solve_batched(solvers, max_iter: int):
+    """Solve several independent problems concurrently, one CTA group each, in ONE persistent launch
+    (``b2svm_solve_batched``): the one-vs-one / one-vs-rest sub-problems of the multiclass wrappers
+    (reference svc.py:332-342 + sklearn.multiclass).  Problems are grouped by (dtype, row width)."""
+    lib = N.load()
+    groups = {}
+    for s in solvers:
+        eng = s._need()
+        key = (eng.desc.x_dtype, eng.desc.n_features, eng.desc.device)
+        groups.setdefault(key, []).append(s)
+    for group in groups.values():
+        n = len(group)
+        handles = (C.c_void_p * n)(*[s._engine.h for s in group])
+        stats = (N.SolveStats * n)()
+        N.check(lib.b2svm_solve_batched(handles, n, int(max_iter), stats))
+        for s, st in zip(group, stats):
+            cp = N.SolveStats()
+            C.memmove(C.byref(cp), C.byref(st), C.sizeof(N.SolveStats))
+            s.last_stats = cp
+    return [s.last_stats for s in solvers]

@@ -1,6 +1,8 @@
 """Classification estimators with PySVM's API (reference ``pysvm/svm/svc.py``), solved on the GPU."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 from sklearn.base import BaseEstimator
@@ -9,7 +11,35 @@ from sklearn.multiclass import OneVsOneClassifier, OneVsRestClassifier
 
 from ..rff import NormalRFF, rff_decision_device
 from ..solver import (KernelSpec, NuSolverWithCache, QColumns, SolverWithCache, default_device, kernel_matvec,
-                      to_device_matrix)
+                      solve_batched, to_device_matrix)
+
+
+# ---- batching of small independent sub-problems (one-vs-one / one-vs-rest) --------------------------------
+_PENDING = None                  # list of (estimator, solver, finish) while a multiclass wrapper is fitting
+BATCH_MAX_ROWS = int(os.environ.get("B2SVM_BATCH_MAX_ROWS", "4096"))
+
+
+class deferred_solves:
+    """While active, ``Bi*.fit`` on a small problem uploads its data and creates its device solver but
+    leaves the SMO loop to ``run()``, which solves all collected sub-problems in one persistent launch
+    (one CTA each).  sklearn's OneVsOne / OneVsRest code stays in charge of everything else."""
+
+    def __enter__(self):
+        global _PENDING
+        self._saved, _PENDING = _PENDING, []
+        self.items = _PENDING
+        return self
+
+    def __exit__(self, *exc):
+        global _PENDING
+        _PENDING = self._saved
+
+    def run(self, max_iter):
+        if not self.items:
+            return
+        stats = solve_batched([it[1] for it in self.items], max_iter)
+        for (est, solver, finish), st in zip(self.items, stats):
+            finish(st)
 
 
 class _Fitted:
@@ -59,11 +89,18 @@ class BiLinearSVC(BaseEstimator):
         p = -np.ones(l)
         func = QColumns(X, y, KernelSpec("linear"))
         solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func)
-        self._report(solver.solve(self.max_iter))
-        # svc.py:76 accumulates w += delta_i y_i x_i + delta_j y_j x_j; the sum telescopes to X^T (alpha*y)
-        w = (func.X.to(torch.float64).t() @ (solver.alpha * func.y)).cpu().numpy()
-        self.coef_ = (w, solver.calculate_rho())
-        self._fitted = _Fitted(solver, func, func.kernel, solver.alpha * func.y)
+
+        def finish(stats):
+            self._report(stats)
+            # svc.py:76 accumulates w += delta_i y_i x_i + delta_j y_j x_j; the sum telescopes to X^T (alpha*y)
+            w = (func.X.to(torch.float64).t() @ (solver.alpha * func.y)).cpu().numpy()
+            self.coef_ = (w, solver.calculate_rho())
+            self._fitted = _Fitted(solver, func, func.kernel, solver.alpha * func.y)
+
+        if _PENDING is not None and l <= BATCH_MAX_ROWS:
+            _PENDING.append((self, solver, finish))
+        else:
+            finish(solver.solve(self.max_iter))
         return self
 
     def decision_function(self, X) -> np.ndarray:
@@ -89,7 +126,10 @@ class LinearSVC(BiLinearSVC):
         self.multiclass_model = {"ovo": OneVsOneClassifier(**params), "ovr": OneVsRestClassifier(**params)}[multiclass]
 
     def fit(self, X, y):
-        self.multiclass_model.fit(X, y)
+        # sklearn builds the sub-problems (svc.py:134-149); their SMO loops run together on the GPU
+        with deferred_solves() as batch:
+            self.multiclass_model.fit(X, y)
+        batch.run(self.max_iter)
         return self
 
     def decision_function(self, X):
@@ -152,8 +192,15 @@ class BiKernelSVC(BiLinearSVC):
             return self._fit_sharded(X, y, sharded)
         func, spec, rff = self._columns(X, y)
         solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func)
-        self._report(solver.solve(self.max_iter))
-        self._finish(solver, func, spec, rff, X, solver.alpha * func.y)
+
+        def finish(stats):
+            self._report(stats)
+            self._finish(solver, func, spec, rff, X, solver.alpha * func.y)
+
+        if _PENDING is not None and l <= BATCH_MAX_ROWS:
+            _PENDING.append((self, solver, finish))       # solved together with its sibling sub-problems
+        else:
+            finish(solver.solve(self.max_iter))
         return self
 
     def _finish(self, solver, func, spec, rff, X, coef):
@@ -234,9 +281,16 @@ class BiNuSVC(BiKernelSVC):
         p = np.zeros(l)
         func, spec, rff = self._columns(X, y)
         solver = NuSolverWithCache(p, y, self.nu * l, self.C, func, self.tol, self.cache_size)
-        self._report(solver.solve(self.max_iter))
-        self._finish(solver, func, spec, rff, X, solver.alpha * func.y)
-        self.rho_, self.b_ = solver.calculate_rho_b()
+
+        def finish(stats):
+            self._report(stats)
+            self._finish(solver, func, spec, rff, X, solver.alpha * func.y)
+            self.rho_, self.b_ = solver.calculate_rho_b()
+
+        if _PENDING is not None and l <= BATCH_MAX_ROWS:
+            _PENDING.append((self, solver, finish))
+        else:
+            finish(solver.solve(self.max_iter))
         return self
 
     def decision_function(self, x) -> np.ndarray:
