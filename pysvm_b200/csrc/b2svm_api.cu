@@ -179,16 +179,6 @@ __global__ void finish_gradient_kernel(const double* __restrict__ y, const doubl
   }
 }
 
-// published alpha of a shard: [first half | second half], each rows_per_rank long (the peers index it
-// without knowing this rank's row count)
-__global__ void publish_alpha_kernel(const double* __restrict__ alpha, int64_t l, int64_t nv, int64_t rpr,
-                                     double* __restrict__ pub) {
-  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
-    const bool second = v >= l;
-    pub[(second ? rpr : 0) + (second ? v - l : v)] = alpha[v];
-  }
-}
-
 }  // namespace b2svm
 
 using namespace b2svm;
@@ -221,12 +211,12 @@ struct b2svm_handle {
   long long ntiles = 0;
   size_t smem_bytes = 0;
   int launches = 0;
-  // ---- row-sharded multi-GPU: one IPC-shareable block [mailbox | norms | published alpha | X slice]
+  // ---- row-sharded multi-GPU: one IPC-shareable block [record mailbox | payload mailbox]
   unsigned char* block = nullptr;
-  size_t block_bytes = 0, off_norms = 0, off_alpha = 0, off_x = 0;
+  size_t block_bytes = 0, off_pay = 0;
   long long rows_per_rank = 0;
   std::vector<void*> peer_blocks;          // opened IPC mappings (nullptr for this rank)
-  void** peer_tables = nullptr;            // device: [4][world] = mbox, X, norms, alpha pointers of every rank
+  void** peer_tables = nullptr;            // device: [2][world] = record / payload mailbox pointers of every rank
   bool attached = false, prepared = false;
   void* cache = nullptr;          // Q-column cache [cache_slots][n_rows] in the input dtype
   int* slot_of = nullptr;
@@ -247,8 +237,8 @@ inline int grid_for(int64_t n, int block = 256, int cap = 148 * 8) {
 template <typename T, int CH>
 struct Geometry {
   using C = Cfg<T, CH>;
-  static size_t smem_for(int stages) {
-    return (size_t)stages * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + MAX_STAGES * sizeof(unsigned) +
+  static size_t smem_for(int stages, bool multi) {
+    return (multi ? (size_t)NCAND * C::PAY_STRIDE : 0) + (size_t)stages * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + MAX_STAGES * sizeof(unsigned) +
            2 * (size_t)C::ROWB +
            sizeof(Shared<T>) + 128;
   }
@@ -262,9 +252,10 @@ int plan_T(b2svm_handle* h) {
   using C = Cfg<T, CH>;
   int stages = (int)std::min<size_t>(MAX_STAGES, kRingBudget / C::TILE_BYTES);
   if (stages < 2) stages = 2;
-  while (stages > 2 && Geometry<T, CH>::smem_for(stages) > kSmemBudget) --stages;
+  const bool multi = h->d.world > 1;
+  while (stages > 2 && Geometry<T, CH>::smem_for(stages, multi) > kSmemBudget) --stages;
   h->stages = stages;
-  h->smem_bytes = Geometry<T, CH>::smem_for(stages);
+  h->smem_bytes = Geometry<T, CH>::smem_for(stages, multi);
   h->ntiles = (h->d.n_rows + C::BR - 1) / C::BR;
   int min_tiles = NW;
   if (const char* e = getenv("B2SVM_MIN_TILES_PER_CTA")) min_tiles = std::max(1, atoi(e));
@@ -344,11 +335,9 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.rows_per_rank = h->d.world > 1 ? h->rows_per_rank : h->d.n_rows;
   if (h->d.world > 1) {
     P.mbox = reinterpret_cast<uint4*>(h->block);
+    P.mbox_pay = reinterpret_cast<uint4*>(h->block + h->off_pay);
     P.peer_mbox = reinterpret_cast<uint4* const*>(h->peer_tables);
-    P.peer_X = reinterpret_cast<const void* const*>(h->peer_tables + h->d.world);
-    P.peer_norms = reinterpret_cast<const void* const*>(h->peer_tables + 2 * h->d.world);
-    P.peer_alpha = reinterpret_cast<const double* const*>(h->peer_tables + 3 * h->d.world);
-    P.alpha_pub = reinterpret_cast<double*>(h->block + h->off_alpha);
+    P.peer_pay = reinterpret_cast<uint4* const*>(h->peer_tables + h->d.world);
   }
   P.timeline = h->timeline;
   P.dbg_steps = h->dbg_steps;
@@ -367,10 +356,7 @@ int prepare_launch(b2svm_handle* h) {
   B2_CUDA(cudaMemsetAsync(h->cand, 0, h->cand_bytes, h->stream));
   B2_CUDA(cudaMemsetAsync(h->abort_flag, 0, sizeof(int), h->stream));
   if (h->d.world > 1) {
-    B2_CUDA(cudaMemsetAsync(h->block, 0, h->off_norms, h->stream));
-    publish_alpha_kernel<<<grid_for(nv), 256, 0, h->stream>>>(h->d.alpha, h->d.n_rows, nv, h->rows_per_rank,
-                                                              reinterpret_cast<double*>(h->block + h->off_alpha));
-    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
     B2_CUDA(cudaStreamSynchronize(h->stream));
   }
   h->prepared = true;
@@ -466,24 +452,17 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     if (desc->row_offset != (long long)desc->rank * rpr || desc->n_rows != want)
       return cleanup_fail(B2SVM_E_INVALID, "shard must be rows [rank*rpr, min(n,(rank+1)*rpr)), rpr = roundup32(ceil(n/world))");
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    h->off_norms = up(sizeof(uint4) * 2 * desc->world * NCAND);
-    h->off_alpha = h->off_norms + up((size_t)rpr * esz);
-    h->off_x = h->off_alpha + up((size_t)2 * rpr * sizeof(double));
-    h->block_bytes = h->off_x + (size_t)rpr * h->dp * esz;
+    h->off_pay = up(sizeof(uint4) * 2 * desc->world * NCAND);
+    h->block_bytes = h->off_pay + sizeof(uint4) * 2 * (size_t)desc->world * NCAND * PAY_UNITS_MAX;
     B2_TRY(cudaMalloc(&h->block, h->block_bytes));
     B2_TRY(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
   }
-  const bool in_place = desc->world <= 1 && desc->ldx == h->dp && desc->n_features == h->dp && ((uintptr_t)desc->X % 16 == 0);
+  const bool in_place = desc->ldx == h->dp && desc->n_features == h->dp && ((uintptr_t)desc->X % 16 == 0);
   if (in_place) {
     h->Xuse = desc->X;
   } else {
-    void* xdst = nullptr;
-    if (desc->world > 1) {
-      xdst = h->block + h->off_x;
-    } else {
-      B2_TRY(cudaMalloc(&h->Xown, (size_t)l * h->dp * esz));
-      xdst = h->Xown;
-    }
+    B2_TRY(cudaMalloc(&h->Xown, (size_t)l * h->dp * esz));
+    void* xdst = h->Xown;
     if (h->f64)
       pad_rows_kernel<double><<<grid_for(l * h->dp), 256, 0, h->stream>>>((const double*)desc->X, desc->ldx,
                                                                           (double*)xdst, l, desc->n_features, h->dp);
@@ -493,8 +472,7 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     B2_TRY(cudaGetLastError());
     h->Xuse = xdst;
   }
-  if (desc->world > 1) h->norms = h->block + h->off_norms;
-  else B2_TRY(cudaMalloc(&h->norms, (size_t)l * esz));
+  B2_TRY(cudaMalloc(&h->norms, (size_t)l * esz));
   if (h->f64)
     row_norms_kernel<double><<<grid_for(l * 32), 256, 0, h->stream>>>((const double*)h->Xuse, l, h->dp, (double*)h->norms);
   else
@@ -546,7 +524,7 @@ int b2svm_destroy(b2svm_handle* h) {
   cudaSetDevice(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream); else cudaDeviceSynchronize();
   cudaFree(h->Xown);
-  if (!h->block) cudaFree(h->norms);
+  cudaFree(h->norms);
   for (void* pb : h->peer_blocks)
     if (pb) cudaIpcCloseMemHandle(pb);
   cudaFree(h->peer_tables);
@@ -846,7 +824,7 @@ int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles) {
   B2_CUDA(cudaSetDevice(h->d.device));
   const int world = h->d.world;
   h->peer_blocks.assign(world, nullptr);
-  std::vector<void*> tab(4 * (size_t)world);
+  std::vector<void*> tab(2 * (size_t)world);
   for (int r = 0; r < world; ++r) {
     unsigned char* base = h->block;
     if (r != h->d.rank) {
@@ -857,10 +835,8 @@ int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles) {
       h->peer_blocks[r] = p;
       base = reinterpret_cast<unsigned char*>(p);
     }
-    tab[r] = base;                              // mailbox
-    tab[world + r] = base + h->off_x;           // X slice
-    tab[2 * world + r] = base + h->off_norms;   // norms
-    tab[3 * world + r] = base + h->off_alpha;   // published alpha
+    tab[r] = base;                       // record mailbox
+    tab[world + r] = base + h->off_pay;  // payload mailbox
   }
   B2_CUDA(cudaMalloc(&h->peer_tables, sizeof(void*) * tab.size()));
   B2_CUDA(cudaMemcpy(h->peer_tables, tab.data(), sizeof(void*) * tab.size(), cudaMemcpyHostToDevice));

@@ -37,6 +37,10 @@ constexpr int NTHREADS = (NW + 1) * 32;    // + one producer warp
 constexpr int MAX_STAGES = 64;
 constexpr int NCAND = 4;                   // up/low (C variant) or up+/low+/up-/low- (nu variant)
 constexpr int REC_STRIDE = 1;              // one 128-byte line per record (uint4 units): spreads the polling over L2 slices
+// Cross-GPU payload: {alpha 8 B, norm 8 B, row} of a winning variable, shipped as 16-byte units of 12 data
+// bytes + a 4-byte epoch tag so that every unit validates itself (no fence between data and flag).
+constexpr int PAY_HDR = 16;
+constexpr int PAY_UNITS_MAX = (PAY_HDR + 128 * 16 + 11) / 12;
 constexpr int TL_ITERS = 64, TL_SLOTS = 8; // debug timeline
 constexpr int DBG_EPOCHS = 2048;
 constexpr int TL_WARP_SLOTS = 4;           // + per-warp {start, end, tiles, wait} of one sweep
@@ -82,12 +86,10 @@ struct ProblemDev {
   // ---- row-sharded multi-GPU (world > 1): this GPU owns global rows [row_offset, row_offset + l) --------
   int world, rank;
   long long row_offset, l_global, rows_per_rank;   // every rank's slice starts at rank * rows_per_rank
-  uint4* mbox;                    // local mailbox [2][world][NCAND], written by the peers over NVLink
-  uint4* const* peer_mbox;        // [world] every rank's mailbox (peer mapping; own entry = local)
-  const void* const* peer_X;      // [world] every rank's padded X slice
-  const void* const* peer_norms;  // [world]
-  const double* const* peer_alpha;   // [world] every rank's published alpha [2][rows_per_rank]
-  double* alpha_pub;              // this rank's published alpha (the peers read it)
+  uint4* mbox;                    // local record mailbox [2][world][NCAND], written by the peers over NVLink
+  uint4* mbox_pay;                // local payload mailbox [2][world][NCAND][PAY_UNITS_MAX]: winner alpha, norm, row
+  uint4* const* peer_mbox;        // [world] every rank's record mailbox (peer mapping; own entry = local)
+  uint4* const* peer_pay;         // [world] every rank's payload mailbox
   double* dbg_steps;              // optional [DBG_EPOCHS][ncta][6] = si, sj, gi, gj, ai, aj seen by each leader
   int debug_flags;                // B2SVM_DEBUG_FLAGS: 1 = static tile assignment, 2 = L2 loads for G/flags
 };
@@ -113,6 +115,8 @@ struct Cfg {
   static constexpr int NV = 2 * RPL;                               // partial sums per lane
   static constexpr int ROWB = CH * 16;
   static constexpr int TILE_BYTES = BR * ROWB;
+  static constexpr int PAY_UNITS = (PAY_HDR + ROWB + 11) / 12;          // cross-GPU payload units per winner
+  static constexpr int PAY_STRIDE = (PAY_UNITS * 12 + 15) / 16 * 16;    // staging bytes per candidate type
 };
 
 // State only the leader warp needs between iterations.  It lives in shared memory and is loaded into
@@ -164,33 +168,29 @@ __device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (
   }
 }
 
-// Where variable `idx` lives: its row in the owner's X slice, its norm, its published alpha.
+// Where the leader finds variable `idx`: its row, its norm and its alpha.  On one GPU these are the
+// problem's own arrays; in a row-sharded solve they are the payload the owner GPU pushed with its record,
+// staged in shared memory (alpha as double at +0, norm as T at +8, the row at +16).
 template <typename T>
 struct VarRef {
   const typename Chunk<T>::V* row;
   const T* norm;
-  const double* alpha;     // nullptr on a single GPU (the caller's alpha array is used)
-  int owner;
 };
 template <typename T, int CH>
 __device__ __forceinline__ VarRef<T> locate(const ProblemDev& P, int idx) {
   using V = typename Chunk<T>::V;
   VarRef<T> r;
-  const bool second = P.mirror && idx >= P.l_global;
-  const long long grow = second ? idx - P.l_global : idx;
-  if (P.world == 1) {
-    r.owner = 0;
-    r.row = reinterpret_cast<const V*>(P.X) + grow * CH;
-    r.norm = reinterpret_cast<const T*>(P.norms) + grow;
-    r.alpha = nullptr;
-  } else {
-    const int rk = (int)(grow / P.rows_per_rank);
-    const long long lrow = grow - (long long)rk * P.rows_per_rank;
-    r.owner = rk;
-    r.row = reinterpret_cast<const V*>(P.peer_X[rk]) + lrow * CH;
-    r.norm = reinterpret_cast<const T*>(P.peer_norms[rk]) + lrow;
-    r.alpha = P.peer_alpha[rk] + (second ? P.rows_per_rank : 0) + lrow;
-  }
+  const long long grow = (P.mirror && idx >= P.l_global) ? idx - P.l_global : idx;
+  const long long lrow = grow - P.row_offset;          // single GPU: row_offset == 0
+  r.row = reinterpret_cast<const V*>(P.X) + lrow * CH;
+  r.norm = reinterpret_cast<const T*>(P.norms) + lrow;
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ VarRef<T> staged(const unsigned char* sb) {
+  VarRef<T> r;
+  r.row = reinterpret_cast<const typename Chunk<T>::V*>(sb + PAY_HDR);
+  r.norm = reinterpret_cast<const T*>(sb + 8);
   return r;
 }
 
@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   volatile unsigned* gen = reinterpret_cast<volatile unsigned*>(empty + MAX_STAGES);
   V* xs = reinterpret_cast<V*>(const_cast<unsigned*>(gen) + MAX_STAGES);      // [2][CH]
   Shared<T>* sh = reinterpret_cast<Shared<T>*>(xs + 2 * CH);
+  // winner payloads of a row-sharded solve (only allocated when world > 1)
+  unsigned char* stagebuf = reinterpret_cast<unsigned char*>(sh) + (sizeof(Shared<T>) + 15) / 16 * 16;
 
   const ProblemDev& P = probs[blockIdx.x / ncta_pp];
   const int cta = blockIdx.x % ncta_pp;
@@ -389,20 +391,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
 #else
   auto stamp = [&](int) {};
 #endif
-  // alpha of any variable: the caller's array on one GPU, the owner's published copy otherwise
-  auto read_alpha = [&](int idx) -> double {
+  // local index of a variable this GPU owns
+  auto local_var = [&](int idx) -> long long {
+    const bool second = mirror && idx >= lg;
+    return (second ? l : 0) + ((second ? idx - lg : idx) - goff);
+  };
+  // alpha / row / norm of a winner of candidate type `type`
+  auto read_alpha = [&](int idx, int type) -> double {
     if (world == 1) return __ldcg(alpha + idx);
-    return ld_relaxed_sys_f64(locate<T, CH>(P, idx).alpha);
+    return *reinterpret_cast<const double*>(stagebuf + type * C::PAY_STRIDE);
+  };
+  auto ref_of = [&](int idx, int type) -> VarRef<T> {
+    if (world == 1) return locate<T, CH>(P, idx);
+    return staged<T>(stagebuf + type * C::PAY_STRIDE);
   };
   // deferred store of a step's new alpha by the lane that owns the variable (local index lv)
-  auto store_alpha = [&](long long lv, bool second, long long lrow, double a) {
+  auto store_alpha = [&](long long lv, double a) {
     alpha[lv] = a;
-    if (world > 1) {
-      P.alpha_pub[(second ? P.rows_per_rank : 0) + lrow] = a;
-      __threadfence_system();
-    } else {
-      __threadfence();
-    }
+    __threadfence();
   };
   // cache columns in use by the current / next sweep (set after bar (A))
   bool sweep_warm = false;
@@ -541,36 +547,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       for (int k = 0; k < NCAND; ++k)
         if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, w[k]);
       if (world > 1) {
-        // ---- cross-GPU exchange over NVLink: CTA 0 pushes this GPU's winners into every rank's mailbox
-        // (16-byte tagged records again), every leader polls the local mailbox, same reduction.
-        if (cta == 0 && lane < world * ntypes) {
-          const int r = lane / ntypes, k = lane - r * ntypes;
-          Cand m = w[0];
+        // ---- cross-GPU exchange over NVLink.  CTA 0 pushes, for every candidate type, this GPU's winner
+        // record AND its payload (alpha, norm, row) into every rank's mailboxes; every leader then polls
+        // its LOCAL mailboxes only.  Nothing is ever loaded across the link.
+        const uint32_t par = epoch & 1u;
+        if (cta == 0) {
+          for (int k = 0; k < ntypes; ++k) {
+            Cand m = w[0];
 #pragma unroll
-          for (int kk = 1; kk < NCAND; ++kk)
-            if (k == kk) m = w[kk];
-          uint4* rp = const_cast<uint4*>(P.peer_mbox[r]) + ((size_t)(epoch & 1) * world + P.rank) * NCAND + k;
-          st_relaxed_sys_v4(rp, make_uint4((uint32_t)__double2loint(m.g), (uint32_t)__double2hiint(m.g), (uint32_t)m.idx,
-                                           (epoch << 3) | (uint32_t)m.flags));
+            for (int kk = 1; kk < NCAND; ++kk)
+              if (k == kk) m = w[kk];
+            if (m.idx >= 0) {
+              unsigned char* sb = stagebuf + k * C::PAY_STRIDE;
+              const VarRef<T> A = locate<T, CH>(P, m.idx);
+              if (lane == 0) {
+                const double a = m.idx == L.i ? L.ai : (m.idx == L.j ? L.aj : __ldcg(alpha + local_var(m.idx)));
+                *reinterpret_cast<double*>(sb) = a;
+                *reinterpret_cast<T*>(sb + 8) = *A.norm;
+              }
+#pragma unroll
+              for (int q = 0; q < QL; ++q) {
+                const int c = lane + 32 * q;
+                if (c < CH) *reinterpret_cast<V*>(sb + PAY_HDR + 16 * c) = A.row[c];
+              }
+              __syncwarp();
+              for (int u = lane; u < C::PAY_UNITS; u += 32) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(sb + 12 * u);
+                const uint4 unit = make_uint4(src[0], src[1], src[2], epoch);
+                for (int r = 0; r < world; ++r) {
+                  uint4* pp = const_cast<uint4*>(P.peer_pay[r]) + (((size_t)par * world + P.rank) * NCAND + k) * PAY_UNITS_MAX;
+                  st_relaxed_sys_v4(pp + u, unit);
+                }
+              }
+              __syncwarp();
+            }
+          }
+          if (lane < world * ntypes) {
+            const int r = lane / ntypes, k = lane - r * ntypes;
+            Cand m = w[0];
+#pragma unroll
+            for (int kk = 1; kk < NCAND; ++kk)
+              if (k == kk) m = w[kk];
+            uint4* rp = const_cast<uint4*>(P.peer_mbox[r]) + ((size_t)par * world + P.rank) * NCAND + k;
+            st_relaxed_sys_v4(rp, make_uint4((uint32_t)__double2loint(m.g), (uint32_t)__double2hiint(m.g), (uint32_t)m.idx,
+                                             (epoch << 3) | (uint32_t)m.flags));
+          }
         }
         uint32_t rounds2 = 0;
         for (;;) {
           bool all = true;
 #pragma unroll
           for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; }
-          for (int r = lane; r < world; r += 32) {
-            const uint4* rp = P.mbox + ((size_t)(epoch & 1) * world + r) * NCAND;
+          if (lane < world) {
+            const uint4* rp = P.mbox + ((size_t)par * world + lane) * NCAND;
+            uint4 h[NCAND];
+#pragma unroll
+            for (int k = 0; k < NCAND; ++k)
+              if (k < ntypes) h[k] = ld_relaxed_sys_v4(rp + k);
 #pragma unroll
             for (int k = 0; k < NCAND; ++k) {
               if (k < ntypes) {
-                const uint4 h = ld_relaxed_sys_v4(rp + k);
-                if ((h.w >> 3) != epoch) {
+                if ((h[k].w >> 3) != epoch) {
                   all = false;
                 } else {
-                  const double g = __hiloint2double((int)h.y, (int)h.x);
-                  const int idx = (int)h.z;
-                  const bool take = (k & 1) == 0 ? better_max(g, idx, w[k].g, w[k].idx) : better_min(g, idx, w[k].g, w[k].idx);
-                  if (take) { w[k].g = g; w[k].idx = idx; w[k].flags = (int)(h.w & 7u); }
+                  w[k].g = __hiloint2double((int)h[k].y, (int)h[k].x);
+                  w[k].idx = (int)h[k].z;
+                  w[k].flags = (int)(h[k].w & 7u);
                 }
               }
             }
@@ -588,6 +630,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
 #pragma unroll
         for (int k = 0; k < NCAND; ++k)
           if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, w[k]);
+        // the global winners' payloads: wait until every 16-byte unit carries this epoch, stage them
+        for (int k = 0; k < ntypes && !status; ++k) {
+          Cand m = w[0];
+#pragma unroll
+          for (int kk = 1; kk < NCAND; ++kk)
+            if (k == kk) m = w[kk];
+          if (m.idx < 0) continue;
+          const long long grow = (mirror && m.idx >= lg) ? m.idx - lg : m.idx;
+          const int owner = (int)(grow / P.rows_per_rank);
+          const uint4* pp = P.mbox_pay + (((size_t)par * world + owner) * NCAND + k) * PAY_UNITS_MAX;
+          unsigned char* sb = stagebuf + k * C::PAY_STRIDE;
+          uint32_t rounds3 = 0;
+          for (;;) {
+            bool ok = true;
+            for (int u = lane; u < C::PAY_UNITS; u += 32) {
+              const uint4 h = ld_relaxed_sys_v4(pp + u);
+              if (h.w != epoch) {
+                ok = false;
+              } else {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(sb + 12 * u);
+                dst[0] = h.x; dst[1] = h.y; dst[2] = h.z;
+              }
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            if ((++rounds3 & 63u) == 0) {
+              int bad = *(volatile int*)P.abort_flag;
+              if (!bad && globaltimer_ns() - t_start > 8000000000ull) {
+                *(volatile int*)P.abort_flag = 1;
+                bad = 1;
+              }
+              if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
+            }
+          }
+        }
+        __syncwarp();
       }
       stamp(4);   // global winners known
 
@@ -599,6 +676,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       V xi[QL], xj[QL];
       T ni = 0, nj = 0, Kii = 0, Kjj = 0, Kij = 0;
       bool have_k = false;
+      int ti = 0, tj = 1;   // candidate types the pair came from (where a row-sharded solve staged their payload)
       if (forced && epoch == 1) {
         si = (int)P.forced_i;     // single GPU only (checked on the host)
         sj = (int)P.forced_j;
@@ -611,8 +689,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         gi = w[0].g; gj = w[1].g; fi = w[0].flags; fj = w[1].flags;
         stop_sel = si < 0 || sj < 0 || (gi - gj < P.tol);
         if (!stop_sel) {
-          ai = si == L.i ? L.ai : (si == L.j ? L.aj : read_alpha(si));
-          aj = sj == L.i ? L.ai : (sj == L.j ? L.aj : read_alpha(sj));
+          ai = si == L.i ? L.ai : (si == L.j ? L.aj : read_alpha(si, 0));
+          aj = sj == L.i ? L.ai : (sj == L.j ? L.aj : read_alpha(sj, 1));
         }
       } else {
         // solver.py:300-339: no tol test, gain comparison between the class-wise pairs
@@ -625,14 +703,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         else {
           V xa[QL], xb[QL];
           T na, nb, Kaa, Kbb, Kab;
-          pair_kernels<T, CH>(kp, locate<T, CH>(P, w[0].idx), locate<T, CH>(P, w[1].idx), lane, xa, xb, na, nb, Kaa, Kbb,
-                              Kab);
+          pair_kernels<T, CH>(kp, ref_of(w[0].idx, 0), ref_of(w[1].idx, 1), lane, xa, xb, na, nb, Kaa, Kbb, Kab);
           double quad_p = ((double)Kaa + (double)Kbb) - 2.0 * (double)Kab;
           if (quad_p <= 0) quad_p = 1e-12;
           const double dp = w[0].g - w[1].g;
           const double gain_p = -(dp * dp) / quad_p;
-          pair_kernels<T, CH>(kp, locate<T, CH>(P, w[2].idx), locate<T, CH>(P, w[3].idx), lane, xi, xj, ni, nj, Kii, Kjj,
-                              Kij);
+          pair_kernels<T, CH>(kp, ref_of(w[2].idx, 2), ref_of(w[3].idx, 3), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
           double quad_n = ((double)Kii + (double)Kjj) - 2.0 * (double)Kij;
           if (quad_n <= 0) quad_n = 1e-12;
           const double dn = w[2].g - w[3].g;
@@ -651,8 +727,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           const Cand& a = pick == 0 ? w[0] : w[2];
           const Cand& b = pick == 0 ? w[1] : w[3];
           si = a.idx; sj = b.idx; gi = a.g; gj = b.g; fi = a.flags; fj = b.flags;
-          ai = si == L.i ? L.ai : (si == L.j ? L.aj : read_alpha(si));
-          aj = sj == L.i ? L.ai : (sj == L.j ? L.aj : read_alpha(sj));
+          ti = pick == 0 ? 0 : 2;
+          tj = ti + 1;
+          ai = si == L.i ? L.ai : (si == L.j ? L.aj : read_alpha(si, ti));
+          aj = sj == L.i ? L.ai : (sj == L.j ? L.aj : read_alpha(sj, tj));
         }
       }
 
@@ -676,7 +754,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
                 const long long lrow = (second ? pend[q] - lg : pend[q]) - goff;
                 if (lrow >= 0 && lrow < l) {
                   alpha[(second ? l : 0) + lrow] = pval[q];
-                  if (world > 1) P.alpha_pub[(second ? P.rows_per_rank : 0) + lrow] = pval[q];
                 }
               }
             }
@@ -702,8 +779,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         }
       } else {
         // ---- Solver.update / NuSolver.update: the analytic step (solver.py:82-145, 342-373) ----
-        if (!have_k)
-          pair_kernels<T, CH>(kp, locate<T, CH>(P, si), locate<T, CH>(P, sj), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
+        if (!have_k) pair_kernels<T, CH>(kp, ref_of(si, ti), ref_of(sj, tj), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
         const double yi = (fi & F_YPOS) ? 1.0 : -1.0;
         const double yj = (fj & F_YPOS) ? 1.0 : -1.0;
         const StepOut so = smo_step(nu, (double)Kii, (double)Kjj, (double)Kij, yi, yj, gi, gj, ai, aj, Cbox);
@@ -887,8 +963,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           int f = cur.f0;
           if (v == wi) { f = nfi; flags[row] = (uint8_t)nfi; }
           else if (v == wj) { f = nfj; flags[row] = (uint8_t)nfj; }
-          if (v == pvi) store_alpha(row, false, row, pai);
-          else if (v == pvj) store_alpha(row, false, row, paj);
+          if (v == pvi) store_alpha(row, pai);
+          else if (v == pvj) store_alpha(row, paj);
           consider(nu, f, g, v, best);
         }
         if (mirror) {
@@ -898,8 +974,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           int f = cur.f1;
           if (v == wi) { f = nfi; flags[row + l] = (uint8_t)nfi; }
           else if (v == wj) { f = nfj; flags[row + l] = (uint8_t)nfj; }
-          if (v == pvi) store_alpha(row + l, true, row, pai);
-          else if (v == pvj) store_alpha(row + l, true, row, paj);
+          if (v == pvi) store_alpha(row + l, pai);
+          else if (v == pvj) store_alpha(row + l, paj);
           consider(nu, f, g, v, best);
         }
       }
