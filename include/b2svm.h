@@ -67,7 +67,7 @@ typedef struct b2svm_problem_desc {
   int64_t n_rows;          /* l: rows of X                                                  */
   int32_t n_features;      /* d                                                             */
   int32_t x_dtype;         /* B2SVM_F32 / B2SVM_F64: kernel values are evaluated in this type */
-  const void* X;           /* dev, row-major [n_rows][ldx]                                  */
+  const void* X;           /* dev, row-major [n_rows][ldx]; with world > 1: ALL n_rows_global rows  */
   int64_t ldx;             /* leading dimension of X in elements                            */
   int64_t n_vars;          /* n_rows, or 2*n_rows (mirror: vars t and t+l share row t)      */
   int32_t variant;         /* B2SVM_SOLVER_C / B2SVM_SOLVER_NU                              */
@@ -170,11 +170,13 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
  * its peers' mailboxes before the first solve. */
 int b2svm_mailbox_export(b2svm_handle* h, void* ipc_handle_out /* 64 bytes */);
 int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles /* world * 64 bytes */);
-/* Multi-GPU only, before EVERY b2svm_solve: clears this rank's mailbox and publishes its alpha slice.
- * The host then runs a barrier over all ranks (torch.distributed) and calls b2svm_solve on each.
- * Shards are equal slices of whole 32-row tiles: rank r owns global rows
- * [r*rpr, min(n, (r+1)*rpr)), rpr = roundup32(ceil(n_rows_global / world)); y, alpha, neg_y_grad of a
- * mirror problem are laid out [first half | second half] of the LOCAL rows. */
+/* Multi-GPU only, before EVERY b2svm_solve: clears this rank's mailbox.  The host then runs a barrier
+ * over all ranks (torch.distributed) and calls b2svm_solve on each.
+ * Shards are equal slices of whole 32-row tiles: rank r sweeps global rows
+ * [r*rpr, min(n, (r+1)*rpr)), rpr = roundup32(ceil(n_rows_global / world)), and owns the matching slices of
+ * y, alpha, neg_y_grad (a mirror problem keeps [first half | second half] of its LOCAL rows) and of every
+ * cached column.  X itself (read-only) is given in full to every rank: the two winning rows of an iteration
+ * are then local reads and only 16-byte candidate records cross NVLink. */
 int b2svm_prepare(b2svm_handle* h);
 
 #ifdef __cplusplus

@@ -196,8 +196,6 @@ struct b2svm_handle {
   const void* Xuse = nullptr;
   void* norms = nullptr;
   uint8_t* flags = nullptr;
-  uint4* cand = nullptr;        // tagged candidate records [2][num_sms][NCAND][2]
-  size_t cand_bytes = 0;
   int* abort_flag = nullptr;
   SolveResult* result = nullptr;
   SolveResult* result_host = nullptr;
@@ -211,12 +209,12 @@ struct b2svm_handle {
   long long ntiles = 0;
   size_t smem_bytes = 0;
   int launches = 0;
-  // ---- row-sharded multi-GPU: one IPC-shareable block [record mailbox | payload mailbox]
+  // ---- candidate mailbox [2][world * num_sms][NCAND][2] x 16 B; with several GPUs it is shared over CUDA IPC
   unsigned char* block = nullptr;
-  size_t block_bytes = 0, off_pay = 0;
+  size_t block_bytes = 0;
   long long rows_per_rank = 0;
   std::vector<void*> peer_blocks;          // opened IPC mappings (nullptr for this rank)
-  void** peer_tables = nullptr;            // device: [2][world] = record / payload mailbox pointers of every rank
+  void** peer_tables = nullptr;            // device: [world] mailbox pointer of every rank (own entry = block)
   bool attached = false, prepared = false;
   void* cache = nullptr;          // Q-column cache [cache_slots][n_rows] in the input dtype
   int* slot_of = nullptr;
@@ -238,7 +236,8 @@ template <typename T, int CH>
 struct Geometry {
   using C = Cfg<T, CH>;
   static size_t smem_for(int stages, bool multi) {
-    return (multi ? (size_t)NCAND * C::PAY_STRIDE : 0) + (size_t)stages * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + MAX_STAGES * sizeof(unsigned) +
+    (void)multi;
+    return (size_t)stages * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + MAX_STAGES * sizeof(unsigned) +
            2 * (size_t)C::ROWB +
            sizeof(Shared<T>) + 128;
   }
@@ -257,20 +256,23 @@ int plan_T(b2svm_handle* h) {
   h->stages = stages;
   h->smem_bytes = Geometry<T, CH>::smem_for(stages, multi);
   h->ntiles = (h->d.n_rows + C::BR - 1) / C::BR;
+  // every rank of a sharded solve must launch the same number of CTAs (the mailbox is indexed rank * ncta + cta):
+  // plan with the common slice size, not with this rank's (possibly shorter) last slice
+  const long long plan_tiles = h->d.world > 1 ? (h->rows_per_rank + C::BR - 1) / C::BR : h->ntiles;
   int min_tiles = NW;
   if (const char* e = getenv("B2SVM_MIN_TILES_PER_CTA")) min_tiles = std::max(1, atoi(e));
   int max_ctas = h->d.max_ctas > 0 ? h->d.max_ctas : h->num_sms;
   if (const char* e = getenv("B2SVM_MAX_CTAS")) max_ctas = std::max(1, atoi(e));
   max_ctas = std::min(max_ctas, h->num_sms);
-  long long ncta = std::max<long long>(1, std::min<long long>(max_ctas, h->ntiles / min_tiles));
+  long long ncta = std::max<long long>(1, std::min<long long>(max_ctas, plan_tiles / min_tiles));
   // prefer a split whose slices fit the ring, so X stays resident in shared memory for the whole solve
-  const long long fit = (h->ntiles + stages - 1) / stages;
+  const long long fit = (plan_tiles + stages - 1) / stages;
   if (fit <= max_ctas) ncta = std::max(ncta, fit);
   // ... and, when the GPU has room, one tile per consumer warp (no intra-CTA imbalance)
-  const long long one_each = (h->ntiles + NW - 1) / NW;
+  const long long one_each = (plan_tiles + NW - 1) / NW;
   if (one_each <= max_ctas) ncta = std::max(ncta, one_each);
   h->ncta = (int)ncta;
-  h->tiles_per_cta = (int)((h->ntiles + ncta - 1) / ncta);   // informational: the kernel deals tiles out evenly
+  h->tiles_per_cta = (int)((plan_tiles + ncta - 1) / ncta);   // informational: the kernel deals tiles out evenly
   return B2SVM_OK;
 }
 
@@ -318,7 +320,6 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.ncta = h->ncta;
   P.tiles_per_cta = h->tiles_per_cta;
   P.ntiles = h->ntiles;
-  P.cand = h->cand;
   P.abort_flag = h->abort_flag;
   P.result = h->result;
   P.max_iter = max_iter;
@@ -333,12 +334,8 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.row_offset = h->d.world > 1 ? h->d.row_offset : 0;
   P.l_global = h->d.world > 1 ? h->d.n_rows_global : h->d.n_rows;
   P.rows_per_rank = h->d.world > 1 ? h->rows_per_rank : h->d.n_rows;
-  if (h->d.world > 1) {
-    P.mbox = reinterpret_cast<uint4*>(h->block);
-    P.mbox_pay = reinterpret_cast<uint4*>(h->block + h->off_pay);
-    P.peer_mbox = reinterpret_cast<uint4* const*>(h->peer_tables);
-    P.peer_pay = reinterpret_cast<uint4* const*>(h->peer_tables + h->d.world);
-  }
+  P.mbox = reinterpret_cast<uint4*>(h->block);
+  P.peer_mbox = reinterpret_cast<uint4* const*>(h->peer_tables);
   P.timeline = h->timeline;
   P.dbg_steps = h->dbg_steps;
   P.debug_flags = getenv("B2SVM_DEBUG_FLAGS") ? atoi(getenv("B2SVM_DEBUG_FLAGS")) : 0;
@@ -353,12 +350,9 @@ int prepare_launch(b2svm_handle* h) {
   const int64_t nv = h->d.n_vars;
   refresh_flags_kernel<<<grid_for(nv), 256, 0, h->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, nv);
   B2_CUDA(cudaGetLastError());
-  B2_CUDA(cudaMemsetAsync(h->cand, 0, h->cand_bytes, h->stream));
+  B2_CUDA(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
   B2_CUDA(cudaMemsetAsync(h->abort_flag, 0, sizeof(int), h->stream));
-  if (h->d.world > 1) {
-    B2_CUDA(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
-    B2_CUDA(cudaStreamSynchronize(h->stream));
-  }
+  if (h->d.world > 1) B2_CUDA(cudaStreamSynchronize(h->stream));
   h->prepared = true;
   return B2SVM_OK;
 }
@@ -451,32 +445,32 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     const long long want = std::min<long long>(rpr, desc->n_rows_global - (long long)desc->rank * rpr);
     if (desc->row_offset != (long long)desc->rank * rpr || desc->n_rows != want)
       return cleanup_fail(B2SVM_E_INVALID, "shard must be rows [rank*rpr, min(n,(rank+1)*rpr)), rpr = roundup32(ceil(n/world))");
-    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    h->off_pay = up(sizeof(uint4) * 2 * desc->world * NCAND);
-    h->block_bytes = h->off_pay + sizeof(uint4) * 2 * (size_t)desc->world * NCAND * PAY_UNITS_MAX;
-    B2_TRY(cudaMalloc(&h->block, h->block_bytes));
-    B2_TRY(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
   }
+  h->block_bytes = sizeof(uint4) * 2 * (size_t)std::max(1, desc->world) * h->num_sms * NCAND * 2;
+  B2_TRY(cudaMalloc(&h->block, h->block_bytes));
+  B2_TRY(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
+  // rows of X held by this GPU: its own slice on one GPU, ALL rows (replicated, read-only) in a sharded solve
+  const int64_t lx = desc->world > 1 ? desc->n_rows_global : l;
   const bool in_place = desc->ldx == h->dp && desc->n_features == h->dp && ((uintptr_t)desc->X % 16 == 0);
   if (in_place) {
     h->Xuse = desc->X;
   } else {
-    B2_TRY(cudaMalloc(&h->Xown, (size_t)l * h->dp * esz));
+    B2_TRY(cudaMalloc(&h->Xown, (size_t)lx * h->dp * esz));
     void* xdst = h->Xown;
     if (h->f64)
-      pad_rows_kernel<double><<<grid_for(l * h->dp), 256, 0, h->stream>>>((const double*)desc->X, desc->ldx,
-                                                                          (double*)xdst, l, desc->n_features, h->dp);
+      pad_rows_kernel<double><<<grid_for(lx * h->dp), 256, 0, h->stream>>>((const double*)desc->X, desc->ldx,
+                                                                           (double*)xdst, lx, desc->n_features, h->dp);
     else
-      pad_rows_kernel<float><<<grid_for(l * h->dp), 256, 0, h->stream>>>((const float*)desc->X, desc->ldx,
-                                                                         (float*)xdst, l, desc->n_features, h->dp);
+      pad_rows_kernel<float><<<grid_for(lx * h->dp), 256, 0, h->stream>>>((const float*)desc->X, desc->ldx,
+                                                                          (float*)xdst, lx, desc->n_features, h->dp);
     B2_TRY(cudaGetLastError());
     h->Xuse = xdst;
   }
-  B2_TRY(cudaMalloc(&h->norms, (size_t)l * esz));
+  B2_TRY(cudaMalloc(&h->norms, (size_t)lx * esz));
   if (h->f64)
-    row_norms_kernel<double><<<grid_for(l * 32), 256, 0, h->stream>>>((const double*)h->Xuse, l, h->dp, (double*)h->norms);
+    row_norms_kernel<double><<<grid_for(lx * 32), 256, 0, h->stream>>>((const double*)h->Xuse, lx, h->dp, (double*)h->norms);
   else
-    row_norms_kernel<float><<<grid_for(l * 32), 256, 0, h->stream>>>((const float*)h->Xuse, l, h->dp, (float*)h->norms);
+    row_norms_kernel<float><<<grid_for(lx * 32), 256, 0, h->stream>>>((const float*)h->Xuse, lx, h->dp, (float*)h->norms);
   B2_TRY(cudaGetLastError());
   B2_TRY(cudaMalloc(&h->flags, (size_t)nv));
   if (desc->cache_bytes > 0) {
@@ -492,8 +486,11 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
       h->cache_slots = slots;
     }
   }
-  h->cand_bytes = sizeof(uint4) * 2 * h->num_sms * NCAND * REC_STRIDE;
-  B2_TRY(cudaMalloc(&h->cand, h->cand_bytes));
+  if (desc->world <= 1) {   // the peer table of a single GPU is just its own mailbox
+    void* self = h->block;
+    B2_TRY(cudaMalloc(&h->peer_tables, sizeof(void*)));
+    B2_TRY(cudaMemcpy(h->peer_tables, &self, sizeof(void*), cudaMemcpyHostToDevice));
+  }
   B2_TRY(cudaMalloc(&h->abort_flag, sizeof(int)));
   B2_TRY(cudaMalloc(&h->result, sizeof(SolveResult)));
   B2_TRY(cudaMallocHost(&h->result_host, sizeof(SolveResult)));
@@ -532,7 +529,6 @@ int b2svm_destroy(b2svm_handle* h) {
   cudaFree(h->flags);
   cudaFree(h->cache);
   cudaFree(h->slot_of);
-  cudaFree(h->cand);
   cudaFree(h->abort_flag);
   cudaFree(h->result);
   if (h->result_host) cudaFreeHost(h->result_host);
@@ -741,7 +737,7 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
   for (int k = 0; k < count; ++k) {
     b2svm_handle* h = handles[k];
     refresh_flags_kernel<<<grid_for(h->d.n_vars), 256, 0, h0->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, h->d.n_vars);
-    cudaMemsetAsync(h->cand, 0, h->cand_bytes, h0->stream);
+    cudaMemsetAsync(h->block, 0, h->block_bytes, h0->stream);
     cudaMemsetAsync(h->abort_flag, 0, sizeof(int), h0->stream);
     memset(&P[k], 0, sizeof(ProblemDev));
     fill_problem(h, P[k], max_iter, -1, -1);
@@ -824,7 +820,7 @@ int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles) {
   B2_CUDA(cudaSetDevice(h->d.device));
   const int world = h->d.world;
   h->peer_blocks.assign(world, nullptr);
-  std::vector<void*> tab(2 * (size_t)world);
+  std::vector<void*> tab((size_t)world);
   for (int r = 0; r < world; ++r) {
     unsigned char* base = h->block;
     if (r != h->d.rank) {
@@ -835,8 +831,7 @@ int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles) {
       h->peer_blocks[r] = p;
       base = reinterpret_cast<unsigned char*>(p);
     }
-    tab[r] = base;                       // record mailbox
-    tab[world + r] = base + h->off_pay;  // payload mailbox
+    tab[r] = base;
   }
   B2_CUDA(cudaMalloc(&h->peer_tables, sizeof(void*) * tab.size()));
   B2_CUDA(cudaMemcpy(h->peer_tables, tab.data(), sizeof(void*) * tab.size(), cudaMemcpyHostToDevice));

@@ -18,15 +18,16 @@
 // select -> step chain are in flight.  When a CTA's slice fits in the ring it is loaded once and
 // stays resident in shared memory for the whole solve (small problems, multi-GPU shards).
 //
-// Candidate exchange.  A record is one 16-byte word {g, idx, epoch<<3 | flags}, written and read with
-// one 16-byte relaxed access and double-buffered by epoch parity.  A reader accepts a record only
-// when it carries the epoch it waits for, so data and "flag" travel together and no release/acquire
-// fence (MEMBAR.SC + CCTL.IVALL, ~2-4k cycles each on B200) sits on the per-iteration critical
-// path.  G / flags of a row are only ever read by the CTA (= SM) that writes them.  alpha_i / alpha_j
-// are fetched by every leader straight from L2 together with rows x_i / x_j.  To keep a fast CTA from
-// overwriting alpha_j while a slow leader still reads it, the store of a step's new alphas is
-// deferred to the NEXT sweep (every leader forwards the previous pair's values from registers), and
-// the lane that stores fences it (off the critical path) before its CTA's next record.
+// Candidate exchange (one level, same code on one GPU and on a row-sharded box).  Every CTA writes, per
+// candidate type, one 16-byte record {g, idx, epoch<<3 | flags} and one 16-byte unit {alpha, epoch} into the
+// mailbox of EVERY GPU (its own included; peers over NVLink through CUDA-IPC mappings), each with a single
+// relaxed 16-byte store, double-buffered by epoch parity.  A reader accepts a word only when it carries
+// the epoch it waits for, so data and "flag" travel together: no atomics and no release/acquire fences
+// (MEMBAR.SC + CCTL.IVALL cost 2-4 k cycles each on B200) on the per-iteration critical path.  All consumer
+// warps of a CTA share the polling of the world * nCTA records (one L2 round trip), reduce through shared
+// memory, and the leader warp finishes.  X (read-only) is replicated on every GPU of a sharded solve, so
+// the winning rows are local reads; only the sweep, the gradient, alpha and the column cache are sharded.
+// G / flags / alpha of a row are only ever touched by the CTA (= SM) that owns the row.
 #pragma once
 #include "b2svm_device.cuh"
 
@@ -37,10 +38,6 @@ constexpr int NTHREADS = (NW + 1) * 32;    // + one producer warp
 constexpr int MAX_STAGES = 64;
 constexpr int NCAND = 4;                   // up/low (C variant) or up+/low+/up-/low- (nu variant)
 constexpr int REC_STRIDE = 1;              // one 128-byte line per record (uint4 units): spreads the polling over L2 slices
-// Cross-GPU payload: {alpha 8 B, norm 8 B, row} of a winning variable, shipped as 16-byte units of 12 data
-// bytes + a 4-byte epoch tag so that every unit validates itself (no fence between data and flag).
-constexpr int PAY_HDR = 16;
-constexpr int PAY_UNITS_MAX = (PAY_HDR + 128 * 16 + 11) / 12;
 constexpr int TL_ITERS = 64, TL_SLOTS = 8; // debug timeline
 constexpr int DBG_EPOCHS = 2048;
 constexpr int TL_WARP_SLOTS = 4;           // + per-warp {start, end, tiles, wait} of one sweep
@@ -72,7 +69,8 @@ struct ProblemDev {
   int ncta;             // CTAs cooperating on this problem
   int tiles_per_cta;
   long long ntiles;
-  uint4* cand;          // [2][ncta][NCAND] tagged records (zeroed before every launch)
+  uint4* mbox;          // local mailbox [2][world * ncta][NCAND][2] {record, alpha unit} (zeroed before every launch)
+  uint4* const* peer_mbox;   // [world] every rank's mailbox (peer mapping; own entry = mbox)
   int* abort_flag;
   SolveResult* result;
   long long max_iter;
@@ -83,13 +81,10 @@ struct ProblemDev {
   int* slot_of;                   // [l_global] slot of global row r, -1 = not cached (replicated per GPU)
   long long cache_slots;          // 0 = cache off
   long long cache_used;           // slots already filled by earlier solves on this handle
-  // ---- row-sharded multi-GPU (world > 1): this GPU owns global rows [row_offset, row_offset + l) --------
+  // ---- row-sharded multi-GPU (world > 1): this GPU sweeps global rows [row_offset, row_offset + l); X and
+  // norms hold ALL l_global rows on every GPU
   int world, rank;
   long long row_offset, l_global, rows_per_rank;   // every rank's slice starts at rank * rows_per_rank
-  uint4* mbox;                    // local record mailbox [2][world][NCAND], written by the peers over NVLink
-  uint4* mbox_pay;                // local payload mailbox [2][world][NCAND][PAY_UNITS_MAX]: winner alpha, norm, row
-  uint4* const* peer_mbox;        // [world] every rank's record mailbox (peer mapping; own entry = local)
-  uint4* const* peer_pay;         // [world] every rank's payload mailbox
   double* dbg_steps;              // optional [DBG_EPOCHS][ncta][6] = si, sj, gi, gj, ai, aj seen by each leader
   int debug_flags;                // B2SVM_DEBUG_FLAGS: 1 = static tile assignment, 2 = L2 loads for G/flags
 };
@@ -115,16 +110,17 @@ struct Cfg {
   static constexpr int NV = 2 * RPL;                               // partial sums per lane
   static constexpr int ROWB = CH * 16;
   static constexpr int TILE_BYTES = BR * ROWB;
-  static constexpr int PAY_UNITS = (PAY_HDR + ROWB + 11) / 12;          // cross-GPU payload units per winner
-  static constexpr int PAY_STRIDE = (PAY_UNITS * 12 + 15) / 16 * 16;    // staging bytes per candidate type
+};
+
+struct WCand {
+  double g, alpha;
+  int idx, flags;
 };
 
 // State only the leader warp needs between iterations.  It lives in shared memory and is loaded into
 // registers for the duration of the leader block only, so it costs the sweep loop no registers.
 struct LeaderState {
   double di, dj;          // last step
-  double ai, aj;          // ... its new alphas (stored one sweep later, forwarded meanwhile)
-  int i, j;               // ... its pair
   int ri, rj, si, sj;     // ... its rows / cache slots (same deferral)
   int n_cached;           // cache slots handed out so far (identical in every leader)
   int converged;
@@ -140,14 +136,16 @@ struct Shared {
   int slot_i, slot_j;   // cache slots of rows i, j (-1 = none); store_* = fill the slot during this sweep
   int store_i, store_j, warm;
   int p_ri, p_rj, p_si, p_sj;   // previous pair's rows / slots: slot_of[] is updated one sweep late, like alpha
-  int pi, pj;           // previous pair, whose alphas (pai, paj) are stored during this sweep
-  double pai, paj;
   int stop;
   volatile int producer_stop;
   volatile long long consumed;
   LeaderState leader;
   int ticket;           // next dynamically assigned tile of the current sweep
-  Cand wc[NW][NCAND];
+  volatile int status;  // a warp's watchdog tripped
+  WCand wc[NW][NCAND];  // per-warp candidates of the sweep (with their alpha)
+  WCand cw[NCAND];      // this CTA's winners
+  WCand ws[NW][NCAND];  // per-warp winners of the polled records (alpha field unused, flags = source slot)
+  int wsrc[NW][NCAND];  // ... and the mailbox source (rank * ncta + cta) they came from
 };
 
 __device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (&b)[NCAND]) {
@@ -168,9 +166,7 @@ __device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (
   }
 }
 
-// Where the leader finds variable `idx`: its row, its norm and its alpha.  On one GPU these are the
-// problem's own arrays; in a row-sharded solve they are the payload the owner GPU pushed with its record,
-// staged in shared memory (alpha as double at +0, norm as T at +8, the row at +16).
+// Where the leader finds variable `idx`: row and norm in the (replicated) X / norms arrays.
 template <typename T>
 struct VarRef {
   const typename Chunk<T>::V* row;
@@ -181,16 +177,8 @@ __device__ __forceinline__ VarRef<T> locate(const ProblemDev& P, int idx) {
   using V = typename Chunk<T>::V;
   VarRef<T> r;
   const long long grow = (P.mirror && idx >= P.l_global) ? idx - P.l_global : idx;
-  const long long lrow = grow - P.row_offset;          // single GPU: row_offset == 0
-  r.row = reinterpret_cast<const V*>(P.X) + lrow * CH;
-  r.norm = reinterpret_cast<const T*>(P.norms) + lrow;
-  return r;
-}
-template <typename T>
-__device__ __forceinline__ VarRef<T> staged(const unsigned char* sb) {
-  VarRef<T> r;
-  r.row = reinterpret_cast<const typename Chunk<T>::V*>(sb + PAY_HDR);
-  r.norm = reinterpret_cast<const T*>(sb + 8);
+  r.row = reinterpret_cast<const V*>(P.X) + grow * CH;
+  r.norm = reinterpret_cast<const T*>(P.norms) + grow;
   return r;
 }
 
@@ -255,8 +243,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   volatile unsigned* gen = reinterpret_cast<volatile unsigned*>(empty + MAX_STAGES);
   V* xs = reinterpret_cast<V*>(const_cast<unsigned*>(gen) + MAX_STAGES);      // [2][CH]
   Shared<T>* sh = reinterpret_cast<Shared<T>*>(xs + 2 * CH);
-  // winner payloads of a row-sharded solve (only allocated when world > 1)
-  unsigned char* stagebuf = reinterpret_cast<unsigned char*>(sh) + (sizeof(Shared<T>) + 15) / 16 * 16;
 
   const ProblemDev& P = probs[blockIdx.x / ncta_pp];
   const int cta = blockIdx.x % ncta_pp;
@@ -290,9 +276,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     sh->producer_stop = 0;
     sh->consumed = 0;
     sh->ticket = NW;
+    sh->status = 0;
     LeaderState L0;
-    L0.di = L0.dj = L0.ai = L0.aj = 0.0;
-    L0.i = L0.j = L0.ri = L0.rj = L0.si = L0.sj = -1;
+    L0.di = L0.dj = 0.0;
+    L0.ri = L0.rj = L0.si = L0.sj = -1;
     L0.n_cached = (int)P.cache_used;
     L0.converged = 0;
     L0.warm_cnt = L0.stored_cnt = 0;
@@ -303,7 +290,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   // ============================== producer warp ==============================================
   if (warp == NW) {
     if (NT > 0) {
-      const unsigned char* Xb = reinterpret_cast<const unsigned char*>(P.X);
+      const unsigned char* Xb = reinterpret_cast<const unsigned char*>(P.X) + (size_t)P.row_offset * C::ROWB;
       unsigned long long Tp = 0;
       unsigned stage = 0, par = 0;   // stage = Tp % S, par = (Tp / S) & 1
       int t = 0;                     // Tp % NT
@@ -359,7 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   kp.gamma = (T)P.gamma;
   kp.coef0 = (T)P.coef0;
   kp.degree = (T)P.degree;
-  const T* __restrict__ norms = reinterpret_cast<const T*>(P.norms);
+  const T* __restrict__ norms = reinterpret_cast<const T*>(P.norms) + P.row_offset;   // this GPU's rows
   double* __restrict__ G = P.G;
   double* __restrict__ alpha = P.alpha;
   uint8_t* __restrict__ flags = P.flags;
@@ -395,20 +382,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   auto local_var = [&](int idx) -> long long {
     const bool second = mirror && idx >= lg;
     return (second ? l : 0) + ((second ? idx - lg : idx) - goff);
-  };
-  // alpha / row / norm of a winner of candidate type `type`
-  auto read_alpha = [&](int idx, int type) -> double {
-    if (world == 1) return __ldcg(alpha + idx);
-    return *reinterpret_cast<const double*>(stagebuf + type * C::PAY_STRIDE);
-  };
-  auto ref_of = [&](int idx, int type) -> VarRef<T> {
-    if (world == 1) return locate<T, CH>(P, idx);
-    return staged<T>(stagebuf + type * C::PAY_STRIDE);
-  };
-  // deferred store of a step's new alpha by the lane that owns the variable (local index lv)
-  auto store_alpha = [&](long long lv, double a) {
-    alpha[lv] = a;
-    __threadfence();
   };
   // cache columns in use by the current / next sweep (set after bar (A))
   bool sweep_warm = false;
@@ -452,35 +425,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   RowState<T> pf = load_row_state(warp);   // first tile of the first sweep (tiles 0..NW-1 are static)
 
   for (;;) {
-    // ---- (B) warp -> CTA candidate reduce, publish, exchange, global reduce (leader) ------------
+    // ---- (B) warp -> CTA candidate reduce, publish to every GPU, shared polling, global reduce ----------
     ++epoch;
     stamp(0);   // this warp's sweep done
+    const uint32_t par = epoch & 1u;
 #pragma unroll
     for (int k = 0; k < NCAND; ++k)
       if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, best[k]);
-    if (lane == 0) {
+    __syncwarp();
+    if (lane < ntypes) {
+      // one lane per type attaches the candidate's alpha (a row of this warp: same-SM coherent); the load's
+      // latency hides behind the CTA join
+      Cand m = best[0];
 #pragma unroll
-      for (int k = 0; k < NCAND; ++k) sh->wc[warp][k] = best[k];
+      for (int k = 1; k < NCAND; ++k)
+        if (lane == k) m = best[k];
+      WCand wv;
+      wv.g = m.g;
+      wv.idx = m.idx;
+      wv.flags = m.flags;
+      wv.alpha = m.idx >= 0 ? alpha[local_var(m.idx)] : 0.0;
+      sh->wc[warp][lane] = wv;
     }
     named_bar_sync(1, NW * 32);
     stamp(1);   // all warps of this CTA done
 
     if (warp == 0) {
-      LeaderState L = sh->leader;
-      int status = 0;
-      const long long n_iter = (long long)epoch - 1;
-      // CTA-level winner per type -> tagged record in global memory (two types per pass, 16 lanes each)
+      // CTA-level winner per type (two types per pass, 16 lanes each) ...
       for (int k0 = 0; k0 < ntypes; k0 += 2) {
         const int k = k0 + (lane >> 4), src = lane & 15;
+        const unsigned half = lane < 16 ? 0x0000ffffu : 0xffff0000u;
+        WCand mw;
+        mw.g = 0.0; mw.alpha = 0.0; mw.idx = -1; mw.flags = 0;
+        if (src < NW) mw = sh->wc[src][k];
         Cand m;
-        m.g = 0.0; m.idx = -1; m.flags = 0;
-        if (src < NW) m = sh->wc[src][k];
-        redux_select(lane < 16 ? 0x0000ffffu : 0xffff0000u, (k & 1) == 0, m);
+        m.g = mw.g; m.idx = mw.idx; m.flags = mw.flags;
+        redux_select(half, (k & 1) == 0, m);
+        const unsigned holders = __ballot_sync(half, m.idx >= 0 && mw.idx == m.idx) & half;
+        const int from = holders ? __ffs(holders) - 1 : (lane & 16);
+        const double wa = __shfl_sync(half, mw.alpha, from);
         if (src == 0) {
-          uint4* rp = P.cand + (((size_t)(epoch & 1) * ncta + cta) * NCAND + k) * REC_STRIDE;
-          st_relaxed_v4(rp, make_uint4((uint32_t)__double2loint(m.g), (uint32_t)__double2hiint(m.g), (uint32_t)m.idx,
-                                       (epoch << 3) | (uint32_t)m.flags));
+          WCand c;
+          c.g = m.g; c.alpha = wa; c.idx = m.idx; c.flags = m.flags;
+          sh->cw[k] = c;
         }
+      }
+      __syncwarp();
+      // ... pushed into the mailbox of every GPU: one lane per (rank, type), two 16-byte stores each
+      if (lane < world * ntypes) {
+        const int r = lane / ntypes, k = lane - r * ntypes;
+        const WCand c = sh->cw[k];
+        uint4* rp = const_cast<uint4*>(P.peer_mbox[r]) +
+                    ((((size_t)par * world + P.rank) * ncta + cta) * NCAND + k) * 2;
+        const uint4 rec = make_uint4((uint32_t)__double2loint(c.g), (uint32_t)__double2hiint(c.g), (uint32_t)c.idx,
+                                     (epoch << 3) | (uint32_t)c.flags);
+        const uint4 au = make_uint4((uint32_t)__double2loint(c.alpha), (uint32_t)__double2hiint(c.alpha), 0u, epoch);
+        if (world == 1) { st_relaxed_v4(rp, rec); st_relaxed_v4(rp + 1, au); }
+        else { st_relaxed_sys_v4(rp, rec); st_relaxed_sys_v4(rp + 1, au); }
       }
       if (lane == 0) sh->ticket = NW;   // next sweep: tiles 0..NW-1 are static, the rest are drawn here
       stamp(2);   // published
@@ -490,32 +491,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         P.timeline[TL_CTA_BASE + 2 * cta + 1] = NT;
       }
 #endif
+    }
 
-      // read every CTA's record of this epoch (this is the grid barrier)
+    // ---- every consumer warp polls its share of the world * ncta records (this is the grid / box barrier)
+    {
+      const int NS = world * ncta;
+      const int per = (NS + NW - 1) / NW;
+      const int s_begin = warp * per;
+      const int s_end = min(NS, s_begin + per);
+      constexpr int MAXM = 4;   // per <= ceil(8 * 148 / 11) = 108 <= 4 * 32
+      const uint4* rbase = P.mbox + (size_t)par * NS * NCAND * 2;
       Cand w[NCAND];
+      int wsrc[NCAND];
       const uint64_t t_start = globaltimer_ns();
       uint32_t rounds = 0;
       for (;;) {
         bool all = true;
 #pragma unroll
-        for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; }
-        // all loads of a pass are issued before any is looked at: one L2 round trip per pass, not one per record
-        constexpr int MAXC = 5;   // ceil(160 CTAs / 32 lanes)
-        const uint4* rbase = P.cand + (size_t)(epoch & 1) * ncta * NCAND * REC_STRIDE;
+        for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; wsrc[k] = 0; }
+        // all loads of a pass are issued before any is looked at: one round trip per pass, not one per record
         for (int k0 = 0; k0 < ntypes; k0 += 2) {
-          uint4 h[MAXC][2];
+          uint4 h[MAXM][2];
 #pragma unroll
-          for (int m = 0; m < MAXC; ++m) {
-            const int c = lane + 32 * m;
-            if (c < ncta) {
-              h[m][0] = ld_relaxed_v4(rbase + ((size_t)c * NCAND + k0) * REC_STRIDE);
-              h[m][1] = ld_relaxed_v4(rbase + ((size_t)c * NCAND + k0 + 1) * REC_STRIDE);
+          for (int m = 0; m < MAXM; ++m) {
+            const int sidx = s_begin + lane + 32 * m;
+            if (sidx < s_end) {
+              if (world == 1) {   // gpu scope is enough (and cheaper) when no peer writes into this mailbox
+                h[m][0] = ld_relaxed_v4(rbase + ((size_t)sidx * NCAND + k0) * 2);
+                h[m][1] = ld_relaxed_v4(rbase + ((size_t)sidx * NCAND + k0 + 1) * 2);
+              } else {
+                h[m][0] = ld_relaxed_sys_v4(rbase + ((size_t)sidx * NCAND + k0) * 2);
+                h[m][1] = ld_relaxed_sys_v4(rbase + ((size_t)sidx * NCAND + k0 + 1) * 2);
+              }
             }
           }
 #pragma unroll
-          for (int m = 0; m < MAXC; ++m) {
-            const int c = lane + 32 * m;
-            if (c < ncta) {
+          for (int m = 0; m < MAXM; ++m) {
+            const int sidx = s_begin + lane + 32 * m;
+            if (sidx < s_end) {
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
                 const uint4 hh = h[m][kk];
@@ -525,8 +538,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
                   const double g = __hiloint2double((int)hh.y, (int)hh.x);
                   const int idx = (int)hh.z;
                   Cand& wk = (k0 == 0) ? w[kk] : w[2 + kk];
+                  int& ws = (k0 == 0) ? wsrc[kk] : wsrc[2 + kk];
                   const bool take = kk == 0 ? better_max(g, idx, wk.g, wk.idx) : better_min(g, idx, wk.g, wk.idx);
-                  if (take) { wk.g = g; wk.idx = idx; wk.flags = (int)(hh.w & 7u); }
+                  if (take) { wk.g = g; wk.idx = idx; wk.flags = (int)(hh.w & 7u); ws = sidx; }
                 }
               }
             }
@@ -534,138 +548,84 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         }
         if (__all_sync(0xffffffffu, all)) break;
         if ((++rounds & 63u) == 0) {
-          int bad = *(volatile int*)P.abort_flag;
-          if (!bad && globaltimer_ns() - t_start > 4000000000ull) {
+          int bad = *(volatile int*)P.abort_flag | sh->status;
+          if (!bad && globaltimer_ns() - t_start > 6000000000ull) {
             *(volatile int*)P.abort_flag = 1;
             bad = 1;
           }
-          if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
+          if (__any_sync(0xffffffffu, bad)) { sh->status = 1; break; }
         }
       }
-      stamp(3);   // every CTA's record read
+      // warp winner per type, with the mailbox source it came from
 #pragma unroll
-      for (int k = 0; k < NCAND; ++k)
-        if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, w[k]);
-      if (world > 1) {
-        // ---- cross-GPU exchange over NVLink.  CTA 0 pushes, for every candidate type, this GPU's winner
-        // record AND its payload (alpha, norm, row) into every rank's mailboxes; every leader then polls
-        // its LOCAL mailboxes only.  Nothing is ever loaded across the link.
-        const uint32_t par = epoch & 1u;
-        if (cta == 0) {
-          for (int k = 0; k < ntypes; ++k) {
-            Cand m = w[0];
-#pragma unroll
-            for (int kk = 1; kk < NCAND; ++kk)
-              if (k == kk) m = w[kk];
-            if (m.idx >= 0) {
-              unsigned char* sb = stagebuf + k * C::PAY_STRIDE;
-              const VarRef<T> A = locate<T, CH>(P, m.idx);
-              if (lane == 0) {
-                const double a = m.idx == L.i ? L.ai : (m.idx == L.j ? L.aj : __ldcg(alpha + local_var(m.idx)));
-                *reinterpret_cast<double*>(sb) = a;
-                *reinterpret_cast<T*>(sb + 8) = *A.norm;
-              }
-#pragma unroll
-              for (int q = 0; q < QL; ++q) {
-                const int c = lane + 32 * q;
-                if (c < CH) *reinterpret_cast<V*>(sb + PAY_HDR + 16 * c) = A.row[c];
-              }
-              __syncwarp();
-              for (int u = lane; u < C::PAY_UNITS; u += 32) {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(sb + 12 * u);
-                const uint4 unit = make_uint4(src[0], src[1], src[2], epoch);
-                for (int r = 0; r < world; ++r) {
-                  uint4* pp = const_cast<uint4*>(P.peer_pay[r]) + (((size_t)par * world + P.rank) * NCAND + k) * PAY_UNITS_MAX;
-                  st_relaxed_sys_v4(pp + u, unit);
-                }
-              }
-              __syncwarp();
-            }
-          }
-          if (lane < world * ntypes) {
-            const int r = lane / ntypes, k = lane - r * ntypes;
-            Cand m = w[0];
-#pragma unroll
-            for (int kk = 1; kk < NCAND; ++kk)
-              if (k == kk) m = w[kk];
-            uint4* rp = const_cast<uint4*>(P.peer_mbox[r]) + ((size_t)par * world + P.rank) * NCAND + k;
-            st_relaxed_sys_v4(rp, make_uint4((uint32_t)__double2loint(m.g), (uint32_t)__double2hiint(m.g), (uint32_t)m.idx,
-                                             (epoch << 3) | (uint32_t)m.flags));
-          }
+      for (int k = 0; k < NCAND; ++k) {
+        if (k < ntypes) {
+          const int mine = w[k].idx;
+          redux_select(0xffffffffu, (k & 1) == 0, w[k]);
+          const unsigned holders = __ballot_sync(0xffffffffu, w[k].idx >= 0 && mine == w[k].idx);
+          const int from = holders ? __ffs(holders) - 1 : 0;
+          wsrc[k] = __shfl_sync(0xffffffffu, wsrc[k], from);
         }
-        uint32_t rounds2 = 0;
-        for (;;) {
-          bool all = true;
-#pragma unroll
-          for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; }
-          if (lane < world) {
-            const uint4* rp = P.mbox + ((size_t)par * world + lane) * NCAND;
-            uint4 h[NCAND];
-#pragma unroll
-            for (int k = 0; k < NCAND; ++k)
-              if (k < ntypes) h[k] = ld_relaxed_sys_v4(rp + k);
-#pragma unroll
-            for (int k = 0; k < NCAND; ++k) {
-              if (k < ntypes) {
-                if ((h[k].w >> 3) != epoch) {
-                  all = false;
-                } else {
-                  w[k].g = __hiloint2double((int)h[k].y, (int)h[k].x);
-                  w[k].idx = (int)h[k].z;
-                  w[k].flags = (int)(h[k].w & 7u);
-                }
-              }
-            }
-          }
-          if (__all_sync(0xffffffffu, all)) break;
-          if ((++rounds2 & 63u) == 0) {
-            int bad = *(volatile int*)P.abort_flag;
-            if (!bad && globaltimer_ns() - t_start > 8000000000ull) {
-              *(volatile int*)P.abort_flag = 1;
-              bad = 1;
-            }
-            if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < NCAND; ++k)
-          if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, w[k]);
-        // the global winners' payloads: wait until every 16-byte unit carries this epoch, stage them
-        for (int k = 0; k < ntypes && !status; ++k) {
-          Cand m = w[0];
-#pragma unroll
-          for (int kk = 1; kk < NCAND; ++kk)
-            if (k == kk) m = w[kk];
-          if (m.idx < 0) continue;
-          const long long grow = (mirror && m.idx >= lg) ? m.idx - lg : m.idx;
-          const int owner = (int)(grow / P.rows_per_rank);
-          const uint4* pp = P.mbox_pay + (((size_t)par * world + owner) * NCAND + k) * PAY_UNITS_MAX;
-          unsigned char* sb = stagebuf + k * C::PAY_STRIDE;
-          uint32_t rounds3 = 0;
-          for (;;) {
-            bool ok = true;
-            for (int u = lane; u < C::PAY_UNITS; u += 32) {
-              const uint4 h = ld_relaxed_sys_v4(pp + u);
-              if (h.w != epoch) {
-                ok = false;
-              } else {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(sb + 12 * u);
-                dst[0] = h.x; dst[1] = h.y; dst[2] = h.z;
-              }
-            }
-            if (__all_sync(0xffffffffu, ok)) break;
-            if ((++rounds3 & 63u) == 0) {
-              int bad = *(volatile int*)P.abort_flag;
-              if (!bad && globaltimer_ns() - t_start > 8000000000ull) {
-                *(volatile int*)P.abort_flag = 1;
-                bad = 1;
-              }
-              if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
-            }
-          }
-        }
-        __syncwarp();
       }
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NCAND; ++k) {
+          WCand c;
+          c.g = w[k].g; c.alpha = 0.0; c.idx = w[k].idx; c.flags = w[k].flags;
+          sh->ws[warp][k] = c;
+          sh->wsrc[warp][k] = wsrc[k];
+        }
+      }
+    }
+    named_bar_sync(3, NW * 32);
+    stamp(3);   // every record of the box read
+
+    if (warp == 0) {
+      LeaderState L = sh->leader;
+      int status = sh->status;
+      const long long n_iter = (long long)epoch - 1;
+      // global winners: reduce the NW warp winners (16 lanes per type), keep the source slot of each
+      Cand w[NCAND];
+      int wsrc[NCAND];
+#pragma unroll
+      for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; wsrc[k] = 0; }
+      for (int k0 = 0; k0 < ntypes; k0 += 2) {
+        const int k = k0 + (lane >> 4), src = lane & 15;
+        const unsigned half = lane < 16 ? 0x0000ffffu : 0xffff0000u;
+        Cand m;
+        m.g = 0.0; m.idx = -1; m.flags = 0;
+        int msrc = 0;
+        if (src < NW) {
+          const WCand c = sh->ws[src][k];
+          m.g = c.g; m.idx = c.idx; m.flags = c.flags;
+          msrc = sh->wsrc[src][k];
+        }
+        const int mine = m.idx;
+        redux_select(half, (k & 1) == 0, m);
+        const unsigned holders = __ballot_sync(half, m.idx >= 0 && mine == m.idx) & half;
+        const int from = holders ? __ffs(holders) - 1 : (lane & 16);
+        msrc = __shfl_sync(half, msrc, from);
+        // hand both halves' results to every lane
+        const Cand lo = {__shfl_sync(0xffffffffu, m.g, 0), __shfl_sync(0xffffffffu, m.idx, 0), __shfl_sync(0xffffffffu, m.flags, 0)};
+        const Cand hi = {__shfl_sync(0xffffffffu, m.g, 16), __shfl_sync(0xffffffffu, m.idx, 16), __shfl_sync(0xffffffffu, m.flags, 16)};
+        const int slo = __shfl_sync(0xffffffffu, msrc, 0), shi = __shfl_sync(0xffffffffu, msrc, 16);
+        if (k0 == 0) { w[0] = lo; w[1] = hi; wsrc[0] = slo; wsrc[1] = shi; }
+        else { w[2] = lo; w[3] = hi; wsrc[2] = slo; wsrc[3] = shi; }
+      }
+      // alpha of a winner: the 16-byte unit its CTA pushed next to the record (polled until it carries the epoch)
+      const uint4* abase = P.mbox + (size_t)par * world * ncta * NCAND * 2;
+      auto alpha_unit = [&](int type) -> const uint4* { return abase + ((size_t)wsrc[type] * NCAND + type) * 2 + 1; };
+      auto load_unit = [&](int type) -> uint4 {
+        return world == 1 ? ld_relaxed_v4(alpha_unit(type)) : ld_relaxed_sys_v4(alpha_unit(type));
+      };
+      auto settle_alpha = [&](uint4 u, int type) -> double {   // re-poll until the unit carries this epoch
+        uint32_t spins = 0;
+        while (u.w != epoch) {
+          u = load_unit(type);
+          if ((++spins & 4095u) == 0 && *(volatile int*)P.abort_flag) break;
+        }
+        return __hiloint2double((int)u.y, (int)u.x);
+      };
       stamp(4);   // global winners known
 
       // ---- decide the next pair (working_set_select) ------------------------------------------
@@ -676,7 +636,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       V xi[QL], xj[QL];
       T ni = 0, nj = 0, Kii = 0, Kjj = 0, Kij = 0;
       bool have_k = false;
-      int ti = 0, tj = 1;   // candidate types the pair came from (where a row-sharded solve staged their payload)
+      int ti = 0, tj = 1;   // candidate types the pair came from
       if (forced && epoch == 1) {
         si = (int)P.forced_i;     // single GPU only (checked on the host)
         sj = (int)P.forced_j;
@@ -688,10 +648,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         si = w[0].idx; sj = w[1].idx;
         gi = w[0].g; gj = w[1].g; fi = w[0].flags; fj = w[1].flags;
         stop_sel = si < 0 || sj < 0 || (gi - gj < P.tol);
-        if (!stop_sel) {
-          ai = si == L.i ? L.ai : (si == L.j ? L.aj : read_alpha(si, 0));
-          aj = sj == L.i ? L.ai : (sj == L.j ? L.aj : read_alpha(sj, 1));
-        }
+        // (alpha_i, alpha_j are fetched together with the rows in the step below)
       } else {
         // solver.py:300-339: no tol test, gain comparison between the class-wise pairs
         const bool pos_ok = w[0].idx >= 0 && w[1].idx >= 0;
@@ -703,12 +660,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         else {
           V xa[QL], xb[QL];
           T na, nb, Kaa, Kbb, Kab;
-          pair_kernels<T, CH>(kp, ref_of(w[0].idx, 0), ref_of(w[1].idx, 1), lane, xa, xb, na, nb, Kaa, Kbb, Kab);
+          pair_kernels<T, CH>(kp, locate<T, CH>(P, w[0].idx), locate<T, CH>(P, w[1].idx), lane, xa, xb, na, nb, Kaa, Kbb, Kab);
           double quad_p = ((double)Kaa + (double)Kbb) - 2.0 * (double)Kab;
           if (quad_p <= 0) quad_p = 1e-12;
           const double dp = w[0].g - w[1].g;
           const double gain_p = -(dp * dp) / quad_p;
-          pair_kernels<T, CH>(kp, ref_of(w[2].idx, 2), ref_of(w[3].idx, 3), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
+          pair_kernels<T, CH>(kp, locate<T, CH>(P, w[2].idx), locate<T, CH>(P, w[3].idx), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
           double quad_n = ((double)Kii + (double)Kjj) - 2.0 * (double)Kij;
           if (quad_n <= 0) quad_n = 1e-12;
           const double dn = w[2].g - w[3].g;
@@ -729,8 +686,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           si = a.idx; sj = b.idx; gi = a.g; gj = b.g; fi = a.flags; fj = b.flags;
           ti = pick == 0 ? 0 : 2;
           tj = ti + 1;
-          ai = si == L.i ? L.ai : (si == L.j ? L.aj : read_alpha(si, ti));
-          aj = sj == L.i ? L.ai : (sj == L.j ? L.aj : read_alpha(sj, tj));
         }
       }
 
@@ -746,17 +701,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         if (lane == 0) {
           sh->stop = 1;
           if (cta == 0) {
-            if (L.i >= 0) {   // the last step's alphas are still pending: each rank flushes what it owns
-              const int pend[2] = {L.i, L.j};
-              const double pval[2] = {L.ai, L.aj};
-              for (int q = 0; q < 2; ++q) {
-                const bool second = mirror && pend[q] >= lg;
-                const long long lrow = (second ? pend[q] - lg : pend[q]) - goff;
-                if (lrow >= 0 && lrow < l) {
-                  alpha[(second ? l : 0) + lrow] = pval[q];
-                }
-              }
-            }
             SolveResult r;
             r.n_iter = n_iter;
             r.last_i = stop_sel ? -1 : si;
@@ -779,7 +723,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         }
       } else {
         // ---- Solver.update / NuSolver.update: the analytic step (solver.py:82-145, 342-373) ----
-        if (!have_k) pair_kernels<T, CH>(kp, ref_of(si, ti), ref_of(sj, tj), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
+        // alpha units and the two rows are requested together: one memory round trip, not three
+        uint4 ua = make_uint4(0u, 0u, 0u, 0u), ub = ua;
+        const bool from_records = !(forced && epoch == 1);
+        if (from_records) { ua = load_unit(ti); ub = load_unit(tj); }
+        if (!have_k) pair_kernels<T, CH>(kp, locate<T, CH>(P, si), locate<T, CH>(P, sj), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
+        if (from_records) { ai = settle_alpha(ua, ti); aj = settle_alpha(ub, tj); }
         const double yi = (fi & F_YPOS) ? 1.0 : -1.0;
         const double yj = (fj & F_YPOS) ? 1.0 : -1.0;
         const StepOut so = smo_step(nu, (double)Kii, (double)Kjj, (double)Kij, yi, yj, gi, gj, ai, aj, Cbox);
@@ -797,12 +746,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         if (lane == 0) {
           sh->slot_i = slot_i; sh->slot_j = slot_j; sh->store_i = store_i; sh->store_j = store_j; sh->warm = warm;
           sh->p_ri = L.ri; sh->p_rj = L.rj; sh->p_si = L.si; sh->p_sj = L.sj;
-          sh->pi = L.i; sh->pj = L.j; sh->pai = L.ai; sh->paj = L.aj;
         }
         L.ri = gri; L.rj = grj; L.si = slot_i; L.sj = slot_j;
         if (warm) ++L.warm_cnt;
         L.stored_cnt += store_i + store_j;
-        L.di = so.di; L.dj = so.dj; L.i = si; L.j = sj; L.ai = so.ai; L.aj = so.aj;
+        L.di = so.di; L.dj = so.dj;
 #ifdef B2SVM_TIMELINE
         if (P.dbg_steps && lane == 0 && cta == 0 && epoch <= (uint32_t)DBG_EPOCHS) {
           double* o = P.dbg_steps + (size_t)DBG_EPOCHS * ncta * 6 + (size_t)(epoch - 1) * 2;
@@ -838,8 +786,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     // ---- sweep: both Q columns, gradient update, next candidates --------------------------------
     const double ci = sh->ci, cj = sh->cj;
     const int wi = sh->i, wj = sh->j, nfi = sh->fi, nfj = sh->fj;
-    const int pvi = sh->pi, pvj = sh->pj;
-    const double pai = sh->pai, paj = sh->paj;
+    const double nai = sh->ai, naj = sh->aj;
     const T ni = sh->ni, nj = sh->nj;
     V xi[C::CPL], xj[C::CPL];
 #pragma unroll
@@ -961,10 +908,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           const double g = cur.g0 - c;
           G[row] = g;
           int f = cur.f0;
-          if (v == wi) { f = nfi; flags[row] = (uint8_t)nfi; }
-          else if (v == wj) { f = nfj; flags[row] = (uint8_t)nfj; }
-          if (v == pvi) store_alpha(row, pai);
-          else if (v == pvj) store_alpha(row, paj);
+          if (v == wi) { f = nfi; flags[row] = (uint8_t)nfi; alpha[row] = nai; }
+          else if (v == wj) { f = nfj; flags[row] = (uint8_t)nfj; alpha[row] = naj; }
           consider(nu, f, g, v, best);
         }
         if (mirror) {
@@ -972,10 +917,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           const double g = cur.g1 - c;
           G[row + l] = g;
           int f = cur.f1;
-          if (v == wi) { f = nfi; flags[row + l] = (uint8_t)nfi; }
-          else if (v == wj) { f = nfj; flags[row + l] = (uint8_t)nfj; }
-          if (v == pvi) store_alpha(row + l, pai);
-          else if (v == pvj) store_alpha(row + l, paj);
+          if (v == wi) { f = nfi; flags[row + l] = (uint8_t)nfi; alpha[row + l] = nai; }
+          else if (v == wj) { f = nfj; flags[row + l] = (uint8_t)nfj; alpha[row + l] = naj; }
           consider(nu, f, g, v, best);
         }
       }

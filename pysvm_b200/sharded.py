@@ -3,8 +3,8 @@
 One process per GPU (``torch.distributed``).  Each rank owns a contiguous slice of the training rows
 and the matching slices of ``alpha`` / ``neg_y_grad``; per SMO iteration the persistent kernels of all
 ranks exchange their working-set candidates through 16-byte tagged records written straight into
-each other's memory over NVLink (CUDA IPC peer mappings), and read the two winning rows from the
-owner's published block.  ``torch.distributed`` is used for plumbing only: the one-off exchange of
+each other's memory over NVLink (CUDA IPC peer mappings).  X itself is read-only and replicated on every
+GPU, so the two winning rows of an iteration are local reads.  ``torch.distributed`` is used for plumbing only: the one-off exchange of
 IPC handles, a barrier before each solve, and the final gather / reduction of results.
 """
 from __future__ import annotations
@@ -117,13 +117,20 @@ def all_gather_array(a: np.ndarray, group=None) -> np.ndarray:
 
 
 class ShardedColumns(QColumns):
-    """QColumns over this rank's rows only; carries the shard geometry to b2svm_create."""
+    """QColumns of one rank: the FULL X (read-only, replicated on every GPU so the two winning rows of an
+    iteration are local reads) with this rank's slice of y; carries the shard geometry to b2svm_create."""
 
-    def __init__(self, X_local, y_local, kernel: KernelSpec, shard: Shard, mirror: bool = False, device=None,
+    def __init__(self, X_full, y_local, kernel: KernelSpec, shard: Shard, mirror: bool = False, device=None,
                  cache_bytes=None):
-        super().__init__(X_local, y_local, kernel, mirror=mirror, device=device, cache_bytes=cache_bytes)
         self.shard = shard
-        assert self.X.shape[0] == shard.n_local
+        super().__init__(X_full, y_local, kernel, mirror=mirror, device=device, cache_bytes=cache_bytes)
+        assert self.X.shape[0] == shard.n_global
+
+    def _n_local_rows(self) -> int:
+        return self.shard.n_local
+
+    def local_rows(self) -> torch.Tensor:
+        return self.X[self.shard.rows()]
 
 
 class ShardedSolver(SolverWithCache):
@@ -195,8 +202,7 @@ def fit_csvc_sharded(X: np.ndarray, y01: np.ndarray, C: float, kernel: KernelSpe
     y = np.array(y01, dtype=float)
     y[y != 1] = -1
     shard = plan(X.shape[0], world, rank)
-    func = ShardedColumns(np.ascontiguousarray(X[shard.rows()]), local_vector(y, shard, False), kernel, shard,
-                          cache_bytes=cache_bytes)
+    func = ShardedColumns(X, local_vector(y, shard, False), kernel, shard, cache_bytes=cache_bytes)
     solver = ShardedSolver(local_vector(-np.ones(X.shape[0]), shard, False), func.y, C, tol, func, group)
     stats = solver.solve(max_iter)
     return solver, shard, stats
@@ -213,8 +219,7 @@ def fit_svr_sharded(X: np.ndarray, z: np.ndarray, C: float, eps: float, kernel: 
     p[:l] -= z
     p[l:] += z
     shard = plan(l, world, rank)
-    func = ShardedColumns(np.ascontiguousarray(X[shard.rows()]), local_vector(y, shard, True), kernel, shard,
-                          mirror=True)
+    func = ShardedColumns(X, local_vector(y, shard, True), kernel, shard, mirror=True)
     solver = ShardedSolver(local_vector(p, shard, True), func.y, C, tol, func, group)
     stats = solver.solve(max_iter)
     return solver, shard, stats
@@ -224,7 +229,7 @@ def decision_sharded(solver: ShardedSolver, coef_local: torch.Tensor, Xq: np.nda
     """sum over ALL support rows of coef K(x_s, x_q): each rank sums its slice, one all-reduce adds them."""
     func = solver._engine.func
     q = to_device_matrix(np.asarray(Xq), func.device).to(func.X.dtype)
-    part = kernel_matvec(func.kernel, func.X, coef_local, q)
+    part = kernel_matvec(func.kernel, func.local_rows(), coef_local, q)
     if dist.get_backend(group) != "nccl":
         part = part.cpu()
     dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)

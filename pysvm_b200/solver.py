@@ -81,10 +81,13 @@ class QColumns:
         self.y = _dev_f64(y, self.device)
         self.kernel = kernel
         self.mirror = bool(mirror)
-        l = self.X.shape[0]
+        l = self._n_local_rows()
         if self.y.shape[0] != (2 * l if mirror else l):
             raise ValueError("y must have n_rows entries (2*n_rows in mirror mode)")
         self._engine = None
+
+    def _n_local_rows(self) -> int:
+        return self.X.shape[0]
 
     def __call__(self, i: int) -> torch.Tensor:
         if self._engine is None:
@@ -106,7 +109,7 @@ class _Engine:
         d.struct_bytes = C.sizeof(N.ProblemDesc)
         d.device = func.device.index if func.device.index is not None else torch.cuda.current_device()
         d.stream = None
-        d.n_rows, d.n_features = X.shape[0], X.shape[1]
+        d.n_rows, d.n_features = (shard.n_local if shard is not None else X.shape[0]), X.shape[1]
         d.x_dtype = N.F64 if X.dtype == torch.float64 else N.F32
         d.X = X.data_ptr()
         d.ldx = X.stride(0)
@@ -119,7 +122,7 @@ class _Engine:
         d.kernel = func.kernel.desc()
         esz = 8 if X.dtype == torch.float64 else 4
         n_glob = shard.n_global if shard is not None else X.shape[0]
-        full_q = int(n_glob) * int(X.shape[0]) * esz
+        full_q = int(n_glob) * int(d.n_rows) * esz
         cb = func.cache_bytes
         if cb is None:
             env = os.environ.get("B2SVM_CACHE_GB")
