@@ -249,6 +249,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- converged fit seconds (cold path), reported next to the throughput ---------------------------------
     fit_info = None
+    del est
+    import gc
+    gc.collect()                    # release the e2e fits' device memory (their Q-column caches) first
     if world == 1 and not args.no_full_fit:
         with contextlib.redirect_stdout(io.StringIO()):
             t0 = time.perf_counter()

@@ -727,6 +727,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         uint4 ua = make_uint4(0u, 0u, 0u, 0u), ub = ua;
         const bool from_records = !(forced && epoch == 1);
         if (from_records) { ua = load_unit(ti); ub = load_unit(tj); }
+        // (the slot-table entries of the two rows ride along in the same round trip)
+        const int gri = (int)((mirror && si >= lg) ? si - lg : si), grj = (int)((mirror && sj >= lg) ? sj - lg : sj);
+        int raw_si = -1, raw_sj = -1;
+        if (CACHE && P.cache_slots > 0) { raw_si = __ldcg(P.slot_of + gri); raw_sj = __ldcg(P.slot_of + grj); }
         if (!have_k) pair_kernels<T, CH>(kp, locate<T, CH>(P, si), locate<T, CH>(P, sj), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
         if (from_records) { ai = settle_alpha(ua, ti); aj = settle_alpha(ub, tj); }
         const double yi = (fi & F_YPOS) ? 1.0 : -1.0;
@@ -734,10 +738,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         const StepOut so = smo_step(nu, (double)Kii, (double)Kjj, (double)Kij, yi, yj, gi, gj, ai, aj, Cbox);
         // ---- Q-column cache: which of the two columns are already resident, which get stored now --------
         int slot_i = -1, slot_j = -1, store_i = 0, store_j = 0;
-        const int gri = (int)((mirror && si >= lg) ? si - lg : si), grj = (int)((mirror && sj >= lg) ? sj - lg : sj);
         if (CACHE && P.cache_slots > 0) {
-          slot_i = gri == L.ri ? L.si : (gri == L.rj ? L.sj : __ldcg(P.slot_of + gri));
-          slot_j = grj == L.ri ? L.si : (grj == L.rj ? L.sj : __ldcg(P.slot_of + grj));
+          slot_i = gri == L.ri ? L.si : (gri == L.rj ? L.sj : raw_si);
+          slot_j = grj == L.ri ? L.si : (grj == L.rj ? L.sj : raw_sj);
           if (slot_i < 0 && L.n_cached < P.cache_slots) { slot_i = L.n_cached++; store_i = 1; }
           if (grj == gri) { slot_j = slot_i; }
           else if (slot_j < 0 && L.n_cached < P.cache_slots) { slot_j = L.n_cached++; store_j = 1; }

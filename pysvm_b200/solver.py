@@ -99,7 +99,7 @@ class _Engine:
     """Owns one b2svm handle; keeps every tensor the handle points at alive."""
 
     def __init__(self, func: QColumns, alpha: torch.Tensor, g: torch.Tensor, Cbox: float, tol: float, variant: int,
-                 max_ctas: int = 0):
+                 max_ctas: int = 0, max_columns: Optional[int] = None):
         shard = getattr(func, "shard", None)
         self.lib = N.load()
         self.func = func
@@ -131,6 +131,13 @@ class _Engine:
             else:
                 free, _total = torch.cuda.mem_get_info(func.device)
                 cb = int(free * 0.7)
+        if max_columns is not None and func.cache_bytes is None:
+            # automatic policy: columns are only re-used once variables get selected again, i.e. after the
+            # opening phase in which every step drives fresh variables to a bound.  A run capped below one
+            # step per variable cannot get there, so it skips the cache (and its 4 B/row store traffic).
+            if max_columns < 2 * int(d.n_vars):
+                cb = 0
+            cb = min(int(cb), int(max_columns) * int(d.n_rows) * esz)
         d.cache_bytes = max(0, min(int(cb), full_q))
         d.max_ctas = max_ctas
         if shard is None:
@@ -219,7 +226,9 @@ class Solver:
     """
     _variant = N.SOLVER_C
 
-    def __init__(self, Q, p, y, C: float, tol: float = 1e-5, func: Optional[QColumns] = None, device=None):
+    def __init__(self, Q, p, y, C: float, tol: float = 1e-5, func: Optional[QColumns] = None, device=None,
+                 max_iter_hint: Optional[int] = None):
+        self._max_iter_hint = max_iter_hint
         if Q is not None:
             raise NotImplementedError("dense-Q mode (cache_size == 0) is not built; pass Q=None and a QColumns func")
         self.device = (func.device if func is not None else
@@ -249,7 +258,9 @@ class Solver:
             raise TypeError("func must be a pysvm_b200.solver.QColumns (an arbitrary Python callable cannot "
                             "run on the GPU; there is no CPU fallback)")
         self.y = func.y
-        self._engine = _Engine(func, self._alpha, self._g, self.C, self.tol, self._variant)
+        hint = getattr(self, "_max_iter_hint", None)
+        self._engine = _Engine(func, self._alpha, self._g, self.C, self.tol, self._variant,
+                               max_columns=None if hint is None else 2 * int(hint) + 2)
         self._init_state()
         return self._engine
 
@@ -314,8 +325,8 @@ class SolverWithCache(Solver):
     cache_size = 256
 
     def __init__(self, p, y, C: float, tol: float = 1e-5, cache_size: int = 256, func: Optional[QColumns] = None,
-                 device=None):
-        super().__init__(None, p, y, C, tol, func=func, device=device)
+                 device=None, max_iter_hint: Optional[int] = None):
+        super().__init__(None, p, y, C, tol, func=func, device=device, max_iter_hint=max_iter_hint)
 
 
 def nu_initial_alpha(y: np.ndarray, t: float) -> np.ndarray:
@@ -334,10 +345,11 @@ class NuSolver(Solver):
     r"""ν-variant with the extra constraint eᵀα = t (reference ``NuSolver``, solver.py:232-419)."""
     _variant = N.SOLVER_NU
 
-    def __init__(self, Q, p, y, t: float, C: float, tol: float = 1e-5, func: Optional[QColumns] = None, device=None):
+    def __init__(self, Q, p, y, t: float, C: float, tol: float = 1e-5, func: Optional[QColumns] = None, device=None,
+                 max_iter_hint: Optional[int] = None):
         self.t = t
         self._y_host = np.asarray(y.detach().cpu().numpy() if isinstance(y, torch.Tensor) else y, dtype=np.float64)
-        super().__init__(Q, p, y, C, tol, func=func, device=device)
+        super().__init__(Q, p, y, C, tol, func=func, device=device, max_iter_hint=max_iter_hint)
 
     def _init_state(self):
         # solver.py:269-281 / 456-473: alpha fill, then neg_y_grad = -y * (Q alpha + p)
@@ -367,8 +379,9 @@ class NuSolverWithCache(NuSolver):
     """Reference ``NuSolverWithCache(p, y, t, C, func, tol, cache_size)`` (solver.py:422-486)."""
     cache_size = 256
 
-    def __init__(self, p, y, t: float, C: float, func: QColumns, tol: float = 1e-5, cache_size: int = 256):
-        super().__init__(None, p, y, t, C, tol, func=func)
+    def __init__(self, p, y, t: float, C: float, func: QColumns, tol: float = 1e-5, cache_size: int = 256,
+                 max_iter_hint: Optional[int] = None):
+        super().__init__(None, p, y, t, C, tol, func=func, max_iter_hint=max_iter_hint)
 
 
 class _LazyColumn:

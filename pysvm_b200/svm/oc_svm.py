@@ -34,7 +34,7 @@ class OneClassSVM(BiNuSVC):
         p = np.zeros(l)
         y = np.ones(l)
         func, spec, rff = self._columns(X, y)
-        solver = SolverWithCache(p, y, 1, self.tol, self.cache_size, func=func)
+        solver = SolverWithCache(p, y, 1, self.tol, self.cache_size, func=func, max_iter_hint=self.max_iter)
         solver.alpha = oneclass_initial_alpha(self.nu, l)          # oc_svm.py:76-83, 93
         solver._engine.init_gradient(None)                         # oc_svm.py:94-95: g = -K alpha
         self._report(solver.solve(self.max_iter))

@@ -88,7 +88,7 @@ class BiLinearSVC(BaseEstimator):
         l, self.n_features = X.shape
         p = -np.ones(l)
         func = QColumns(X, y, KernelSpec("linear"))
-        solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func)
+        solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func, max_iter_hint=self.max_iter)
 
         def finish(stats):
             self._report(stats)
@@ -191,7 +191,7 @@ class BiKernelSVC(BiLinearSVC):
         if sharded.active() and not self.rff:
             return self._fit_sharded(X, y, sharded)
         func, spec, rff = self._columns(X, y)
-        solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func)
+        solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func, max_iter_hint=self.max_iter)
 
         def finish(stats):
             self._report(stats)
@@ -280,7 +280,7 @@ class BiNuSVC(BiKernelSVC):
         l, self.n_features = X.shape
         p = np.zeros(l)
         func, spec, rff = self._columns(X, y)
-        solver = NuSolverWithCache(p, y, self.nu * l, self.C, func, self.tol, self.cache_size)
+        solver = NuSolverWithCache(p, y, self.nu * l, self.C, func, self.tol, self.cache_size, max_iter_hint=self.max_iter)
 
         def finish(stats):
             self._report(stats)

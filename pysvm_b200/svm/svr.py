@@ -33,7 +33,7 @@ class LinearSVR(BiLinearSVC):
         l, self.n_features = X.shape
         y, p = _svr_vectors(z, l, self.eps)
         func = QColumns(X, y, KernelSpec("linear"), mirror=True)
-        solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func)
+        solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func, max_iter_hint=self.max_iter)
         self._report(solver.solve(self.max_iter))
         coef = solver.alpha[:l] - solver.alpha[l:]
         w = (func.X.to(torch.float64).t() @ coef).cpu().numpy()      # svr.py:89-90, telescoped
@@ -63,7 +63,7 @@ class KernelSVR(BiKernelSVC):
         l, self.n_features = X.shape
         y, p = _svr_vectors(z, l, self.eps)
         func, spec, rff = self._columns(X, y, mirror=True)
-        solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func)
+        solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func, max_iter_hint=self.max_iter)
         self._report(solver.solve(self.max_iter))
         self._finish(solver, func, spec, rff, X, solver.alpha[:l] - solver.alpha[l:])
         return self
@@ -93,7 +93,7 @@ class NuSVR(KernelSVR):
         p = np.empty(2 * l)
         p[:l], p[l:] = -z, z
         func, spec, rff = self._columns(X, y, mirror=True)
-        solver = NuSolverWithCache(p, y, self.C * l * self.nu, self.C, func, self.tol, self.cache_size)
+        solver = NuSolverWithCache(p, y, self.C * l * self.nu, self.C, func, self.tol, self.cache_size, max_iter_hint=self.max_iter)
         self._report(solver.solve(self.max_iter))
         self._finish(solver, func, spec, rff, X, solver.alpha[:l] - solver.alpha[l:])
         self.rho_, self.b_ = solver.calculate_rho_b()

@@ -22,7 +22,7 @@ lib.b2svm_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 N.check(lib.b2svm_debug_timeline(solver._engine.h, buf, NT_ALL))
 t = np.array(buf[:512], dtype=np.int64).reshape(64, 8)
 seg = t[2:60]
-names = ["join(0->1)", "publish(1->2)", "local poll(2->3)", "reduce+NVLink exch(3->4)", "step incl. remote rows(4->5)", "bar(5->6)", "sweep(6->next0)"]
+names = ["join(0->1)", "publish(1->2)", "box poll(2->3)", "final reduce(3->4)", "step(4->5)", "bar(5->6)", "sweep(6->next0)"]
 d01 = [seg[:, 1] - seg[:, 0], seg[:, 2] - seg[:, 1], seg[:, 3] - seg[:, 2], seg[:, 4] - seg[:, 3], seg[:, 5] - seg[:, 4], seg[:, 6] - seg[:, 5], np.r_[seg[1:, 0] - seg[:-1, 6], 0]]
 for r in range(world):
     if r == rank:
