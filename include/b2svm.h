@@ -45,7 +45,10 @@ enum {
 };
 
 enum { B2SVM_F32 = 0, B2SVM_F64 = 1 };
-enum { B2SVM_KERNEL_LINEAR = 0, B2SVM_KERNEL_POLY = 1, B2SVM_KERNEL_RBF = 2, B2SVM_KERNEL_SIGMOID = 3 };
+enum { B2SVM_KERNEL_LINEAR = 0, B2SVM_KERNEL_POLY = 1, B2SVM_KERNEL_RBF = 2, B2SVM_KERNEL_SIGMOID = 3,
+       /* X is the dense n_rows x n_rows kernel matrix itself (the reference's dense-Q mode, solver.py:25-45
+        * with cache_size == 0, and the RFF kernel z(a).z(b) of svc.py:225-228 for any D) */
+       B2SVM_KERNEL_PRECOMPUTED = 4 };
 enum { B2SVM_SOLVER_C = 0, B2SVM_SOLVER_NU = 1 };
 
 /* Kernel function description: pysvm/svm/svc.py:210-241 (register_kernel).

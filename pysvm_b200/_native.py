@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "_lib", "libb2svm.so")
 ABI_VERSION = 1
 
 F32, F64 = 0, 1
-KERNEL_IDS = {"linear": 0, "poly": 1, "rbf": 2, "sigmoid": 3}
+KERNEL_IDS = {"linear": 0, "poly": 1, "rbf": 2, "sigmoid": 3, "precomputed": 4}
 SOLVER_C, SOLVER_NU = 0, 1
 
 EXPORTS = [

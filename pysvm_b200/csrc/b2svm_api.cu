@@ -93,6 +93,36 @@ __global__ void column_kernel(const T* __restrict__ X, const T* __restrict__ nor
   }
 }
 
+template <typename T>
+__global__ void column_precomputed_kernel(const T* __restrict__ K, const double* __restrict__ y, int64_t l, int64_t nv,
+                                          int64_t i, double* __restrict__ out) {
+  const int64_t ri = i >= l ? i - l : i;
+  const double yi = y[i];
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < l; r += (int64_t)gridDim.x * blockDim.x) {
+    const double k = (double)K[r * l + ri];
+    out[r] = y[r] * k * yi;
+    if (nv > l) out[r + l] = y[r + l] * k * yi;
+  }
+}
+
+// m = K w for a precomputed kernel matrix (initial gradients of the nu / one-class starts), one warp per row
+template <typename T>
+__global__ void dense_matvec_kernel(const T* __restrict__ K, const double* __restrict__ w, int64_t l, double* __restrict__ m) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < l; r += nwarps) {
+    double s = 0.0;
+    for (int64_t c = lane; c < l; c += 32) s += w[c] * (double)K[r * l + c];
+    s = warp_sum(s);
+    if (lane == 0) m[r] = s;
+  }
+}
+
+__global__ void iota_kernel(int* __restrict__ a, int64_t n) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) a[v] = (int)v;
+}
+
 // Everything calculate_rho (solver.py:160-177) and calculate_rho_b (solver.py:378-419) need,
 // reduced in a fixed order by one block.
 struct BiasStats {
@@ -216,6 +246,7 @@ struct b2svm_handle {
   std::vector<void*> peer_blocks;          // opened IPC mappings (nullptr for this rank)
   void** peer_tables = nullptr;            // device: [world] mailbox pointer of every rank (own entry = block)
   bool attached = false, prepared = false;
+  bool precomputed = false;       // kernel.kind == 4: X is the kernel matrix itself and doubles as a full cache
   void* cache = nullptr;          // Q-column cache [cache_slots][n_rows] in the input dtype
   int* slot_of = nullptr;
   long long cache_slots = 0, cache_used = 0;
@@ -407,12 +438,15 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
   if (desc->n_vars >= (1ll << 29)) return fail(B2SVM_E_UNSUPPORTED, "n_vars must be below 2^29");
   if (!desc->X || !desc->y || !desc->alpha || !desc->neg_y_grad) return fail(B2SVM_E_INVALID, "null device pointer");
   if (desc->x_dtype != B2SVM_F32 && desc->x_dtype != B2SVM_F64) return fail(B2SVM_E_INVALID, "bad x_dtype");
-  if (desc->kernel.kind < 0 || desc->kernel.kind > 3) return fail(B2SVM_E_INVALID, "bad kernel kind");
+  if (desc->kernel.kind < 0 || desc->kernel.kind > 4) return fail(B2SVM_E_INVALID, "bad kernel kind");
+  const bool precomputed = desc->kernel.kind == 4;
+  if (precomputed && (desc->world > 1 || desc->n_features != desc->n_rows || desc->ldx != desc->n_rows))
+    return fail(B2SVM_E_INVALID, "precomputed kernel: X must be the dense n_rows x n_rows kernel matrix (single GPU)");
   if (desc->world > 1) {
     if (desc->world > 8) return fail(B2SVM_E_UNSUPPORTED, "at most 8 ranks (one NVSwitch box)");
     if (desc->rank < 0 || desc->rank >= desc->world) return fail(B2SVM_E_INVALID, "bad rank");
   }
-  const int ch = chunks_for(desc->x_dtype, desc->n_features);
+  const int ch = precomputed ? 4 : chunks_for(desc->x_dtype, desc->n_features);
   if (ch == 0) return fail(B2SVM_E_UNSUPPORTED, "n_features above the compiled maximum (512 f32 / 256 f64)");
 
   B2_CUDA(cudaSetDevice(desc->device));
@@ -421,6 +455,7 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
   h->stream = (cudaStream_t)desc->stream;
   h->ch = ch;
   h->f64 = desc->x_dtype == B2SVM_F64;
+  h->precomputed = precomputed;
   const int esz = h->f64 ? 8 : 4;
   h->dp = ch * 16 / esz;
   cudaDeviceProp prop;
@@ -451,7 +486,7 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
   B2_TRY(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
   // rows of X held by this GPU: its own slice on one GPU, ALL rows (replicated, read-only) in a sharded solve
   const int64_t lx = desc->world > 1 ? desc->n_rows_global : l;
-  const bool in_place = desc->ldx == h->dp && desc->n_features == h->dp && ((uintptr_t)desc->X % 16 == 0);
+  const bool in_place = precomputed || (desc->ldx == h->dp && desc->n_features == h->dp && ((uintptr_t)desc->X % 16 == 0));
   if (in_place) {
     h->Xuse = desc->X;
   } else {
@@ -467,13 +502,22 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     h->Xuse = xdst;
   }
   B2_TRY(cudaMalloc(&h->norms, (size_t)lx * esz));
-  if (h->f64)
+  if (precomputed) B2_TRY(cudaMemsetAsync(h->norms, 0, (size_t)lx * esz, h->stream));
+  else if (h->f64)
     row_norms_kernel<double><<<grid_for(lx * 32), 256, 0, h->stream>>>((const double*)h->Xuse, lx, h->dp, (double*)h->norms);
   else
     row_norms_kernel<float><<<grid_for(lx * 32), 256, 0, h->stream>>>((const float*)h->Xuse, lx, h->dp, (float*)h->norms);
   B2_TRY(cudaGetLastError());
   B2_TRY(cudaMalloc(&h->flags, (size_t)nv));
-  if (desc->cache_bytes > 0) {
+  if (precomputed) {
+    // the kernel matrix IS a completely filled column cache: every iteration takes the warm path
+    h->cache = const_cast<void*>(desc->X);
+    B2_TRY(cudaMalloc(&h->slot_of, sizeof(int) * (size_t)l));
+    iota_kernel<<<grid_for(l), 256, 0, h->stream>>>(h->slot_of, l);
+    B2_TRY(cudaGetLastError());
+    h->cache_slots = l;
+    h->cache_used = l;
+  } else if (desc->cache_bytes > 0) {
     // device-resident Q-column cache: as many whole columns (this GPU's rows) as the budget holds
     const size_t col_bytes = (size_t)l * esz;
     long long slots = (long long)(desc->cache_bytes / col_bytes);
@@ -527,7 +571,7 @@ int b2svm_destroy(b2svm_handle* h) {
   cudaFree(h->peer_tables);
   cudaFree(h->block);
   cudaFree(h->flags);
-  cudaFree(h->cache);
+  if (!h->precomputed) cudaFree(h->cache);
   cudaFree(h->slot_of);
   cudaFree(h->abort_flag);
   cudaFree(h->result);
@@ -576,8 +620,14 @@ int b2svm_init_gradient(b2svm_handle* h, const double* p) {
   double* m = h->scratch + l;
   row_weights_kernel<<<grid_for(l), 256, 0, h->stream>>>(h->d.y, h->d.alpha, l, nv, w);
   B2_CUDA(cudaGetLastError());
-  rc = kernel_matvec_impl(h->stream, h->d.kernel, h->d.x_dtype, h->dp, h->Xuse, l, h->dp, h->Xuse, l, h->dp, w, m);
-  if (rc) return rc;
+  if (h->precomputed) {
+    if (h->f64) dense_matvec_kernel<double><<<grid_for(l * 32), 256, 0, h->stream>>>((const double*)h->Xuse, w, l, m);
+    else dense_matvec_kernel<float><<<grid_for(l * 32), 256, 0, h->stream>>>((const float*)h->Xuse, w, l, m);
+    B2_CUDA(cudaGetLastError());
+  } else {
+    rc = kernel_matvec_impl(h->stream, h->d.kernel, h->d.x_dtype, h->dp, h->Xuse, l, h->dp, h->Xuse, l, h->dp, w, m);
+    if (rc) return rc;
+  }
   finish_gradient_kernel<<<grid_for(nv), 256, 0, h->stream>>>(h->d.y, pu, m, l, nv, h->d.neg_y_grad);
   B2_CUDA(cudaGetLastError());
   return B2SVM_OK;
@@ -609,6 +659,12 @@ int b2svm_kernel_column(b2svm_handle* h, int64_t i, double* out) {
   if (i < 0 || i >= h->d.n_vars) return fail(B2SVM_E_INVALID, "index out of range");
   B2_CUDA(cudaSetDevice(h->d.device));
   const int64_t l = h->d.n_rows;
+  if (h->precomputed) {
+    if (h->f64) column_precomputed_kernel<double><<<grid_for(l), 256, 0, h->stream>>>((const double*)h->Xuse, h->d.y, l, h->d.n_vars, i, out);
+    else column_precomputed_kernel<float><<<grid_for(l), 256, 0, h->stream>>>((const float*)h->Xuse, h->d.y, l, h->d.n_vars, i, out);
+    B2_CUDA(cudaGetLastError());
+    return B2SVM_OK;
+  }
   if (h->f64) {
     KernelParams<double> kp{h->d.kernel.kind, h->d.kernel.gamma, h->d.kernel.coef0, h->d.kernel.degree};
     column_kernel<double><<<grid_for(l * 32), 256, 0, h->stream>>>((const double*)h->Xuse, (const double*)h->norms,

@@ -155,7 +155,7 @@ struct Chunk<double> {
 // (pysvm/svm/svc.py:230-241): gamma / coef0 / degree are Python scalars there, so under NumPy's
 // promotion rules they are rounded to the array dtype first -- KernelParams<T> holds them in T.
 // ------------------------------------------------------------------------------------------
-enum { K_LINEAR = 0, K_POLY = 1, K_RBF = 2, K_SIGMOID = 3 };
+enum { K_LINEAR = 0, K_POLY = 1, K_RBF = 2, K_SIGMOID = 3, K_PRECOMPUTED = 4 };
 
 template <typename T>
 struct KernelParams {

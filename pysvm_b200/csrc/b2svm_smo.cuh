@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
 
   // ============================== producer warp ==============================================
   if (warp == NW) {
-    if (NT > 0) {
+    if (NT > 0 && P.kind != K_PRECOMPUTED) {   // a precomputed kernel matrix is only ever read through the cache path
       const unsigned char* Xb = reinterpret_cast<const unsigned char*>(P.X) + (size_t)P.row_offset * C::ROWB;
       unsigned long long Tp = 0;
       unsigned stage = 0, par = 0;   // stage = Tp % S, par = (Tp / S) & 1
@@ -411,6 +411,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       }
     }
     return r;
+  };
+
+  // K(a,a), K(b,b), K(a,b) for the leader: from the rows, or straight from a precomputed kernel matrix
+  auto pair_k = [&](int ia, int ib, V (&xa)[QL], V (&xb)[QL], T& na, T& nb, T& Kaa, T& Kbb, T& Kab) {
+    if (CACHE && P.kind == K_PRECOMPUTED) {
+      const long long ra = (mirror && ia >= lg) ? ia - lg : ia, rb = (mirror && ib >= lg) ? ib - lg : ib;
+      const T* Kc = reinterpret_cast<const T*>(P.cache);
+      na = nb = 0;
+      Kaa = __ldg(Kc + ra * l + ra);
+      Kbb = __ldg(Kc + rb * l + rb);
+      Kab = __ldg(Kc + ra * l + rb);
+    } else {
+      pair_kernels<T, CH>(kp, locate<T, CH>(P, ia), locate<T, CH>(P, ib), lane, xa, xb, na, nb, Kaa, Kbb, Kab);
+    }
   };
 
   // ---- initial selection pass over G / flags only (no X) -------------------------------------
@@ -634,6 +648,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       int fi = 0, fj = 0;
       bool stop_sel = false;
       V xi[QL], xj[QL];
+#pragma unroll
+      for (int q = 0; q < QL; ++q) { xi[q] = CK::zero(); xj[q] = CK::zero(); }
       T ni = 0, nj = 0, Kii = 0, Kjj = 0, Kij = 0;
       bool have_k = false;
       int ti = 0, tj = 1;   // candidate types the pair came from
@@ -660,12 +676,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         else {
           V xa[QL], xb[QL];
           T na, nb, Kaa, Kbb, Kab;
-          pair_kernels<T, CH>(kp, locate<T, CH>(P, w[0].idx), locate<T, CH>(P, w[1].idx), lane, xa, xb, na, nb, Kaa, Kbb, Kab);
+          pair_k(w[0].idx, w[1].idx, xa, xb, na, nb, Kaa, Kbb, Kab);
           double quad_p = ((double)Kaa + (double)Kbb) - 2.0 * (double)Kab;
           if (quad_p <= 0) quad_p = 1e-12;
           const double dp = w[0].g - w[1].g;
           const double gain_p = -(dp * dp) / quad_p;
-          pair_kernels<T, CH>(kp, locate<T, CH>(P, w[2].idx), locate<T, CH>(P, w[3].idx), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
+          pair_k(w[2].idx, w[3].idx, xi, xj, ni, nj, Kii, Kjj, Kij);
           double quad_n = ((double)Kii + (double)Kjj) - 2.0 * (double)Kij;
           if (quad_n <= 0) quad_n = 1e-12;
           const double dn = w[2].g - w[3].g;
@@ -731,7 +747,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         const int gri = (int)((mirror && si >= lg) ? si - lg : si), grj = (int)((mirror && sj >= lg) ? sj - lg : sj);
         int raw_si = -1, raw_sj = -1;
         if (CACHE && P.cache_slots > 0) { raw_si = __ldcg(P.slot_of + gri); raw_sj = __ldcg(P.slot_of + grj); }
-        if (!have_k) pair_kernels<T, CH>(kp, locate<T, CH>(P, si), locate<T, CH>(P, sj), lane, xi, xj, ni, nj, Kii, Kjj, Kij);
+        if (!have_k) pair_k(si, sj, xi, xj, ni, nj, Kii, Kjj, Kij);
         if (from_records) { ai = settle_alpha(ua, ti); aj = settle_alpha(ub, tj); }
         const double yi = (fi & F_YPOS) ? 1.0 : -1.0;
         const double yj = (fj & F_YPOS) ? 1.0 : -1.0;

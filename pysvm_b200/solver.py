@@ -221,8 +221,8 @@ class _Engine:
 class Solver:
     r"""SMO on  min ½ αᵀQα + pᵀα  s.t. yᵀα = 0, 0 ≤ α ≤ C  (reference ``Solver``, solver.py:5-184).
 
-    ``Q`` must be ``None``: columns come from ``func`` (a :class:`QColumns`).  The dense-Q mode of the
-    reference (``cache_size == 0``) is not built yet.
+    Columns come from ``func`` (a :class:`QColumns`), or -- the reference's dense-Q mode -- from a full
+    ``Q`` matrix, which the device solver uses as a precomputed kernel matrix.
     """
     _variant = N.SOLVER_C
 
@@ -230,7 +230,17 @@ class Solver:
                  max_iter_hint: Optional[int] = None):
         self._max_iter_hint = max_iter_hint
         if Q is not None:
-            raise NotImplementedError("dense-Q mode (cache_size == 0) is not built; pass Q=None and a QColumns func")
+            # dense-Q mode of the reference (solver.py:25-45 with cache_size == 0): Q = y y^T * K is handed
+            # over whole.  The device solver takes K itself as a precomputed kernel matrix.
+            if func is not None:
+                raise ValueError("pass either Q or func, not both")
+            dev = torch.device(device) if device is not None else default_device()
+            Qd = to_device_matrix(Q, dev)
+            yd = _dev_f64(y, dev).to(Qd.dtype)
+            if Qd.shape[0] != Qd.shape[1] or Qd.shape[0] != yd.shape[0]:
+                raise ValueError("Q must be n_vars x n_vars (mirror problems: pass func=QColumns(K, y, 'precomputed', mirror=True))")
+            K = (Qd * yd[:, None] * yd[None, :]).contiguous()
+            func = QColumns(K, y, KernelSpec("precomputed"), device=dev, cache_bytes=0)
         self.device = (func.device if func is not None else
                        (torch.device(device) if device is not None else default_device()))
         self.Q = None

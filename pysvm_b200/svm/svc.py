@@ -9,6 +9,7 @@ from sklearn.base import BaseEstimator
 from sklearn.metrics import accuracy_score
 from sklearn.multiclass import OneVsOneClassifier, OneVsRestClassifier
 
+from .._native import B2SVMError
 from ..rff import NormalRFF, rff_decision_device
 from ..solver import (KernelSpec, NuSolverWithCache, QColumns, SolverWithCache, default_device, kernel_matvec,
                       solve_batched, to_device_matrix)
@@ -45,8 +46,9 @@ class deferred_solves:
 class _Fitted:
     """What the reference keeps alive inside the ``decision_function`` closure."""
 
-    def __init__(self, solver, func, spec, coef, rff=None, X_raw=None):
+    def __init__(self, solver, func, spec, coef, rff=None, X_raw=None, Z=None):
         self.solver, self.func, self.spec, self.coef, self.rff, self.X_raw = solver, func, spec, coef, rff, X_raw
+        self.Z = Z            # random Fourier features of the training rows (rff=True)
         self._wz = None
 
     def kernel_sum(self, x) -> np.ndarray:
@@ -56,7 +58,7 @@ class _Fitted:
             # K(a, b) = z(a).z(b)  =>  coef.K(X, x) = z(x).(Z^T coef)
             Xq = to_device_matrix(np.array(x), dev).to(self.X_raw.dtype)
             if self._wz is None:
-                self._wz = self.func.X.t().contiguous() @ self.coef
+                self._wz = self.Z.t().contiguous() @ self.coef
             w, b = self.rff._device_params(dev)
             return rff_decision_device(Xq, w, b, self._wz).cpu().numpy()
         Xq = to_device_matrix(np.array(x), dev).to(self.func.X.dtype)
@@ -177,9 +179,21 @@ class BiKernelSVC(BiLinearSVC):
     def _columns(self, X, y, mirror=False):
         """Device Q-column source for this estimator's kernel (the reference's ``func``)."""
         spec, rff = self.register_kernel(X.std())
+        self._Z = None
         if rff is not None:
-            Z = rff.transform_device(to_device_matrix(X, default_device()))
-            return QColumns(Z, y, KernelSpec("linear"), mirror=mirror), spec, rff
+            Z = rff.transform_device(to_device_matrix(X, default_device()))       # n x D float64, like rff.py:20
+            self._Z = Z
+            if Z.shape[1] <= 256:
+                return QColumns(Z, y, KernelSpec("linear"), mirror=mirror), spec, rff
+            # wider feature maps (default D = 1000): the kernel z(a).z(b) is handed over as a precomputed
+            # n x n matrix (one library GEMM), which the solver reads like a completely filled column cache
+            n = Z.shape[0]
+            free, _ = torch.cuda.mem_get_info(Z.device)
+            if n * n * 8 > 0.6 * free:
+                raise NotImplementedError(f"rff=True with D={Z.shape[1]} > 256 needs the n x n kernel matrix "
+                                          f"({n * n * 8 / 2**30:.1f} GiB); use D <= 256 for this many rows")
+            K = torch.matmul(Z, Z.t()).contiguous()
+            return QColumns(K, y, KernelSpec("precomputed"), mirror=mirror, cache_bytes=0), spec, rff
         return QColumns(X, y, spec, mirror=mirror), spec, None
 
     def fit(self, X, y):
@@ -205,11 +219,22 @@ class BiKernelSVC(BiLinearSVC):
 
     def _finish(self, solver, func, spec, rff, X, coef):
         self._fitted = _Fitted(solver, func, func.kernel, coef, rff=rff,
-                               X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None)
-        self.rho_ = solver.calculate_rho()
+                               X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None,
+                               Z=getattr(self, "_Z", None))
+        try:
+            self.rho_ = solver.calculate_rho()
+        except B2SVMError:
+            # e.g. a single-class problem: the reference's fit() succeeds and calculate_rho() only raises
+            # (ValueError: min of an empty set, solver.py:175) once decision_function is called
+            self.rho_ = None
         a = solver.alpha.cpu().numpy()
         self.alpha_ = a
         self.support_ = np.flatnonzero(a > 0)
+
+    def _rho(self):
+        if self.rho_ is None:
+            raise ValueError("calculate_rho: zero-size bound set (no free support vector and an empty bound class)")
+        return self.rho_
 
     def _fit_sharded(self, X, y, sharded):
         """The same fit, row-sharded over the GPUs of the current process group (sharded.enable())."""
@@ -225,7 +250,7 @@ class BiKernelSVC(BiLinearSVC):
         return self
 
     def decision_function(self, x) -> np.ndarray:
-        return self._fitted.kernel_sum(x) - self.rho_
+        return self._fitted.kernel_sum(x) - self._rho()
 
     def predict(self, X) -> np.ndarray:
         return super().predict(X)
@@ -299,7 +324,8 @@ class BiNuSVC(BiKernelSVC):
 
     def _finish(self, solver, func, spec, rff, X, coef):
         self._fitted = _Fitted(solver, func, func.kernel, coef, rff=rff,
-                               X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None)
+                               X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None,
+                               Z=getattr(self, "_Z", None))
         a = solver.alpha.cpu().numpy()
         self.alpha_ = a
         self.support_ = np.flatnonzero(a > 0)

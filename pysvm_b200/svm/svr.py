@@ -102,7 +102,8 @@ class NuSVR(KernelSVR):
     def _finish(self, solver, func, spec, rff, X, coef):
         from ..solver import to_device_matrix
         self._fitted = _Fitted(solver, func, func.kernel, coef, rff=rff,
-                               X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None)
+                               X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None,
+                               Z=getattr(self, "_Z", None))
         self.alpha_ = solver.alpha.cpu().numpy()
 
     def decision_function(self, x):

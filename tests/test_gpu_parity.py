@@ -413,3 +413,86 @@ def test_readme_accuracy_table_digits_and_breast_cancer():
             # iterate differs, so its accuracy is held to 1.5 points.
             slack = 0.015 if model is P.LinearSVC else 1.5 / len(teY)
             assert abs(acc - want[name][j]) <= slack + 1e-9, (name, model.__name__, acc, want[name][j])
+
+
+# ------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("n,d,dtype", [(3, 1, np.float64), (33, 5, np.float32), (97, 130, np.float32),
+                                       (64, 512, np.float32), (50, 256, np.float64), (1000, 17, np.float64)])
+def test_ragged_shapes_match_oracle(n, d, dtype):
+    """Row counts that are not a multiple of the 32-row tile, feature counts that need padding, the widest
+    compiled rows (512 float32 / 256 float64): same trajectory as the oracle."""
+    *_, svc, _, _ = _mods()
+    rng = np.random.default_rng(n * 1000 + d)
+    X = rng.standard_normal((n, d)).astype(dtype)
+    y = (rng.random(n) < 0.5).astype(int)
+    y[0], y[1] = 1, 0
+    ref = O.fit_csvc(X, y, max_iter=10 ** 5)
+    est = svc.BiKernelSVC(max_iter=10 ** 5).fit(X, y)
+    iters_close(est.n_iter_, ref.n_iter, frac=0.02)
+    rel_close(est.alpha_, ref.alpha, atol=2e-4)
+    np.testing.assert_array_equal(est.predict(X), ref.predict(X))
+
+
+def test_single_class_stops_immediately():
+    """All labels equal: I_low is empty, the reference's select returns (-1, -1) at once (solver.py:66-75)."""
+    *_, svc, _, _ = _mods()
+    X = np.random.default_rng(0).standard_normal((40, 3))
+    est = svc.BiKernelSVC(max_iter=100).fit(X, np.ones(40, dtype=int))
+    assert est.n_iter_ == 0 and est.solve_stats_["converged"] == 1 and est.alpha_.sum() == 0.0
+    with pytest.raises(ValueError):          # the reference's calculate_rho: min() of an empty set
+        O.fit_csvc(X, np.ones(40, dtype=int), max_iter=100)
+    with pytest.raises(ValueError):          # ... which surfaces at decision time there, and here
+        est.decision_function(X)
+
+
+def test_too_many_features_is_an_error_not_a_fallback():
+    torch, _, S, *_ = _mods()
+    from pysvm_b200._native import B2SVMError
+    X = np.zeros((8, 600), dtype=np.float32)
+    y = np.array([1, -1] * 4, dtype=float)
+    with pytest.raises(B2SVMError, match="n_features"):
+        S.SolverWithCache(-np.ones(8), y, 1.0, func=S.QColumns(X, y, S.KernelSpec("rbf", 0.1)))
+
+
+def test_max_iter_zero_and_print(capsys):
+    *_, svc, _, _ = _mods()
+    X = np.random.default_rng(1).standard_normal((20, 2))
+    y = np.array([0, 1] * 10)
+    est = svc.BiKernelSVC(max_iter=0).fit(X, y)
+    assert est.n_iter_ == 0
+    assert "KernelSVC not coverage with 0 iterations" in capsys.readouterr().out      # for/else of svc.py:260-267
+
+
+# ------------------------------------------------------------------------------ precomputed kernel: RFF (any D), dense Q
+def test_g6_rff_default_D(golden, breast_cancer):
+    """BiKernelSVC(rff=True, D=1000): same RNG draws as the reference (seed 7), kernel z(a).z(b) handed to
+    the solver as a precomputed matrix."""
+    *_, svc, _, _ = _mods()
+    X, y = breast_cancer
+    g = golden("g6_breast_cancer_rff")
+    np.random.seed(7)
+    est = svc.BiKernelSVC(rff=True, D=1000, max_iter=10 ** 6).fit(X, y)
+    iters_close(est.n_iter_, int(g["n_iter"]), frac=0.05)
+    np.testing.assert_array_equal(est.support_, np.flatnonzero(g["alpha"] > 0))
+    rel_close(est.alpha_, g["alpha"], atol=2e-4)
+    rel_close(est.rho_, float(g["rho"]), atol=1e-5)
+    rel_close(est.decision_function(X), g["dec"], atol=1e-4)
+    np.testing.assert_array_equal(est.predict(X), g["pred"])
+
+
+def test_dense_q_solver_equals_column_solver(breast_cancer):
+    """Solver(Q, p, y, C): the reference's cache_size == 0 path (svc.py:251-253) gives the same trajectory."""
+    torch, _, S, *_ = _mods()
+    X, y01 = breast_cancer
+    y = np.where(y01 == 1, 1.0, -1.0)
+    spec = O.KernelSpec("rbf", 1 / (30 * X.std()))
+    K = O.make_kernel(spec)(X, X)
+    Q = y.reshape(-1, 1) * y * K
+    dense = S.Solver(Q, -np.ones(len(y)), y, 1.0, 1e-5)
+    sd = dense.solve(10 ** 6)
+    col = S.SolverWithCache(-np.ones(len(y)), y, 1.0, func=S.QColumns(X, y, S.KernelSpec("rbf", spec.gamma)))
+    sc = col.solve(10 ** 6)
+    iters_close(sd.n_iter, sc.n_iter)
+    assert sd.cold_sweeps == 0                       # a kernel matrix is a full cache: never a sweep of X
+    rel_close(dense.alpha.cpu().numpy(), col.alpha.cpu().numpy(), atol=1e-6)
+    np.testing.assert_allclose(dense.get_Q(5).cpu().numpy(), Q[:, 5], rtol=1e-12, atol=1e-14)
