@@ -496,3 +496,25 @@ def test_dense_q_solver_equals_column_solver(breast_cancer):
     assert sd.cold_sweeps == 0                       # a kernel matrix is a full cache: never a sweep of X
     rel_close(dense.alpha.cpu().numpy(), col.alpha.cpu().numpy(), atol=1e-6)
     np.testing.assert_allclose(dense.get_Q(5).cpu().numpy(), Q[:, 5], rtol=1e-12, atol=1e-14)
+
+
+def test_readme_regression_table_diabetes():
+    """tests/dataset_regression.py of the reference (README.md:136-140), diabetes column.  load_boston is
+    gone from scikit-learn, so its split's RNG consumption is emulated: the reference
+    then gives R^2 = 0.4537 / 0.1756 / 0.1459 for LinearSVR / KernelSVR / NuSVR at max_iter=1000."""
+    _, P, *_ = _mods()
+    from sklearn.datasets import load_diabetes
+    from sklearn.preprocessing import StandardScaler
+    from sklearn.model_selection import train_test_split
+    import contextlib, io
+    np.random.seed(2022)
+    train_test_split(np.zeros((506, 13)), np.zeros(506))           # the boston split that ran first
+    X, y = load_diabetes(return_X_y=True)
+    trX, teX, trY, teY = train_test_split(X, y)
+    sc = StandardScaler().fit(trX)
+    trX, teX = sc.transform(trX), sc.transform(teX)
+    want = {"LinearSVR": 0.4537, "KernelSVR": 0.1756, "NuSVR": 0.1459}
+    for model in (P.LinearSVR, P.KernelSVR, P.NuSVR):
+        with contextlib.redirect_stdout(io.StringIO()):
+            r2 = model(max_iter=1000).fit(trX, trY).score(teX, teY)
+        assert abs(r2 - want[model.__name__]) < 2e-3, (model.__name__, r2)
