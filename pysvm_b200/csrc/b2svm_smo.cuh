@@ -141,6 +141,7 @@ struct Shared {
   volatile long long consumed;
   LeaderState leader;
   int ticket;           // next dynamically assigned tile of the current sweep
+  uint4* peer[8];       // mailbox of every rank (copied once from global memory)
   volatile int status;  // a warp's watchdog tripped
   WCand wc[NW][NCAND];  // per-warp candidates of the sweep (with their alpha)
   WCand cw[NCAND];      // this CTA's winners
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     sh->consumed = 0;
     sh->ticket = NW;
     sh->status = 0;
+    for (int r = 0; r < P.world && r < 8; ++r) sh->peer[r] = const_cast<uint4*>(P.peer_mbox[r]);
     LeaderState L0;
     L0.di = L0.dj = 0.0;
     L0.ri = L0.rj = L0.si = L0.sj = -1;
@@ -489,8 +491,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       if (lane < world * ntypes) {
         const int r = lane / ntypes, k = lane - r * ntypes;
         const WCand c = sh->cw[k];
-        uint4* rp = const_cast<uint4*>(P.peer_mbox[r]) +
-                    ((((size_t)par * world + P.rank) * ncta + cta) * NCAND + k) * 2;
+        uint4* rp = sh->peer[r] + ((((size_t)par * world + P.rank) * ncta + cta) * NCAND + k) * 2;
         const uint4 rec = make_uint4((uint32_t)__double2loint(c.g), (uint32_t)__double2hiint(c.g), (uint32_t)c.idx,
                                      (epoch << 3) | (uint32_t)c.flags);
         const uint4 au = make_uint4((uint32_t)__double2loint(c.alpha), (uint32_t)__double2hiint(c.alpha), 0u, epoch);
@@ -519,6 +520,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       int wsrc[NCAND];
       const uint64_t t_start = globaltimer_ns();
       uint32_t rounds = 0;
+      uint32_t seen = 0;   // records whose row has been prefetched already (C variant: bit m*2+kk)
       for (;;) {
         bool all = true;
 #pragma unroll
@@ -555,6 +557,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
                   int& ws = (k0 == 0) ? wsrc[kk] : wsrc[2 + kk];
                   const bool take = kk == 0 ? better_max(g, idx, wk.g, wk.idx) : better_min(g, idx, wk.g, wk.idx);
                   if (take) { wk.g = g; wk.idx = idx; wk.flags = (int)(hh.w & 7u); ws = sidx; }
+                  // a candidate from another GPU's slice is never swept here: pull its row towards L2 now, so
+                  // the leader's fetch of the winning rows does not pay an HBM miss after the exchange
+                  if (world > 1 && cta == 0 && idx >= 0 && !((seen >> (k0 * 4 + m * 2 + kk)) & 1u) && P.kind != K_PRECOMPUTED) {
+                    const long long grow = (mirror && idx >= lg) ? idx - lg : idx;
+                    if (grow < goff || grow >= goff + l) {
+                      const char* rowp = reinterpret_cast<const char*>(P.X) + (size_t)grow * C::ROWB;
+#pragma unroll
+                      for (int b = 0; b < C::ROWB; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + b));
+                    }
+                    seen |= 1u << (k0 * 4 + m * 2 + kk);
+                  }
                 }
               }
             }
