@@ -70,7 +70,7 @@ __global__ void gather_rows_kernel(const T* __restrict__ Xa, int64_t lda, int d,
 // per shared-memory tile, query tile kept in shared memory chunk-major (conflict-free 16-B reads).
 constexpr int MV_TS = 32;
 
-template <typename T, int TQ>
+template <typename T, int TQ, int KIND>
 __global__ void __launch_bounds__(TQ) matvec_kernel(const T* __restrict__ sv, const T* __restrict__ svn,
                                                     const double* __restrict__ svc, int nsv, int dp,
                                                     const T* __restrict__ Xb, int64_t ldb, int d, int64_t nb,
@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(TQ) matvec_kernel(const T* __restrict__ sv, co
 #pragma unroll
     for (int s = 0; s < MV_TS; ++s) {
       if (t0 + s < s1) {
-        const T kv = kernel_value(kp, acc[s], tn[s], nq);
-        sum += tc[s] * (double)kv;
+        const T kv = kernel_value_k<KIND>(kp, acc[s], tn[s], nq);
+        sum = fma(tc[s], (double)kv, sum);
       }
     }
   }
@@ -164,6 +164,12 @@ static int matvec_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, cons
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double) * (size_t)nb, stream);
     return done(e == cudaSuccess ? B2SVM_OK : fail(B2SVM_E_CUDA, cudaGetErrorString(e)));
   }
+  if constexpr (sizeof(T) == 4) {
+    // float32, d <= 64, enough work to fill 128 x 128 tiles: tcgen05 path (b2svm_matvec_tc.cu)
+    const int mode = matvec_tc_mode(B2SVM_F32, d);
+    if (mode == 2 || (mode == 1 && nb >= 1024 && nsv >= 1024))
+      return done(matvec_tc(stream, k, d, (const float*)Xa, lda, idx, nsv, coef, (const float*)Xb, nb, ldb, out));
+  }
 #define MV_TRY(expr)                                                                     \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \
@@ -194,14 +200,21 @@ static int matvec_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, cons
   MV_TRY(cudaMalloc(&partial, sizeof(double) * (size_t)ny * nb));
   const size_t smem = smem_for(TQ);
   dim3 grid(gx, ny);
-#define MV_LAUNCH(TQV)                                                                                     \
-  do {                                                                                                     \
-    MV_TRY(cudaFuncSetAttribute(matvec_kernel<T, TQV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    matvec_kernel<T, TQV><<<grid, TQV, smem, stream>>>(sv, svn, svc, nsv, dp, Xb, ldb, d, nb, kp, slice, partial); \
+#define MV_LAUNCH2(TQV, KIND)                                                                                      \
+  do {                                                                                                             \
+    MV_TRY(cudaFuncSetAttribute(matvec_kernel<T, TQV, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    matvec_kernel<T, TQV, KIND><<<grid, TQV, smem, stream>>>(sv, svn, svc, nsv, dp, Xb, ldb, d, nb, kp, slice, partial); \
   } while (0)
-  if (TQ == 128) MV_LAUNCH(128);
-  else if (TQ == 64) MV_LAUNCH(64);
-  else MV_LAUNCH(32);
+#define MV_LAUNCH(TQV)                                 \
+  switch (k.kind) {                                    \
+    case K_RBF: MV_LAUNCH2(TQV, K_RBF); break;         \
+    case K_POLY: MV_LAUNCH2(TQV, K_POLY); break;       \
+    case K_SIGMOID: MV_LAUNCH2(TQV, K_SIGMOID); break; \
+    default: MV_LAUNCH2(TQV, K_LINEAR); break;         \
+  }
+  if (TQ == 128) { MV_LAUNCH(128) }
+  else if (TQ == 64) { MV_LAUNCH(64) }
+  else { MV_LAUNCH(32) }
   MV_TRY(cudaGetLastError());
   {
     int g = (int)std::min<int64_t>(148 * 8, (nb + 255) / 256);
@@ -210,6 +223,7 @@ static int matvec_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, cons
   }
   MV_TRY(cudaStreamSynchronize(stream));
 #undef MV_LAUNCH
+#undef MV_LAUNCH2
 #undef MV_TRY
   (void)rc;
   return done(B2SVM_OK);

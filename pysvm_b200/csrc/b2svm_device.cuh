@@ -184,6 +184,15 @@ __device__ __forceinline__ T kernel_value(const KernelParams<T>& k, T dot, T nor
   }
 }
 
+// same, with the kind resolved at compile time (dense epilogues: keeps pow / tanh out of the unrolled rbf loop)
+template <int KIND, typename T>
+__device__ __forceinline__ T kernel_value_k(const KernelParams<T>& k, T dot, T norm_a, T norm_b) {
+  if constexpr (KIND == K_RBF) return t_exp(-k.gamma * ((norm_a + norm_b) - T(2) * dot));
+  else if constexpr (KIND == K_POLY) return t_pow(k.gamma * dot + k.coef0, k.degree);
+  else if constexpr (KIND == K_SIGMOID) return t_tanh(k.gamma * dot + k.coef0);
+  else return dot;
+}
+
 // ------------------------------------------------------------------------------------------
 // working-set candidates.  Order: value first, then the LOWER index (np.argmax / np.argmin over an
 // index-sorted subset return the first extremum: solver.py:68-69).  idx < 0 = empty set.

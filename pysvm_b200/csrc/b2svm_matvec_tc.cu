@@ -1,0 +1,447 @@
+// K7 on the 5th-generation tensor cores: out[q] = sum_s coef_s K(sv_s, x_q) for float32 inputs.
+//
+//   D[q][s] = x_q . sv_s  is a GEMM (M = 128 queries per CTA, N = 128 support rows per tile, K = padded d)
+//   issued as tcgen05.mma.kind::tf32 by one elected thread, operands staged in shared memory by TMA
+//   (cp.async.bulk.tensor.2d, 128-byte swizzle), accumulators in TMEM (two buffers of 128 columns);
+//   four epilogue warps read the accumulator back with tcgen05.ld -- TMEM lane = query row, so every thread
+//   owns one query and walks the 128 support columns of the tile: kernel function, times coef, summed in
+//   float64 (the reference multiplies a float64 coefficient vector into the kernel block, svc.py:269-272).
+//   No cross-thread reduction, no n_a x n_b matrix.
+//
+// Precision: TF32 keeps 10 mantissa bits, far too few for exp(-gamma |a-b|^2) at 1e-4.  Every operand is split
+// x = hi + lo (hi = x with the low 13 bits cleared, lo = x - hi exactly) and the product is accumulated as
+// lo.hi + hi.lo + hi.hi ("3xTF32"): relative error ~2^-21, the same order as the FFMA path.
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
+#include <algorithm>
+#include <string>
+
+#include "b2svm_device.cuh"
+#include "b2svm_internal.h"
+
+namespace b2svm {
+
+constexpr int TC_M = 128, TC_N = 128, TC_KBLK = 32;           // tile: 128 x 128, K blocks of 32 floats = 128 B
+constexpr int TC_TILE_BYTES = TC_M * TC_KBLK * 4;              // one [128 rows][128 B] swizzled operand block
+constexpr int TC_EPI_WARPS = 8;                                 // two per TMEM lane quarter, 64 columns each
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;             // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: epilogue
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c_inner, int c_outer,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // bounded spin: a broken pipeline traps (reported as a CUDA error) instead of hanging the device
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand block [rows][128 B], 128-byte swizzle: 8-row groups are 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile) {
+  const uint32_t addr = smem_u32(smem_tile);
+  const uint32_t lo = ((addr & 0x3FFFFu) >> 4) | (1u << 16);          // start address, LBO = 1 (unused)
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO, descriptor version, SWIZZLE_128B
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
+
+#define B2_TMEM_LD32(taddr, v)                                                                                   \
+  asm volatile(                                                                                                  \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                  \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                 \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                  \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),         \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),   \
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])  \
+      : "r"(taddr)                                                                                               \
+      : "memory")
+
+// ------------------------------------------------------------------------------------------ operand preparation
+// rows -> (hi, lo) split, zero padded to [rows_pad][dp32]; optional row gather (support vectors), norms of the
+// ORIGINAL float32 values (they feed the rbf epilogue exactly like the FFMA path)
+__global__ void split_rows_kernel(const float* __restrict__ X, int64_t ld, int d, int dp, const int* __restrict__ idx,
+                                  int64_t rows, int64_t rows_pad, float* __restrict__ hi, float* __restrict__ lo,
+                                  float* __restrict__ norms, float norm_scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp; k < rows_pad; k += nwarps) {
+    const int64_t r = k < rows ? (idx ? (int64_t)idx[k] : k) : -1;
+    float s = 0.f;
+    for (int c = lane; c < dp; c += 32) {
+      const float v = (r >= 0 && c < d) ? X[r * ld + c] : 0.f;
+      const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      hi[k * dp + c] = h;
+      lo[k * dp + c] = v - h;
+      s += v * v;
+    }
+    s = warp_sum(s);
+    if (lane == 0 && norms) norms[k] = s * norm_scale;
+  }
+}
+
+__global__ void gather_coef_kernel(const double* __restrict__ coef, const int* __restrict__ idx, int n, int n_pad,
+                                   double* __restrict__ out) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_pad; k += gridDim.x * blockDim.x)
+    out[k] = k < n ? coef[idx[k]] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+struct TcParams {
+  const float* svn;      // [nsv_pad] squared norms of the support rows
+  const double* svc;     // [nsv_pad] coefficients (0 in the padding)
+  const float* qn;       // [nq_pad]
+  double* partial;       // [slices][nq]
+  int64_t nq;
+  int nsv;               // true number of support rows
+  int tiles_total;       // support tiles of 128 rows
+  int tiles_per_slice;   // blockIdx.y * tiles_per_slice .. + tiles_per_slice
+  int kb;                // K blocks of 32 floats (1 or 2)
+  int stages;            // B pipeline depth
+  float c2;              // rbf: 2 gamma log2(e)
+  int debug;             // B2SVM_TC_DEBUG: 1 = epilogue adds raw dots, 2 = no MMAs, 4 = no TMA of B
+  KernelParams<float> kp;
+};
+
+// Epilogue value of one (query, support row) pair from the tensor-core dot product.
+// rbf: exp(-gamma (|a|^2 + |b|^2 - 2 a.b)) = 2^(c2 * a.b + na' + nb') with the norms pre-scaled by -gamma log2(e)
+// (split_rows_kernel) and c2 = 2 gamma log2(e): one add, one fma, one MUFU.EX2.  The rounding of the exponent
+// is |x| 2^-24 relative -- the same order as the float32 rounding of -gamma * dist in the reference (svc.py:230-232).
+template <int KIND>
+__device__ __forceinline__ float epi_value(const TcParams& p, uint32_t dot_bits, float norm_s, float norm_q) {
+  const float dot = __uint_as_float(dot_bits);
+  if constexpr (KIND == K_RBF) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(p.c2, dot, norm_s + norm_q)));
+    return r;
+  } else {
+    return kernel_value_k<KIND>(p.kp, dot, norm_s, norm_q);
+  }
+}
+
+// 32 accumulator columns (registers v) against support rows base .. base+31: vector loads of the row metadata
+// (warp-uniform addresses), two independent float64 accumulation chains
+// float32 -> float64 of a kernel value.  F2F.F64.F32 issues at a fraction of the MUFU rate and was the epilogue's
+// bound; an rbf value is a non-negative normal (ex2.approx.ftz flushes denormals) or zero, so the widening is
+// three integer ops: exponent rebias (+896) and a 29-bit mantissa shift.  Zero maps to 2^-127 (1e-38 x coef: noise).
+template <int KIND>
+__device__ __forceinline__ double widen(float x) {
+  if constexpr (KIND == K_RBF) {
+    const uint32_t b = __float_as_uint(x);
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+  } else {
+    return (double)x;
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void accum32(const TcParams& p, const uint32_t (&v)[32], int base, float nq, double& s0,
+                                        double& s1) {
+  const float4* n4 = reinterpret_cast<const float4*>(p.svn + base);
+  const double2* c2 = reinterpret_cast<const double2*>(p.svc + base);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 n = __ldg(n4 + j);
+    const double2 ca = __ldg(c2 + 2 * j), cb = __ldg(c2 + 2 * j + 1);
+    s0 = fma(ca.x, widen<KIND>(epi_value<KIND>(p, v[4 * j + 0], n.x, nq)), s0);
+    s1 = fma(ca.y, widen<KIND>(epi_value<KIND>(p, v[4 * j + 1], n.y, nq)), s1);
+    s0 = fma(cb.x, widen<KIND>(epi_value<KIND>(p, v[4 * j + 2], n.z, nq)), s0);
+    s1 = fma(cb.y, widen<KIND>(epi_value<KIND>(p, v[4 * j + 3], n.w, nq)), s1);
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
+                 const __grid_constant__ CUtensorMap tm_s_hi, const __grid_constant__ CUtensorMap tm_s_lo, TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_tc[];
+  const int KB = p.kb, ST = p.stages;
+  // [A_hi KB blocks][A_lo KB blocks][stage: B_hi KB blocks, B_lo KB blocks] ...
+  unsigned char* a_hi = smem_tc;
+  unsigned char* a_lo = a_hi + (size_t)KB * TC_TILE_BYTES;
+  unsigned char* b_base = a_lo + (size_t)KB * TC_TILE_BYTES;
+  const size_t b_stage_bytes = (size_t)2 * KB * TC_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)ST * b_stage_bytes);
+  uint64_t* a_full = bars;            // 1
+  uint64_t* b_full = bars + 1;        // ST
+  uint64_t* b_empty = b_full + ST;    // ST
+  uint64_t* t_full = b_empty + ST;    // 2
+  uint64_t* t_empty = t_full + 2;     // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TC_M;
+  const int tile_begin = blockIdx.y * p.tiles_per_slice;
+  const int tile_end = min(p.tiles_total, tile_begin + p.tiles_per_slice);
+  const int ntile = max(0, tile_end - tile_begin);
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    for (int s = 0; s < ST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], TC_EPI_WARPS); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {   // TMEM: two accumulators of 128 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(a_full, (uint32_t)(2 * KB * TC_TILE_BYTES));
+      for (int kb = 0; kb < KB; ++kb) {
+        tma_load_2d(a_hi + (size_t)kb * TC_TILE_BYTES, &tm_q_hi, kb * TC_KBLK, q0, a_full);
+        tma_load_2d(a_lo + (size_t)kb * TC_TILE_BYTES, &tm_q_lo, kb * TC_KBLK, q0, a_full);
+      }
+      for (int it = 0; it < ntile; ++it) {
+        const int s = it % ST;
+        const uint32_t ph = (uint32_t)((it / ST) & 1);
+        mbar_wait(&b_empty[s], ph ^ 1u);
+        unsigned char* bh = b_base + (size_t)s * b_stage_bytes;
+        unsigned char* bl = bh + (size_t)KB * TC_TILE_BYTES;
+        if (p.debug & 4) { mbar_arrive(&b_full[s]); continue; }
+        mbar_arrive_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
+        const int row = (tile_begin + it) * TC_N;
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_2d(bh + (size_t)kb * TC_TILE_BYTES, &tm_s_hi, kb * TC_KBLK, row, &b_full[s]);
+          tma_load_2d(bl + (size_t)kb * TC_TILE_BYTES, &tm_s_lo, kb * TC_KBLK, row, &b_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one elected thread) =====
+    if (lane == 0) {
+      mbar_wait(a_full, 0);
+      for (int it = 0; it < ntile; ++it) {
+        const int s = it % ST, acc = it & 1;
+        mbar_wait(&t_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained this accumulator
+        mbar_wait(&b_full[s], (uint32_t)((it / ST) & 1));
+        tc_fence_after();
+        const unsigned char* bh = b_base + (size_t)s * b_stage_bytes;
+        const unsigned char* bl = bh + (size_t)KB * TC_TILE_BYTES;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_N);
+        uint32_t accumulate = 0;
+        // lo.hi + hi.lo + hi.hi, smallest terms first
+        for (int pass = (p.debug & 2) ? 3 : 0; pass < 3; ++pass) {
+          const unsigned char* A = pass == 0 ? a_lo : a_hi;
+          const unsigned char* B = pass == 1 ? bl : bh;
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t da = umma_desc_sw128(A + (size_t)kb * TC_TILE_BYTES);
+            const uint64_t db = umma_desc_sw128(B + (size_t)kb * TC_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_KBLK / 8; ++k) {   // UMMA_K = 8 tf32 = 32 bytes: advance the start address
+              tc_mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), TC_IDESC, accumulate);
+              accumulate = 1;
+            }
+          }
+        }
+        tc_commit(&b_empty[s]);     // the smem stage may be refilled once these MMAs have read it
+        tc_commit(&t_full[acc]);    // ... and the accumulator is complete
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane = query row; warps w and w+4 share a lane quarter and split the columns =====
+    const int quarter = warp & 3;                       // a warp may only touch TMEM lanes 32*(warp%4) ..
+    const int half = (warp - 2) >> 2;                   // columns half*64 .. +64 of the tile
+    const int qrow = quarter * 32 + lane;
+    const float nq = p.qn[q0 + qrow];
+    double sum = 0.0, sum1 = 0.0;
+    for (int it = 0; it < ntile; ++it) {
+      const int acc = it & 1;
+      mbar_wait(&t_full[acc], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const int s0 = (tile_begin + it) * TC_N + half * 64;
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + half * 64);
+      B2_TMEM_LD32(taddr, v0);
+      B2_TMEM_LD32(taddr + 32, v1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // the accumulator is in registers: hand the TMEM buffer back before the math
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (p.debug & 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += (double)__uint_as_float(v0[j]) + (double)__uint_as_float(v1[j]);
+        continue;
+      }
+      if (s0 + 64 <= p.nsv) {
+        accum32<KIND>(p, v0, s0, nq, sum, sum1);
+        accum32<KIND>(p, v1, s0 + 32, nq, sum, sum1);
+      } else {   // last, ragged tile: padding rows carry coefficient 0, but their kernel value need not be finite
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (s0 + j < p.nsv) sum = fma(__ldg(p.svc + s0 + j), widen<KIND>(epi_value<KIND>(p, v0[j], __ldg(p.svn + s0 + j), nq)), sum);
+          if (s0 + 32 + j < p.nsv)
+            sum = fma(__ldg(p.svc + s0 + 32 + j), widen<KIND>(epi_value<KIND>(p, v1[j], __ldg(p.svn + s0 + 32 + j), nq)), sum);
+        }
+      }
+    }
+    sum += sum1;
+    // the two column halves of a query row meet in shared memory (the A tiles are dead by now: every MMA that read
+    // them completed before the last t_full flipped)
+    double* red = reinterpret_cast<double*>(a_hi);
+    if (half == 1) red[qrow] = sum;
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
+    if (half == 0 && q0 + qrow < p.nq) p.partial[(size_t)blockIdx.y * p.nq + q0 + qrow] = sum + red[qrow];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+__global__ void reduce_partials_tc_kernel(const double* __restrict__ partial, int ny, int64_t nb, double* __restrict__ out) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nb; q += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int y = 0; y < ny; ++y) s += partial[(size_t)y * nb + q];
+    out[q] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int dp) {
+  const cuuint64_t dims[2] = {(cuuint64_t)dp, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)dp * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_KBLK, (cuuint32_t)TC_M};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int matvec_tc_mode(int x_dtype, int d) {
+  if (x_dtype != B2SVM_F32 || d > 64) return 0;
+  int mode = 1;
+  if (const char* e = getenv("B2SVM_MATVEC_TC")) mode = atoi(e);
+  if (mode <= 0) return 0;
+  return encode_fn() != nullptr ? std::min(mode, 2) : 0;
+}
+
+// idx / nsv: ordered list of rows of Xa with a non-zero coefficient (device), from the caller's compaction
+int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const float* Xa, int64_t lda, const int* idx, int nsv,
+              const double* coef, const float* Xb, int64_t nb, int64_t ldb, double* out) {
+  const int dp = (d + TC_KBLK - 1) / TC_KBLK * TC_KBLK;
+  const int KB = dp / TC_KBLK;
+  const int64_t nsv_pad = ((int64_t)nsv + TC_N - 1) / TC_N * TC_N;
+  const int64_t nq_pad = (nb + TC_M - 1) / TC_M * TC_M;
+  float *s_hi = nullptr, *s_lo = nullptr, *q_hi = nullptr, *q_lo = nullptr, *svn = nullptr, *qn = nullptr;
+  double *svc = nullptr, *partial = nullptr;
+  auto done = [&](int code) {
+    cudaFree(s_hi); cudaFree(s_lo); cudaFree(q_hi); cudaFree(q_lo); cudaFree(svn); cudaFree(qn); cudaFree(svc); cudaFree(partial);
+    return code;
+  };
+#define TC_TRY(expr)                                                                                             \
+  do {                                                                                                           \
+    cudaError_t _e = (expr);                                                                                     \
+    if (_e != cudaSuccess) return done(fail(B2SVM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)));  \
+  } while (0)
+  TC_TRY(cudaMalloc(&s_hi, sizeof(float) * nsv_pad * dp));
+  TC_TRY(cudaMalloc(&s_lo, sizeof(float) * nsv_pad * dp));
+  TC_TRY(cudaMalloc(&q_hi, sizeof(float) * nq_pad * dp));
+  TC_TRY(cudaMalloc(&q_lo, sizeof(float) * nq_pad * dp));
+  TC_TRY(cudaMalloc(&svn, sizeof(float) * nsv_pad));
+  TC_TRY(cudaMalloc(&qn, sizeof(float) * nq_pad));
+  TC_TRY(cudaMalloc(&svc, sizeof(double) * nsv_pad));
+  const float norm_scale = k.kind == K_RBF ? (float)(-(double)(float)k.gamma * 1.4426950408889634) : 1.0f;
+  auto grid_rows = [](int64_t rows) { return (int)std::max<int64_t>(1, std::min<int64_t>(148 * 8, (rows * 32 + 255) / 256)); };
+  split_rows_kernel<<<grid_rows(nsv_pad), 256, 0, stream>>>(Xa, lda, d, dp, idx, nsv, nsv_pad, s_hi, s_lo, svn, norm_scale);
+  split_rows_kernel<<<grid_rows(nq_pad), 256, 0, stream>>>(Xb, ldb, d, dp, nullptr, nb, nq_pad, q_hi, q_lo, qn, norm_scale);
+  gather_coef_kernel<<<std::max(1, (int)std::min<int64_t>(1184, (nsv_pad + 255) / 256)), 256, 0, stream>>>(coef, idx, nsv, (int)nsv_pad, svc);
+  TC_TRY(cudaGetLastError());
+
+  CUtensorMap m_qh, m_ql, m_sh, m_sl;
+  if (!make_map(&m_qh, q_hi, nq_pad, dp) || !make_map(&m_ql, q_lo, nq_pad, dp) || !make_map(&m_sh, s_hi, nsv_pad, dp) ||
+      !make_map(&m_sl, s_lo, nsv_pad, dp))
+    return done(fail(B2SVM_E_CUDA, "cuTensorMapEncodeTiled failed"));
+
+  TcParams p;
+  p.svn = svn; p.svc = svc; p.qn = qn; p.nq = nb; p.nsv = nsv;
+  p.tiles_total = (int)(nsv_pad / TC_N);
+  const int gx = (int)(nq_pad / TC_M);
+  int ny = std::max(1, std::min(p.tiles_total, (2 * 148 + gx - 1) / gx));
+  // one slice of support rows (hi + lo copies) should sit in L2 while the query tiles sweep over it
+  const int l2_tiles = std::max(1, (int)((32u << 20) / (2u * KB * TC_TILE_BYTES)));
+  ny = std::max(ny, (p.tiles_total + l2_tiles - 1) / l2_tiles);
+  ny = std::min(ny, 65535);
+  p.tiles_per_slice = (p.tiles_total + ny - 1) / ny;
+  ny = (p.tiles_total + p.tiles_per_slice - 1) / p.tiles_per_slice;
+  p.kb = KB;
+  p.c2 = (float)(2.0 * (double)(float)k.gamma * 1.4426950408889634);
+  p.debug = getenv("B2SVM_TC_DEBUG") ? atoi(getenv("B2SVM_TC_DEBUG")) : 0;
+  const size_t a_bytes = (size_t)2 * KB * TC_TILE_BYTES, b_stage = (size_t)2 * KB * TC_TILE_BYTES;
+  p.stages = (int)std::min<size_t>(4, (200 * 1024 - a_bytes) / b_stage);
+  if (p.stages < 2) return done(fail(B2SVM_E_UNSUPPORTED, "kernel_matvec (tensor path): n_features too large"));
+  p.kp = KernelParams<float>{k.kind, (float)k.gamma, (float)k.coef0, (float)k.degree};
+  TC_TRY(cudaMalloc(&partial, sizeof(double) * (size_t)ny * nb));
+  p.partial = partial;
+  const size_t smem = a_bytes + p.stages * b_stage + (size_t)(2 * p.stages + 8) * sizeof(uint64_t) + 1024;
+#define TC_LAUNCH(KIND)                                                                                             \
+  do {                                                                                                              \
+    TC_TRY(cudaFuncSetAttribute(matvec_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    matvec_tc_kernel<KIND><<<dim3(gx, ny), TC_THREADS, smem, stream>>>(m_qh, m_ql, m_sh, m_sl, p);                  \
+  } while (0)
+  switch (k.kind) {
+    case K_RBF: TC_LAUNCH(K_RBF); break;
+    case K_POLY: TC_LAUNCH(K_POLY); break;
+    case K_SIGMOID: TC_LAUNCH(K_SIGMOID); break;
+    default: TC_LAUNCH(K_LINEAR); break;
+  }
+#undef TC_LAUNCH
+  TC_TRY(cudaGetLastError());
+  reduce_partials_tc_kernel<<<std::max(1, (int)std::min<int64_t>(1184, (nb + 255) / 256)), 256, 0, stream>>>(partial, ny, nb, out);
+  TC_TRY(cudaGetLastError());
+  TC_TRY(cudaStreamSynchronize(stream));
+#undef TC_TRY
+  return done(B2SVM_OK);
+}
+
+}  // namespace b2svm
