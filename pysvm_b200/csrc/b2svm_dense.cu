@@ -165,7 +165,7 @@ static int matvec_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, cons
     return done(e == cudaSuccess ? B2SVM_OK : fail(B2SVM_E_CUDA, cudaGetErrorString(e)));
   }
   if constexpr (sizeof(T) == 4) {
-    // float32, d <= 64, enough work to fill 128 x 128 tiles: tcgen05 path (b2svm_matvec_tc.cu)
+    // float32, d <= 128, enough work to fill 128 x 128 tiles: tcgen05 path (b2svm_matvec_tc.cu)
     const int mode = matvec_tc_mode(B2SVM_F32, d);
     if (mode == 2 || (mode == 1 && nb >= 1024 && nsv >= 1024))
       return done(matvec_tc(stream, k, d, (const float*)Xa, lda, idx, nsv, coef, (const float*)Xb, nb, ldb, out));

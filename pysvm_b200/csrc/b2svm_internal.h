@@ -27,7 +27,7 @@ int kernel_matvec_impl(cudaStream_t stream, const b2svm_kernel_desc& k, int x_dt
                        int64_t na, int64_t lda, const void* Xb, int64_t nb, int64_t ldb, const double* coef,
                        double* out);
 
-// tensor-core (tcgen05, 3xTF32) variant for float32 rows with d <= 64 (b2svm_matvec_tc.cu).
+// tensor-core (tcgen05, 3xTF32) variant for float32 rows with d <= 128 (b2svm_matvec_tc.cu).
 // mode: 0 = not available / disabled, 1 = use for large problems, 2 = forced (B2SVM_MATVEC_TC=2)
 int matvec_tc_mode(int x_dtype, int d);
 int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const float* Xa, int64_t lda, const int* idx, int nsv,

@@ -23,8 +23,8 @@ namespace b2svm {
 
 constexpr int TC_M = 128, TC_N = 128, TC_KBLK = 32;           // tile: 128 x 128, K blocks of 32 floats = 128 B
 constexpr int TC_TILE_BYTES = TC_M * TC_KBLK * 4;              // one [128 rows][128 B] swizzled operand block
-constexpr int TC_EPI_WARPS = 8;                                 // two per TMEM lane quarter, 64 columns each
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;             // warp 0: TMA, warp 1: MMA + TMEM, warps 2-9: epilogue
+constexpr int TC_EPI_WARPS = 16;                                // four per TMEM lane quarter, 32 columns each
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;             // warp 0: TMA, warp 1: MMA + TMEM, warps 2-17: epilogue
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c_inner, int c_outer,
@@ -117,7 +117,7 @@ struct TcParams {
   int nsv;               // true number of support rows
   int tiles_total;       // support tiles of 128 rows
   int tiles_per_slice;   // blockIdx.y * tiles_per_slice .. + tiles_per_slice
-  int kb;                // K blocks of 32 floats (1 or 2)
+  int kb;                // K blocks of 32 floats (1 .. 4)
   int stages;            // B pipeline depth
   float c2;              // rbf: 2 gamma log2(e)
   int debug;             // B2SVM_TC_DEBUG: 1 = epilogue adds raw dots, 2 = no MMAs, 4 = no TMA of B
@@ -177,11 +177,11 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
                  const __grid_constant__ CUtensorMap tm_s_hi, const __grid_constant__ CUtensorMap tm_s_lo, TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_tc[];
   const int KB = p.kb, ST = p.stages;
-  // [A_hi KB blocks][A_lo KB blocks][stage: B_hi KB blocks, B_lo KB blocks] ...
+  // [A_hi KB blocks][A_lo KB blocks][stage: one K block of B_hi, B_lo] ...
   unsigned char* a_hi = smem_tc;
   unsigned char* a_lo = a_hi + (size_t)KB * TC_TILE_BYTES;
   unsigned char* b_base = a_lo + (size_t)KB * TC_TILE_BYTES;
-  const size_t b_stage_bytes = (size_t)2 * KB * TC_TILE_BYTES;
+  const size_t b_stage_bytes = (size_t)2 * TC_TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)ST * b_stage_bytes);
   uint64_t* a_full = bars;            // 1
   uint64_t* b_full = bars + 1;        // ST
@@ -220,56 +220,54 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
         tma_load_2d(a_hi + (size_t)kb * TC_TILE_BYTES, &tm_q_hi, kb * TC_KBLK, q0, a_full);
         tma_load_2d(a_lo + (size_t)kb * TC_TILE_BYTES, &tm_q_lo, kb * TC_KBLK, q0, a_full);
       }
-      for (int it = 0; it < ntile; ++it) {
-        const int s = it % ST;
-        const uint32_t ph = (uint32_t)((it / ST) & 1);
+      // one pipeline stage = one K block (32 floats) of a support tile, hi and lo copies
+      for (int step = 0; step < ntile * KB; ++step) {
+        const int s = step % ST, it = step / KB, kb = step - it * KB;
+        const uint32_t ph = (uint32_t)((step / ST) & 1);
         mbar_wait(&b_empty[s], ph ^ 1u);
         unsigned char* bh = b_base + (size_t)s * b_stage_bytes;
-        unsigned char* bl = bh + (size_t)KB * TC_TILE_BYTES;
         if (p.debug & 4) { mbar_arrive(&b_full[s]); continue; }
         mbar_arrive_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
         const int row = (tile_begin + it) * TC_N;
-        for (int kb = 0; kb < KB; ++kb) {
-          tma_load_2d(bh + (size_t)kb * TC_TILE_BYTES, &tm_s_hi, kb * TC_KBLK, row, &b_full[s]);
-          tma_load_2d(bl + (size_t)kb * TC_TILE_BYTES, &tm_s_lo, kb * TC_KBLK, row, &b_full[s]);
-        }
+        tma_load_2d(bh, &tm_s_hi, kb * TC_KBLK, row, &b_full[s]);
+        tma_load_2d(bh + TC_TILE_BYTES, &tm_s_lo, kb * TC_KBLK, row, &b_full[s]);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected thread) =====
     if (lane == 0) {
       mbar_wait(a_full, 0);
+      int step = 0;
       for (int it = 0; it < ntile; ++it) {
-        const int s = it % ST, acc = it & 1;
+        const int acc = it & 1;
         mbar_wait(&t_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained this accumulator
-        mbar_wait(&b_full[s], (uint32_t)((it / ST) & 1));
-        tc_fence_after();
-        const unsigned char* bh = b_base + (size_t)s * b_stage_bytes;
-        const unsigned char* bl = bh + (size_t)KB * TC_TILE_BYTES;
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_N);
         uint32_t accumulate = 0;
-        // lo.hi + hi.lo + hi.hi, smallest terms first
-        for (int pass = (p.debug & 2) ? 3 : 0; pass < 3; ++pass) {
-          const unsigned char* A = pass == 0 ? a_lo : a_hi;
-          const unsigned char* B = pass == 1 ? bl : bh;
-          for (int kb = 0; kb < KB; ++kb) {
-            const uint64_t da = umma_desc_sw128(A + (size_t)kb * TC_TILE_BYTES);
-            const uint64_t db = umma_desc_sw128(B + (size_t)kb * TC_TILE_BYTES);
+        for (int kb = 0; kb < KB; ++kb, ++step) {
+          const int s = step % ST;
+          mbar_wait(&b_full[s], (uint32_t)((step / ST) & 1));
+          tc_fence_after();
+          const unsigned char* bh = b_base + (size_t)s * b_stage_bytes;
+          const unsigned char* bl = bh + TC_TILE_BYTES;
+          // lo.hi + hi.lo + hi.hi per K block, small terms first
+          for (int pass = (p.debug & 2) ? 3 : 0; pass < 3; ++pass) {
+            const uint64_t da = umma_desc_sw128((pass == 0 ? a_lo : a_hi) + (size_t)kb * TC_TILE_BYTES);
+            const uint64_t db = umma_desc_sw128(pass == 1 ? bl : bh);
 #pragma unroll
             for (int k = 0; k < TC_KBLK / 8; ++k) {   // UMMA_K = 8 tf32 = 32 bytes: advance the start address
               tc_mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), TC_IDESC, accumulate);
               accumulate = 1;
             }
           }
+          tc_commit(&b_empty[s]);   // the smem stage may be refilled once these MMAs have read it
         }
-        tc_commit(&b_empty[s]);     // the smem stage may be refilled once these MMAs have read it
-        tc_commit(&t_full[acc]);    // ... and the accumulator is complete
+        tc_commit(&t_full[acc]);    // the accumulator is complete
       }
     }
   } else {
-    // ===== epilogue warps: TMEM lane = query row; warps w and w+4 share a lane quarter and split the columns =====
+    // ===== epilogue warps: TMEM lane = query row; the four warps of a lane quarter split the tile's columns =====
     const int quarter = warp & 3;                       // a warp may only touch TMEM lanes 32*(warp%4) ..
-    const int half = (warp - 2) >> 2;                   // columns half*64 .. +64 of the tile
+    const int part = (warp - 2) >> 2;                   // columns part*32 .. +32 of the tile
     const int qrow = quarter * 32 + lane;
     const float nq = p.qn[q0 + qrow];
     double sum = 0.0, sum1 = 0.0;
@@ -277,40 +275,36 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
       const int acc = it & 1;
       mbar_wait(&t_full[acc], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const int s0 = (tile_begin + it) * TC_N + half * 64;
-      uint32_t v0[32], v1[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + half * 64);
-      B2_TMEM_LD32(taddr, v0);
-      B2_TMEM_LD32(taddr + 32, v1);
+      const int s0 = (tile_begin + it) * TC_N + part * 32;
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + part * 32);
+      B2_TMEM_LD32(taddr, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      // the accumulator is in registers: hand the TMEM buffer back before the math
+      // the accumulator slice is in registers: hand the TMEM buffer back before the math
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);
       if (p.debug & 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += (double)__uint_as_float(v0[j]) + (double)__uint_as_float(v1[j]);
+        for (int j = 0; j < 32; ++j) sum += (double)__uint_as_float(v[j]);
         continue;
       }
-      if (s0 + 64 <= p.nsv) {
-        accum32<KIND>(p, v0, s0, nq, sum, sum1);
-        accum32<KIND>(p, v1, s0 + 32, nq, sum, sum1);
+      if (s0 + 32 <= p.nsv) {
+        accum32<KIND>(p, v, s0, nq, sum, sum1);
       } else {   // last, ragged tile: padding rows carry coefficient 0, but their kernel value need not be finite
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (s0 + j < p.nsv) sum = fma(__ldg(p.svc + s0 + j), widen<KIND>(epi_value<KIND>(p, v0[j], __ldg(p.svn + s0 + j), nq)), sum);
-          if (s0 + 32 + j < p.nsv)
-            sum = fma(__ldg(p.svc + s0 + 32 + j), widen<KIND>(epi_value<KIND>(p, v1[j], __ldg(p.svn + s0 + 32 + j), nq)), sum);
-        }
+        for (int j = 0; j < 32; ++j)
+          if (s0 + j < p.nsv) sum = fma(__ldg(p.svc + s0 + j), widen<KIND>(epi_value<KIND>(p, v[j], __ldg(p.svn + s0 + j), nq)), sum);
       }
     }
     sum += sum1;
-    // the two column halves of a query row meet in shared memory (the A tiles are dead by now: every MMA that read
+    // the column parts of a query row meet in shared memory (the A tiles are dead by now: every MMA that read
     // them completed before the last t_full flipped)
-    double* red = reinterpret_cast<double*>(a_hi);
-    if (half == 1) red[qrow] = sum;
+    double* red = reinterpret_cast<double*>(a_hi);      // [3][128]
+    if (part > 0) red[(part - 1) * TC_M + qrow] = sum;
     asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
-    if (half == 0 && q0 + qrow < p.nq) p.partial[(size_t)blockIdx.y * p.nq + q0 + qrow] = sum + red[qrow];
+    if (part == 0 && q0 + qrow < p.nq)
+      p.partial[(size_t)blockIdx.y * p.nq + q0 + qrow] = ((sum + red[qrow]) + red[TC_M + qrow]) + red[2 * TC_M + qrow];
   }
 
   tc_fence_before();
@@ -359,7 +353,7 @@ static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int dp) {
 }
 
 int matvec_tc_mode(int x_dtype, int d) {
-  if (x_dtype != B2SVM_F32 || d > 64) return 0;
+  if (x_dtype != B2SVM_F32 || d > 128) return 0;
   int mode = 1;
   if (const char* e = getenv("B2SVM_MATVEC_TC")) mode = atoi(e);
   if (mode <= 0) return 0;
@@ -417,8 +411,8 @@ int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const floa
   p.kb = KB;
   p.c2 = (float)(2.0 * (double)(float)k.gamma * 1.4426950408889634);
   p.debug = getenv("B2SVM_TC_DEBUG") ? atoi(getenv("B2SVM_TC_DEBUG")) : 0;
-  const size_t a_bytes = (size_t)2 * KB * TC_TILE_BYTES, b_stage = (size_t)2 * KB * TC_TILE_BYTES;
-  p.stages = (int)std::min<size_t>(4, (200 * 1024 - a_bytes) / b_stage);
+  const size_t a_bytes = (size_t)2 * KB * TC_TILE_BYTES, b_stage = (size_t)2 * TC_TILE_BYTES;
+  p.stages = (int)std::min<size_t>(6, (200 * 1024 - a_bytes) / b_stage);
   if (p.stages < 2) return done(fail(B2SVM_E_UNSUPPORTED, "kernel_matvec (tensor path): n_features too large"));
   p.kp = KernelParams<float>{k.kind, (float)k.gamma, (float)k.coef0, (float)k.degree};
   TC_TRY(cudaMalloc(&partial, sizeof(double) * (size_t)ny * nb));

@@ -47,7 +47,8 @@ def main():
     g = torch.Generator(device="cpu").manual_seed(5)
     worst = 0.0
     for (na, nb, d, kind) in [(1000, 777, 32, "rbf"), (4096, 4096, 64, "rbf"), (3333, 2000, 7, "rbf"), (2048, 1500, 33, "poly"),
-                              (2048, 1500, 48, "sigmoid"), (5000, 129, 20, "linear"), (130, 5000, 64, "rbf")]:
+                              (2048, 1500, 48, "sigmoid"), (5000, 129, 20, "linear"), (130, 5000, 64, "rbf"),
+                              (3000, 2500, 100, "rbf"), (2000, 3000, 128, "rbf"), (1500, 1500, 96, "poly")]:
         Xa = torch.randn(na, d, generator=g).to(dev)
         Xb = torch.randn(nb, d, generator=g).to(dev)
         coef = torch.randn(na, generator=g, dtype=torch.float64).to(dev)
@@ -83,6 +84,15 @@ def main():
     o_ff, t_ff = run(0, spec, Xa, coef, Xb, reps=1)
     rel = ((o_tc - o_ff).abs().max() / o_ff.abs().max()).item()
     print(f"400k x 200k d=64: tcgen05 {t_tc*1e3:.1f} ms   ffma {t_ff*1e3:.1f} ms   max rel diff {rel:.2e}")
+    d = 128
+    Xa = torch.randn(100_000, d, generator=g).to(dev)
+    Xb = torch.randn(200_000, d, generator=g).to(dev)
+    coef = torch.rand(100_000, generator=g, dtype=torch.float64).to(dev) + 0.1
+    spec = KernelSpec("rbf", gamma=1.0 / d)
+    o_tc, t_tc = run(2, spec, Xa, coef, Xb, reps=2)
+    o_ff, t_ff = run(0, spec, Xa, coef, Xb, reps=1)
+    rel = ((o_tc - o_ff).abs().max() / o_ff.abs().max()).item()
+    print(f"200k x 100k d=128 (C3 decision): tcgen05 {t_tc*1e3:.1f} ms   ffma {t_ff*1e3:.1f} ms   max rel diff {rel:.2e}")
     assert worst < 2e-6, worst
     print("OK")
 

@@ -518,3 +518,55 @@ def test_readme_regression_table_diabetes():
         with contextlib.redirect_stdout(io.StringIO()):
             r2 = model(max_iter=1000).fit(trX, trY).score(teX, teY)
         assert abs(r2 - want[model.__name__]) < 2e-3, (model.__name__, r2)
+
+
+# ------------------------------------------------------------------------------ K7 on the tensor cores
+def _matvec_truth(torch, kind, gamma, coef0, degree, Xa, coef, Xb):
+    a, q = Xa.double(), Xb.double()
+    dot = q @ a.T
+    if kind == "rbf":
+        k = torch.exp(-gamma * ((q * q).sum(1)[:, None] + (a * a).sum(1)[None, :] - 2 * dot).clamp_min(0))
+    elif kind == "poly":
+        k = (gamma * dot + coef0) ** degree
+    elif kind == "sigmoid":
+        k = torch.tanh(gamma * dot + coef0)
+    else:
+        k = dot
+    return k @ coef.double()
+
+
+@pytest.mark.parametrize("na,nb,d,kind", [(1000, 777, 32, "rbf"), (2500, 1300, 64, "rbf"), (3333, 700, 7, "rbf"),
+                                          (2048, 1500, 33, "poly"), (2048, 900, 48, "sigmoid"), (5000, 129, 20, "linear"),
+                                          (130, 3000, 100, "rbf"), (1111, 2222, 128, "rbf"), (1, 300, 16, "rbf")])
+def test_tensor_core_matvec_matches_float64(monkeypatch, na, nb, d, kind):
+    """b2svm_kernel_matvec through the tcgen05 3xTF32 path (forced) and through the FFMA path against a float64
+    evaluation of svc.py:230-241 + the coefficient product of svc.py:269-272.  Tolerance 2e-6 of the output
+    scale: float32 kernel values, float64 accumulation -- both device paths sit at a few 1e-7."""
+    torch, _, S, *_ = _mods()
+    g = torch.Generator().manual_seed(na + nb + d)
+    dev = torch.device("cuda:0")
+    Xa, Xb = torch.randn(na, d, generator=g).to(dev), torch.randn(nb, d, generator=g).to(dev)
+    coef = torch.randn(na, generator=g, dtype=torch.float64).to(dev)
+    if na > 4:
+        coef[torch.rand(na, generator=g).to(dev) < 0.4] = 0.0
+    spec = S.KernelSpec(kind, gamma=1.0 / d, coef0=0.5 if kind in ("poly", "sigmoid") else 0.0, degree=3)
+    ref = _matvec_truth(torch, kind, spec.gamma, spec.coef0, 3, Xa, coef, Xb)
+    scale = max(ref.abs().max().item(), 1e-30)
+    for mode in ("2", "0"):
+        monkeypatch.setenv("B2SVM_MATVEC_TC", mode)
+        out = S.kernel_matvec(spec, Xa, coef, Xb)
+        assert (out - ref).abs().max().item() / scale < 2e-6, (mode, kind)
+
+
+def test_decision_function_is_the_same_on_both_matvec_paths(monkeypatch, breast_cancer):
+    """A fitted KernelSVC scores the same rows through the tensor-core and the FFMA mat-vec (1e-5 relative)."""
+    _, _, _, svc, *_ = _mods()
+    X, y = breast_cancer
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    est = svc.BiKernelSVC(max_iter=2000).fit(X, y)
+    monkeypatch.setenv("B2SVM_MATVEC_TC", "2")
+    a = np.asarray(est.decision_function(X))
+    monkeypatch.setenv("B2SVM_MATVEC_TC", "0")
+    b = np.asarray(est.decision_function(X))
+    np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert (np.sign(a) == np.sign(b)).all()
