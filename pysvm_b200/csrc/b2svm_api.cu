@@ -235,7 +235,8 @@ struct b2svm_handle {
   double* p_dev = nullptr;      // staging for host-side p
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 0;
-  int ncta = 1, tiles_per_cta = 1, stages = 2;
+  int ncta = 1, tiles_per_cta = 1, stages = 2, sub = 1, stages1 = 2;
+  size_t smem_bytes1 = 0;
   long long ntiles = 0;
   size_t smem_bytes = 0;
   int launches = 0;
@@ -266,9 +267,8 @@ inline int grid_for(int64_t n, int block = 256, int cap = 148 * 8) {
 template <typename T, int CH>
 struct Geometry {
   using C = Cfg<T, CH>;
-  static size_t smem_for(int stages, bool multi) {
-    (void)multi;
-    return (size_t)stages * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + MAX_STAGES * sizeof(unsigned) +
+  static size_t smem_for(int stages, int sub) {
+    return (size_t)stages * sub * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + MAX_STAGES * sizeof(unsigned) +
            2 * (size_t)C::ROWB +
            sizeof(Shared<T>) + 128;
   }
@@ -280,13 +280,14 @@ constexpr size_t kRingBudget = 204 * 1024;
 template <typename T, int CH>
 int plan_T(b2svm_handle* h) {
   using C = Cfg<T, CH>;
-  int stages = (int)std::min<size_t>(MAX_STAGES, kRingBudget / C::TILE_BYTES);
-  if (stages < 2) stages = 2;
-  const bool multi = h->d.world > 1;
-  while (stages > 2 && Geometry<T, CH>::smem_for(stages, multi) > kSmemBudget) --stages;
-  h->stages = stages;
-  h->smem_bytes = Geometry<T, CH>::smem_for(stages, multi);
   h->ntiles = (h->d.n_rows + C::BR - 1) / C::BR;
+  auto geometry = [](int sub, int& stages, size_t& smem) {
+    stages = (int)std::min<size_t>(MAX_STAGES, kRingBudget / ((size_t)sub * C::TILE_BYTES));
+    if (stages < 2) stages = 2;
+    while (stages > 2 && Geometry<T, CH>::smem_for(stages, sub) > kSmemBudget) --stages;
+    smem = Geometry<T, CH>::smem_for(stages, sub);
+  };
+  geometry(1, h->stages1, h->smem_bytes1);   // batched mode (one CTA per problem) always runs with single tiles
   // every rank of a sharded solve must launch the same number of CTAs (the mailbox is indexed rank * ncta + cta):
   // plan with the common slice size, not with this rank's (possibly shorter) last slice
   const long long plan_tiles = h->d.world > 1 ? (h->rows_per_rank + C::BR - 1) / C::BR : h->ntiles;
@@ -295,9 +296,20 @@ int plan_T(b2svm_handle* h) {
   int max_ctas = h->d.max_ctas > 0 ? h->d.max_ctas : h->num_sms;
   if (const char* e = getenv("B2SVM_MAX_CTAS")) max_ctas = std::max(1, atoi(e));
   max_ctas = std::min(max_ctas, h->num_sms);
+  // narrow rows: a 32-row tile is only 2-8 KB, and per-tile costs (ticket, mbarrier round trip, one bulk copy
+  // issued by the single producer lane) dominate a long sweep.  Move several tiles per ring stage ("macro tile")
+  // once every warp still gets at least two of them per sweep.
+  int sub = 1;
+  const int max_sub = std::max<int>(1, 16384 / C::TILE_BYTES);
+  while (sub * 2 <= max_sub && plan_tiles >= (long long)max_ctas * NW * (sub * 2) * 2) sub *= 2;
+  if (const char* e = getenv("B2SVM_SUB")) sub = std::max(1, std::min(max_sub, atoi(e)));
+  h->sub = sub;
+  int stages = 2;
+  geometry(sub, stages, h->smem_bytes);
+  h->stages = stages;
   long long ncta = std::max<long long>(1, std::min<long long>(max_ctas, plan_tiles / min_tiles));
   // prefer a split whose slices fit the ring, so X stays resident in shared memory for the whole solve
-  const long long fit = (plan_tiles + stages - 1) / stages;
+  const long long fit = ((plan_tiles + sub - 1) / sub + stages - 1) / stages;
   if (fit <= max_ctas) ncta = std::max(ncta, fit);
   // ... and, when the GPU has room, one tile per consumer warp (no intra-CTA imbalance)
   const long long one_each = (plan_tiles + NW - 1) / NW;
@@ -350,6 +362,7 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.degree = h->d.kernel.degree;
   P.ncta = h->ncta;
   P.tiles_per_cta = h->tiles_per_cta;
+  P.sub = h->sub;
   P.ntiles = h->ntiles;
   P.abort_flag = h->abort_flag;
   P.result = h->result;
@@ -798,6 +811,7 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
     memset(&P[k], 0, sizeof(ProblemDev));
     fill_problem(h, P[k], max_iter, -1, -1);
     P[k].ncta = 1;
+    P[k].sub = 1;
     P[k].tiles_per_cta = (int)h->ntiles;
     P[k].result = rd + k;
   }
@@ -808,7 +822,7 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
   for (int k = 0; k < count; ++k) any_cache = any_cache || handles[k]->cache_slots > 0;
   bool any_generic = false;
   for (int k = 0; k < count; ++k) any_generic = any_generic || needs_generic(handles[k]);
-  int rc = launch(h0->f64, h0->ch, any_cache, any_generic, pd, count, 1, h0->stages, h0->smem_bytes, h0->stream);
+  int rc = launch(h0->f64, h0->ch, any_cache, any_generic, pd, count, 1, h0->stages1, h0->smem_bytes1, h0->stream);
   if (rc == B2SVM_OK) {
     cudaEventRecord(h0->ev1, h0->stream);
     std::vector<SolveResult> R(count);

@@ -68,6 +68,7 @@ struct ProblemDev {
   double gamma, coef0, degree;
   int ncta;             // CTAs cooperating on this problem
   int tiles_per_cta;
+  int sub;              // 32-row tiles per ring stage (narrow rows: several tiles travel in one bulk copy)
   long long ntiles;
   uint4* mbox;          // local mailbox [2][world * ncta][NCAND][2] {record, alpha unit} (zeroed before every launch)
   uint4* const* peer_mbox;   // [world] every rank's mailbox (peer mapping; own entry = mbox)
@@ -236,7 +237,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
 
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* ring = smem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)ring_stages * C::TILE_BYTES);
+  const ProblemDev& P = probs[blockIdx.x / ncta_pp];
+  // tiles per ring stage: a run-time choice of the host for narrow rows, the constant 1 (folded away) for 16 KB tiles
+  const int SUB = C::TILE_BYTES >= 16384 ? 1 : P.sub;
+  const size_t STAGE_BYTES = (size_t)SUB * C::TILE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)ring_stages * STAGE_BYTES);
   uint64_t* empty = full + MAX_STAGES;
   // gen[s] = number of tiles consumed out of stage s so far.  A consumer waits for use u of a stage on
   // full[s] only once gen[s] == u: mbarrier parity can tell neighbouring phases apart, not phases two
@@ -245,7 +250,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   V* xs = reinterpret_cast<V*>(const_cast<unsigned*>(gen) + MAX_STAGES);      // [2][CH]
   Shared<T>* sh = reinterpret_cast<Shared<T>*>(xs + 2 * CH);
 
-  const ProblemDev& P = probs[blockIdx.x / ncta_pp];
   const int cta = blockIdx.x % ncta_pp;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -259,7 +263,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   const long long row0 = tile0 * C::BR;
   long long row1 = (tile0 + NT) * C::BR;
   if (row1 > P.l) row1 = P.l;
-  const bool resident = (unsigned)NT <= S;
+  const int NM = (NT + SUB - 1) / SUB;            // ring stages' worth of tiles ("macro tiles") in this slice
+  const bool resident = (unsigned)NM <= S;
   const bool nu = GENERIC && P.nu != 0;
   const bool mirror = GENERIC && P.mirror != 0;
   const long long l = P.l;
@@ -291,16 +296,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
 
   // ============================== producer warp ==============================================
   if (warp == NW) {
-    if (NT > 0 && P.kind != K_PRECOMPUTED) {   // a precomputed kernel matrix is only ever read through the cache path
+    if (NM > 0 && P.kind != K_PRECOMPUTED) {   // a precomputed kernel matrix is only ever read through the cache path
       const unsigned char* Xb = reinterpret_cast<const unsigned char*>(P.X) + (size_t)P.row_offset * C::ROWB;
       unsigned long long Tp = 0;
       unsigned stage = 0, par = 0;   // stage = Tp % S, par = (Tp / S) & 1
       int t = 0;                     // Tp % NT
-      auto issue = [&](int tt, unsigned st) {
-        const long long r0 = row0 + (long long)tt * C::BR;
+      auto issue = [&](int tt, unsigned st) {   // macro tile tt -> stage st, one bulk copy
+        const long long r0 = row0 + (long long)tt * SUB * C::BR;
         long long nr = row1 - r0;
-        if (nr > C::BR) nr = C::BR;
-        unsigned char* dst = ring + (size_t)st * C::TILE_BYTES;
+        if (nr > (long long)SUB * C::BR) nr = (long long)SUB * C::BR;
+        unsigned char* dst = ring + (size_t)st * STAGE_BYTES;
         if (lane == 0) {
           const uint32_t bytes = (uint32_t)(nr * C::ROWB);
           mbar_arrive_expect_tx(&full[st], bytes);
@@ -308,8 +313,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         }
       };
       if (resident) {
-        for (int tt = 0; tt < NT; ++tt) issue(tt, (unsigned)tt);
-        Tp = NT;
+        for (int tt = 0; tt < NM; ++tt) issue(tt, (unsigned)tt);
+        Tp = NM;
         if (lane == 0)
           while (!sh->producer_stop) __nanosleep(200);
       } else {
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           if (!go) break;
           issue(t, stage);
           ++Tp;
-          if (++t == NT) t = 0;
+          if (++t == NM) t = 0;
           if (++stage == S) { stage = 0; par ^= 1u; }
         }
       }
@@ -438,7 +443,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       if (mirror) consider(nu, flags[r + l], G[r + l], (int)(r + goff + lg), best);
     }
   }
-  RowState<T> pf = load_row_state(warp);   // first tile of the first sweep (tiles 0..NW-1 are static)
+  RowState<T> pf = load_row_state(warp * SUB);   // first tile of the first sweep (macro tiles 0..NW-1 are static)
 
   for (;;) {
     // ---- (B) warp -> CTA candidate reduce, publish to every GPU, shared polling, global reduce ----------
@@ -520,7 +525,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       int wsrc[NCAND];
       const uint64_t t_start = globaltimer_ns();
       uint32_t rounds = 0;
-      uint32_t seen = 0;   // records whose row has been prefetched already (C variant: bit m*2+kk)
       for (;;) {
         bool all = true;
 #pragma unroll
@@ -557,17 +561,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
                   int& ws = (k0 == 0) ? wsrc[kk] : wsrc[2 + kk];
                   const bool take = kk == 0 ? better_max(g, idx, wk.g, wk.idx) : better_min(g, idx, wk.g, wk.idx);
                   if (take) { wk.g = g; wk.idx = idx; wk.flags = (int)(hh.w & 7u); ws = sidx; }
-                  // a candidate from another GPU's slice is never swept here: pull its row towards L2 now, so
-                  // the leader's fetch of the winning rows does not pay an HBM miss after the exchange
-                  if (world > 1 && cta == 0 && idx >= 0 && !((seen >> (k0 * 4 + m * 2 + kk)) & 1u) && P.kind != K_PRECOMPUTED) {
-                    const long long grow = (mirror && idx >= lg) ? idx - lg : idx;
-                    if (grow < goff || grow >= goff + l) {
-                      const char* rowp = reinterpret_cast<const char*>(P.X) + (size_t)grow * C::ROWB;
-#pragma unroll
-                      for (int b = 0; b < C::ROWB; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + b));
-                    }
-                    seen |= 1u << (k0 * 4 + m * 2 + kk);
-                  }
                 }
               }
             }
@@ -592,6 +585,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           const unsigned holders = __ballot_sync(0xffffffffu, w[k].idx >= 0 && mine == w[k].idx);
           const int from = holders ? __ffs(holders) - 1 : 0;
           wsrc[k] = __shfl_sync(0xffffffffu, wsrc[k], from);
+        }
+      }
+      // a winner from another GPU's slice is never swept here: CTA 0 pulls the rows of its warp winners towards
+      // L2 now, so the leaders' fetch of the pair's rows does not pay an HBM miss after the exchange
+      if (world > 1 && cta == 0 && P.kind != K_PRECOMPUTED) {
+#pragma unroll
+        for (int k = 0; k < NCAND; ++k) {
+          if (k < ntypes && w[k].idx >= 0) {
+            const long long grow = (mirror && w[k].idx >= lg) ? w[k].idx - lg : w[k].idx;
+            if ((grow < goff || grow >= goff + l) && lane * 128 < C::ROWB)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(P.X) + (size_t)grow * C::ROWB + lane * 128));
+          }
         }
       }
       if (lane == 0) {
@@ -843,8 +848,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       __threadfence();
     }
     if (warm) {   // the first tile's state was prefetched before this sweep's plan was known
-      const long long r0w = row0 + (long long)warp * C::BR + rib;
-      if (warp < NT && lane_active && r0w < row1) { pf.ki = col_i[r0w]; pf.kj = col_j[r0w]; }
+      const long long r0w = row0 + (long long)warp * SUB * C::BR + rib;
+      if (warp < NM && lane_active && r0w < row1) { pf.ki = col_i[r0w]; pf.kj = col_j[r0w]; }
     }
 #ifdef B2SVM_TIMELINE
     long long cta_sweep_start = 0;
@@ -854,18 +859,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     long long dbg_wait = 0;
     int dbg_tiles = 0;
 #endif
-    int t = warp;                       // first tile is static (its gradient state is already in pf)
-    while (t < NT) {
-      // draw the next tile now so its gradient state can be prefetched a full tile of work ahead
-      int tn = 0;
-      if (P.debug_flags & 1) {
-        tn = t + NW;
-      } else {
-        if (lane == 0) tn = atomicAdd(&sh->ticket, 1);
-        tn = __shfl_sync(0xffffffffu, tn, 0);
+    int m = warp, sub = 0;              // macro tile (first one static: its gradient state is already in pf), tile in it
+    while (m < NM) {
+      const int t = m * SUB + sub;
+      // next tile: the following one of this macro tile, else draw a new macro tile -- now, so that its
+      // gradient state can be prefetched a full tile of work ahead
+      int mn = m, subn = sub + 1;
+      if (subn == SUB || t + 1 >= NT) {
+        subn = 0;
+        if (P.debug_flags & 1) {
+          mn = m + NW;
+        } else {
+          if (lane == 0) mn = atomicAdd(&sh->ticket, 1);
+          mn = __shfl_sync(0xffffffffu, mn, 0);
+        }
       }
       const RowState<T> cur = pf;
-      pf = load_row_state(tn);
+      pf = load_row_state(mn * SUB + subn);
 
       const long long row = row0 + (long long)t * C::BR + rib;
       const bool valid = lane_active && row < row1;
@@ -873,9 +883,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       if (!warm) {
         unsigned stage, use = 0u;
         if (resident) {
-          stage = (unsigned)t;
+          stage = (unsigned)m;
         } else {
-          const unsigned q = tb_mod + (unsigned)t;
+          const unsigned q = tb_mod + (unsigned)m;
           stage = q % S;
           use = tb_div + q / S;
         }
@@ -886,7 +896,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           uint32_t spins = 0;
           uint64_t t_wait = 0;
           bool ok = false;
-          while (!ok) {
+          while (!ok && sub == 0) {   // the later tiles of a macro tile arrived with its first
             ok = (resident || gen[stage] == use) && mbar_try_wait(&full[stage], use & 1u);
             if (!ok && (++spins & 1023u) == 0) {
               if (*(volatile int*)P.abort_flag) break;
@@ -899,7 +909,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
 #ifdef B2SVM_TIMELINE
         if (dbg) { dbg_wait += clock64() - dbg_w0; ++dbg_tiles; }
 #endif
-        const unsigned char* base = ring + (size_t)stage * C::TILE_BYTES + (size_t)grp * C::RPL * C::ROWB + lig * 16;
+        const unsigned char* base = ring + (size_t)stage * STAGE_BYTES + (size_t)sub * C::TILE_BYTES + (size_t)grp * C::RPL * C::ROWB + lig * 16;
         T acc[C::NV];
 #pragma unroll
         for (int k = 0; k < C::NV; ++k) acc[k] = 0;
@@ -922,7 +932,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           dtj = (lig & 1) ? acc[0] : o;
         }
         __syncwarp();
-        if (!resident && lane == 0) {
+        if (!resident && lane == 0 && subn == 0) {   // leaving this macro tile: hand the stage back
           gen[stage] = use + 1u;
           mbar_arrive(&empty[stage]);
         }
@@ -954,7 +964,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           consider(nu, f, g, v, best);
         }
       }
-      t = tn;
+      m = mn;
+      sub = subn;
     }
 #ifdef B2SVM_TIMELINE
     if (cta_sweep_start) cta_sweep_start_prev = cta_sweep_start;
@@ -964,10 +975,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     }
 #endif
     sweep_warm = false;
-    pf = load_row_state(warp);   // first tile of the next sweep (after this thread's own stores to it)
+    pf = load_row_state(warp * SUB);   // first tile of the next sweep (after this thread's own stores to it)
     if (!warm) {
       if (!resident) {
-        const unsigned q = tb_mod + (unsigned)NT;
+        const unsigned q = tb_mod + (unsigned)NM;
         tb_mod = q % S;
         tb_div = tb_div + q / S;
       }
@@ -977,7 +988,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
 
   // ---- exit: tell the producer how far the consumers got, let it drain --------------------------
   if (threadIdx.x == 0) {
-    sh->consumed = cold * (long long)NT;
+    sh->consumed = cold * (long long)NM;
     __threadfence_block();
     sh->producer_stop = 1;
   }

@@ -570,3 +570,27 @@ def test_decision_function_is_the_same_on_both_matvec_paths(monkeypatch, breast_
     b = np.asarray(est.decision_function(X))
     np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
     assert (np.sign(a) == np.sign(b)).all()
+
+
+# ------------------------------------------------------------------------------ narrow rows: several tiles per ring stage
+@pytest.mark.parametrize("n,d,dtype,max_ctas", [(20011, 32, np.float32, 2), (20011, 32, np.float32, 148),
+                                                (9000, 10, np.float32, 1), (7001, 16, np.float64, 3),
+                                                (5000, 50, np.float32, 2)])
+def test_macro_tiles_are_bit_identical(monkeypatch, n, d, dtype, max_ctas):
+    """Grouping 2-8 tiles of narrow rows into one ring stage (one bulk copy, one ticket) changes how X travels,
+    not what is computed: 400 iterations give bit-identical alpha / gradient with and without grouping, with the
+    slice resident in shared memory (many CTAs) and streamed through the ring (few CTAs)."""
+    torch, _, S, *_ = _mods()
+    X, y01 = O.synth_classification(n=n, d=d, seed=3)
+    X = X.astype(dtype)
+    y = np.where(y01 == 1, 1.0, -1.0)
+    monkeypatch.setenv("B2SVM_MAX_CTAS", str(max_ctas))
+    out = []
+    for sub in ("1", "2", "8"):
+        monkeypatch.setenv("B2SVM_SUB", sub)
+        sol = S.SolverWithCache(-np.ones(n), y, 1.0, func=S.QColumns(X, y, S.KernelSpec("rbf", 1.0 / d), cache_bytes=0))
+        st = sol.solve(400)
+        assert st.n_iter == 400
+        out.append((sol.alpha.cpu().numpy().copy(), sol.neg_y_grad.cpu().numpy().copy()))
+    for a, g in out[1:]:
+        assert np.array_equal(a, out[0][0]) and np.array_equal(g, out[0][1])
