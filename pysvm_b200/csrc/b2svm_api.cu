@@ -235,7 +235,7 @@ struct b2svm_handle {
   double* p_dev = nullptr;      // staging for host-side p
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 0;
-  int ncta = 1, tiles_per_cta = 1, stages = 2, sub = 1, stages1 = 2;
+  int ncta = 1, tiles_per_cta = 1, stages = 2, sub = 1, stages1 = 2, tile_bytes = 0;
   size_t smem_bytes1 = 0;
   long long ntiles = 0;
   size_t smem_bytes = 0;
@@ -268,7 +268,7 @@ template <typename T, int CH>
 struct Geometry {
   using C = Cfg<T, CH>;
   static size_t smem_for(int stages, int sub) {
-    return (size_t)stages * sub * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + MAX_STAGES * sizeof(unsigned) +
+    return PROBLEM_SMEM_BYTES + (size_t)stages * sub * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + MAX_STAGES * sizeof(unsigned) +
            2 * (size_t)C::ROWB +
            sizeof(Shared<T>) + 128;
   }
@@ -304,6 +304,7 @@ int plan_T(b2svm_handle* h) {
   while (sub * 2 <= max_sub && plan_tiles >= (long long)max_ctas * NW * (sub * 2) * 2) sub *= 2;
   if (const char* e = getenv("B2SVM_SUB")) sub = std::max(1, std::min(max_sub, atoi(e)));
   h->sub = sub;
+  h->tile_bytes = C::TILE_BYTES;
   int stages = 2;
   geometry(sub, stages, h->smem_bytes);
   h->stages = stages;
@@ -363,7 +364,19 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.ncta = h->ncta;
   P.tiles_per_cta = h->tiles_per_cta;
   P.sub = h->sub;
-  P.ntiles = h->ntiles;
+  // L2 residency plan.  Every sweep re-reads the same X; the first 48 MB of it (the same leading macro tiles of every
+  // CTA's slice) are fetched with an evict_last hint and stay in the 126 MB L2 across sweeps, the rest streams through
+  // with evict_first.  Measured at C3: DRAM reads 83 -> 40 MB / iteration, 19.9 -> 18.7 us (flat between 40 and 72 MB).
+  // B2SVM_L2_PIN_MB overrides the size (0 = no hints), B2SVM_L2_PIN_SKIP the first pinned macro tile.
+  {
+    double mb = 48.0;
+    if (const char* e = getenv("B2SVM_L2_PIN_MB")) mb = atof(e);
+    const long long per_cta = (long long)(mb * 1048576.0 / ((double)h->ncta * h->tile_bytes * h->sub));
+    const int skip = getenv("B2SVM_L2_PIN_SKIP") ? atoi(getenv("B2SVM_L2_PIN_SKIP")) : 0;
+    P.pin_lo = skip;
+    P.pin_hi = skip + (int)std::min<long long>(per_cta, 1 << 30);
+    if (mb <= 0) P.pin_lo = P.pin_hi = 0;
+  }
   P.abort_flag = h->abort_flag;
   P.result = h->result;
   P.max_iter = max_iter;

@@ -68,6 +68,7 @@ struct ProblemDev {
   double gamma, coef0, degree;
   int ncta;             // CTAs cooperating on this problem
   int tiles_per_cta;
+  int pin_lo, pin_hi;   // macro tiles [pin_lo, pin_hi) of every CTA's slice are fetched with L2 evict_last, the rest evict_first
   int sub;              // 32-row tiles per ring stage (narrow rows: several tiles travel in one bulk copy)
   long long ntiles;
   uint4* mbox;          // local mailbox [2][world * ncta][NCAND][2] {record, alpha unit} (zeroed before every launch)
@@ -89,6 +90,7 @@ struct ProblemDev {
   double* dbg_steps;              // optional [DBG_EPOCHS][ncta][6] = si, sj, gi, gj, ai, aj seen by each leader
   int debug_flags;                // B2SVM_DEBUG_FLAGS: 1 = static tile assignment, 2 = L2 loads for G/flags
 };
+constexpr size_t PROBLEM_SMEM_BYTES = (sizeof(ProblemDev) + 127) / 128 * 128;   // descriptor copy in front of the ring
 
 // Tile geometry.  A tile is one contiguous bulk copy of BR rows of CH 16-byte chunks.  LPR lanes share
 // a row (lane p of the group owns chunks p, p+LPR, ...: the 8 lanes of a quarter-warp read 128
@@ -235,9 +237,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   using V = typename C::V;
   constexpr int QL = (CH + 31) / 32;
 
-  extern __shared__ __align__(128) unsigned char smem[];
+  // The problem descriptor is read all along the latency-critical exchange / step chain; in global memory its
+  // lines are evicted from L1 by every sweep and each first touch costs an L2 round trip.  Keep a copy in
+  // shared memory, in front of the ring.
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(probs + blockIdx.x / ncta_pp);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw);
+    for (int k = threadIdx.x; k < (int)(sizeof(ProblemDev) / 4); k += NTHREADS) dst[k] = src[k];
+  }
+  __syncthreads();
+  const ProblemDev& P = *reinterpret_cast<const ProblemDev*>(smem_raw);
+  unsigned char* smem = smem_raw + PROBLEM_SMEM_BYTES;
   unsigned char* ring = smem;
-  const ProblemDev& P = probs[blockIdx.x / ncta_pp];
   // tiles per ring stage: a run-time choice of the host for narrow rows, the constant 1 (folded away) for 16 KB tiles
   const int SUB = C::TILE_BYTES >= 16384 ? 1 : P.sub;
   const size_t STAGE_BYTES = (size_t)SUB * C::TILE_BYTES;
@@ -301,6 +313,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       unsigned long long Tp = 0;
       unsigned stage = 0, par = 0;   // stage = Tp % S, par = (Tp / S) & 1
       int t = 0;                     // Tp % NT
+      // L2 residency plan: the same part of every slice is kept (evict_last) across sweeps, the rest streams through
+      const int pin_lo = P.pin_lo, pin_hi = P.pin_hi;
+      const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
       auto issue = [&](int tt, unsigned st) {   // macro tile tt -> stage st, one bulk copy
         const long long r0 = row0 + (long long)tt * SUB * C::BR;
         long long nr = row1 - r0;
@@ -309,7 +324,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         if (lane == 0) {
           const uint32_t bytes = (uint32_t)(nr * C::ROWB);
           mbar_arrive_expect_tx(&full[st], bytes);
-          bulk_g2s(dst, Xb + r0 * C::ROWB, bytes, &full[st]);
+          if (pin_hi > pin_lo) bulk_g2s_hint(dst, Xb + r0 * C::ROWB, bytes, &full[st], (tt >= pin_lo && tt < pin_hi) ? pol_keep : pol_stream);
+          else bulk_g2s(dst, Xb + r0 * C::ROWB, bytes, &full[st]);
         }
       };
       if (resident) {
@@ -506,10 +522,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       if (lane == 0) sh->ticket = NW;   // next sweep: tiles 0..NW-1 are static, the rest are drawn here
       stamp(2);   // published
 #ifdef B2SVM_TIMELINE
-      if (P.timeline && threadIdx.x == 0 && epoch == 11u && cta < 160) {
-        P.timeline[TL_CTA_BASE + 2 * cta] = clock64() - cta_sweep_start_prev;
-        P.timeline[TL_CTA_BASE + 2 * cta + 1] = NT;
-      }
+      if (P.timeline && threadIdx.x == 0 && (epoch == 11u || epoch == 41u) && cta < 160)   // two sweeps: is a slow CTA always slow?
+        P.timeline[TL_CTA_BASE + 2 * cta + (epoch == 41u)] = clock64() - cta_sweep_start_prev;
 #endif
     }
 
@@ -853,7 +867,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     }
 #ifdef B2SVM_TIMELINE
     long long cta_sweep_start = 0;
-    if (P.timeline && threadIdx.x == 0 && epoch == 10u) cta_sweep_start = clock64() + (long long)(ci == 123.456);
+    if (P.timeline && threadIdx.x == 0 && (epoch == 10u || epoch == 40u)) cta_sweep_start = clock64() + (long long)(ci == 123.456);
     const bool dbg = P.timeline && cta == 0 && epoch == 10u;
     const long long dbg_start = dbg ? clock64() : 0;
     long long dbg_wait = 0;

@@ -56,12 +56,12 @@ class _Fitted:
         dev = self.func.device
         if self.rff is not None:
             # K(a, b) = z(a).z(b)  =>  coef.K(X, x) = z(x).(Z^T coef)
-            Xq = to_device_matrix(np.array(x), dev).to(self.X_raw.dtype)
+            Xq = to_device_matrix(x if isinstance(x, torch.Tensor) else np.asarray(x), dev).to(self.X_raw.dtype)
             if self._wz is None:
                 self._wz = self.Z.t().contiguous() @ self.coef
             w, b = self.rff._device_params(dev)
             return rff_decision_device(Xq, w, b, self._wz).cpu().numpy()
-        Xq = to_device_matrix(np.array(x), dev).to(self.func.X.dtype)
+        Xq = to_device_matrix(x if isinstance(x, torch.Tensor) else np.asarray(x), dev).to(self.func.X.dtype)
         return kernel_matvec(self.spec, self.func.X, self.coef, Xq).cpu().numpy()
 
 

@@ -15,8 +15,9 @@ def run(n, d, iters, dtype=np.float32):
     yv = np.where(ys == 1, 1.0, -1.0)
     func = S.QColumns(Xs, yv, S.KernelSpec("rbf", 1 / (d * Xs.std())), cache_bytes=int(os.environ.get("CACHE_BYTES", "0")))
     sol = S.SolverWithCache(-np.ones(n), yv, 1.0, func=func)
-    sol.solve(iters)
+    sol.solve(int(os.environ.get("FIRST_ITERS", iters)))   # e.g. enough iterations to fill the column cache
     st = sol.solve(iters)
+    print(f"   timed solve: {st.n_iter} it, cold sweeps {st.cold_sweeps}, warm {st.cache_hits // 2}")
     lib = N.load()
     NT_ALL = 64 * 8 + 64 + 320
     buf = (C.c_longlong * NT_ALL)()
@@ -26,9 +27,14 @@ def run(n, d, iters, dtype=np.float32):
     t = allb[:512].reshape(64, 8)
     wt = allb[512:576].reshape(16, 4)
     ct = allb[576:].reshape(160, 2)[:st.n_ctas]
-    print('   per-CTA sweep cycles (epoch 10): min %d median %d p90 %d max %d; tiles min %d max %d' % (ct[:,0].min(), np.median(ct[:,0]), np.percentile(ct[:,0], 90), ct[:,0].max(), ct[:,1].min(), ct[:,1].max()))
-    order = np.argsort(ct[:,0])
-    print('   slowest CTAs:', [(int(c), int(ct[c,0])) for c in order[-8:]], 'fastest:', [(int(c), int(ct[c,0])) for c in order[:5]])
+    for e in (0, 1):
+        c = ct[:, e]
+        print('   per-CTA sweep cycles (epoch %d): min %d median %d p90 %d max %d' % (10 + 30 * e, c.min(), np.median(c), np.percentile(c, 90), c.max()))
+    order = np.argsort(ct[:, 0])
+    print('   slowest CTAs at epoch 10:', [(int(c), int(ct[c, 0]), int(ct[c, 1])) for c in order[-10:]])
+    print('   fastest CTAs at epoch 10:', [(int(c), int(ct[c, 0]), int(ct[c, 1])) for c in order[:6]])
+    print('   correlation of per-CTA sweep time between the two epochs: %.3f' % np.corrcoef(ct[:, 0], ct[:, 1])[0, 1])
+    print('   sweep time by CTA index block of 16 (epoch 10 / 40):', [(int(ct[b:b+16, 0].mean()), int(ct[b:b+16, 1].mean())) for b in range(0, st.n_ctas, 16)])
     k = min(iters, 60)
     seg = t[2:k]      # skip first epochs
     names = ["join(0->1)", "publish(1->2)", "poll+read(2->3)", "reduce(3->4)", "step(4->5)", "bar(5->6)", "sweep(6->next0)"]
