@@ -364,6 +364,7 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.ncta = h->ncta;
   P.tiles_per_cta = h->tiles_per_cta;
   P.sub = h->sub;
+  P.ntiles = h->ntiles;
   // L2 residency plan.  Every sweep re-reads the same X; the first 48 MB of it (the same leading macro tiles of every
   // CTA's slice) are fetched with an evict_last hint and stay in the 126 MB L2 across sweeps, the rest streams through
   // with evict_first.  Measured at C3: DRAM reads 83 -> 40 MB / iteration, 19.9 -> 18.7 us (flat between 40 and 72 MB).
