@@ -146,7 +146,8 @@ struct Shared {
   int ticket;           // next dynamically assigned tile of the current sweep
   uint4* peer[8];       // mailbox of every rank (copied once from global memory)
   volatile int status;  // a warp's watchdog tripped
-  WCand wc[NW][NCAND];  // per-warp candidates of the sweep (with their alpha)
+  WCand wc[NW][NCAND];  // per-warp candidates of the sweep
+  uint4 wa[NW][NCAND];  // ... their alpha, {lo, hi, epoch, 0}: written when the load lands, after the CTA join
   WCand cw[NCAND];      // this CTA's winners
   WCand ws[NW][NCAND];  // per-warp winners of the polled records (alpha field unused, flags = source slot)
   int wsrc[NW][NCAND];  // ... and the mailbox source (rank * ncta + cta) they came from
@@ -470,22 +471,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     for (int k = 0; k < NCAND; ++k)
       if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, best[k]);
     __syncwarp();
+    // one lane per type also fetches the candidate's alpha (a row of this warp: same-SM coherent).  The load is
+    // only issued here: its value is parked in shared memory after the CTA join and travels in a separate 16-byte
+    // unit, so neither the join nor the candidate record waits for it (the leaders need it at step time only).
+    double cand_alpha = 0.0;
     if (lane < ntypes) {
-      // one lane per type attaches the candidate's alpha (a row of this warp: same-SM coherent); the load's
-      // latency hides behind the CTA join
       Cand m = best[0];
 #pragma unroll
       for (int k = 1; k < NCAND; ++k)
         if (lane == k) m = best[k];
+      if (m.idx >= 0) cand_alpha = alpha[local_var(m.idx)];
       WCand wv;
       wv.g = m.g;
       wv.idx = m.idx;
       wv.flags = m.flags;
-      wv.alpha = m.idx >= 0 ? alpha[local_var(m.idx)] : 0.0;
+      wv.alpha = 0.0;
       sh->wc[warp][lane] = wv;
     }
     named_bar_sync(1, NW * 32);
     stamp(1);   // all warps of this CTA done
+    auto park_alpha = [&]() {
+      if (lane < ntypes)
+        st_volatile_shared_v4(&sh->wa[warp][lane],
+                              make_uint4((uint32_t)__double2loint(cand_alpha), (uint32_t)__double2hiint(cand_alpha), epoch, 0u));
+    };
+    if (warp != 0) park_alpha();
 
     if (warp == 0) {
       // CTA-level winner per type (two types per pass, 16 lanes each) ...
@@ -500,27 +510,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         redux_select(half, (k & 1) == 0, m);
         const unsigned holders = __ballot_sync(half, m.idx >= 0 && mw.idx == m.idx) & half;
         const int from = holders ? __ffs(holders) - 1 : (lane & 16);
-        const double wa = __shfl_sync(half, mw.alpha, from);
         if (src == 0) {
           WCand c;
-          c.g = m.g; c.alpha = wa; c.idx = m.idx; c.flags = m.flags;
+          c.g = m.g; c.alpha = 0.0; c.idx = m.idx; c.flags = (m.flags & 7) | ((from & 15) << 8);   // + the warp it came from
           sh->cw[k] = c;
         }
       }
       __syncwarp();
-      // ... pushed into the mailbox of every GPU: one lane per (rank, type), two 16-byte stores each
+      // ... pushed into the mailbox of every GPU: one lane per (rank, type), the record first ...
+      const int pr = lane / ntypes, pk = lane - pr * ntypes;
+      uint4* rp = nullptr;
+      int from_warp = 0;
       if (lane < world * ntypes) {
-        const int r = lane / ntypes, k = lane - r * ntypes;
-        const WCand c = sh->cw[k];
-        uint4* rp = sh->peer[r] + ((((size_t)par * world + P.rank) * ncta + cta) * NCAND + k) * 2;
+        const WCand c = sh->cw[pk];
+        from_warp = c.flags >> 8;
+        rp = sh->peer[pr] + ((((size_t)par * world + P.rank) * ncta + cta) * NCAND + pk) * 2;
         const uint4 rec = make_uint4((uint32_t)__double2loint(c.g), (uint32_t)__double2hiint(c.g), (uint32_t)c.idx,
-                                     (epoch << 3) | (uint32_t)c.flags);
-        const uint4 au = make_uint4((uint32_t)__double2loint(c.alpha), (uint32_t)__double2hiint(c.alpha), 0u, epoch);
-        if (world == 1) { st_relaxed_v4(rp, rec); st_relaxed_v4(rp + 1, au); }
-        else { st_relaxed_sys_v4(rp, rec); st_relaxed_sys_v4(rp + 1, au); }
+                                     (epoch << 3) | (uint32_t)(c.flags & 7));
+        if (world == 1) st_relaxed_v4(rp, rec);
+        else st_relaxed_sys_v4(rp, rec);
       }
       if (lane == 0) sh->ticket = NW;   // next sweep: tiles 0..NW-1 are static, the rest are drawn here
       stamp(2);   // published
+      // ... then the winner's alpha, as soon as the warp that owns it has parked it
+      park_alpha();
+      __syncwarp();
+      if (lane < world * ntypes) {
+        uint4 u = ld_volatile_shared_v4(&sh->wa[from_warp][pk]);
+        while (u.z != epoch) u = ld_volatile_shared_v4(&sh->wa[from_warp][pk]);
+        const uint4 au = make_uint4(u.x, u.y, 0u, epoch);
+        if (world == 1) st_relaxed_v4(rp + 1, au);
+        else st_relaxed_sys_v4(rp + 1, au);
+      }
 #ifdef B2SVM_TIMELINE
       if (P.timeline && threadIdx.x == 0 && (epoch == 11u || epoch == 41u) && cta < 160)   // two sweeps: is a slow CTA always slow?
         P.timeline[TL_CTA_BASE + 2 * cta + (epoch == 41u)] = clock64() - cta_sweep_start_prev;
@@ -601,14 +622,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           wsrc[k] = __shfl_sync(0xffffffffu, wsrc[k], from);
         }
       }
-      // a winner from another GPU's slice is never swept here: CTA 0 pulls the rows of its warp winners towards
-      // L2 now, so the leaders' fetch of the pair's rows does not pay an HBM miss after the exchange
-      if (world > 1 && cta == 0 && P.kind != K_PRECOMPUTED) {
+      // CTA 0 pulls the rows of its warp winners towards L2 now (a row of another GPU's slice is never swept here,
+      // a local one may have been streamed out): the leaders' fetch of the pair's rows after the exchange then hits
+      if (cta == 0 && P.kind != K_PRECOMPUTED) {
 #pragma unroll
         for (int k = 0; k < NCAND; ++k) {
           if (k < ntypes && w[k].idx >= 0) {
             const long long grow = (mirror && w[k].idx >= lg) ? w[k].idx - lg : w[k].idx;
-            if ((grow < goff || grow >= goff + l) && lane * 128 < C::ROWB)
+            if (lane * 128 < C::ROWB)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(P.X) + (size_t)grow * C::ROWB + lane * 128));
           }
         }
