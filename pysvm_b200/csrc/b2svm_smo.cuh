@@ -38,7 +38,7 @@ constexpr int NTHREADS = (NW + 1) * 32;    // + one producer warp
 constexpr int MAX_STAGES = 64;
 constexpr int NCAND = 4;                   // up/low (C variant) or up+/low+/up-/low- (nu variant)
 constexpr int REC_STRIDE = 1;              // one 128-byte line per record (uint4 units): spreads the polling over L2 slices
-constexpr int TL_ITERS = 64, TL_SLOTS = 8; // debug timeline
+constexpr int TL_ITERS = 64, TL_SLOTS = 16; // debug timeline
 constexpr int DBG_EPOCHS = 2048;
 constexpr int TL_WARP_SLOTS = 4;           // + per-warp {start, end, tiles, wait} of one sweep
 constexpr int TL_CTA_BASE = TL_ITERS * TL_SLOTS + 16 * TL_WARP_SLOTS;   // + per-CTA {sweep cycles, tiles} of one sweep
@@ -498,25 +498,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     if (warp != 0) park_alpha();
 
     if (warp == 0) {
-      // CTA-level winner per type (two types per pass, 16 lanes each) ...
-      for (int k0 = 0; k0 < ntypes; k0 += 2) {
-        const int k = k0 + (lane >> 4), src = lane & 15;
-        const unsigned half = lane < 16 ? 0x0000ffffu : 0xffff0000u;
+      // CTA-level winner per type.  Full-warp collectives only: with two half-warp masks in one instruction the
+      // compiler falls back to a MATCH.ANY / WARPSYNC.EXCLUSIVE emulation that costs ~1000 cycles on this path.
+      for (int k = 0; k < ntypes; ++k) {
         WCand mw;
         mw.g = 0.0; mw.alpha = 0.0; mw.idx = -1; mw.flags = 0;
-        if (src < NW) mw = sh->wc[src][k];
+        if (lane < NW) mw = sh->wc[lane][k];
         Cand m;
         m.g = mw.g; m.idx = mw.idx; m.flags = mw.flags;
-        redux_select(half, (k & 1) == 0, m);
-        const unsigned holders = __ballot_sync(half, m.idx >= 0 && mw.idx == m.idx) & half;
-        const int from = holders ? __ffs(holders) - 1 : (lane & 16);
-        if (src == 0) {
+        redux_select(0xffffffffu, (k & 1) == 0, m);
+        const unsigned holders = __ballot_sync(0xffffffffu, m.idx >= 0 && mw.idx == m.idx);
+        const int from = holders ? __ffs(holders) - 1 : 0;
+        if (lane == 0) {
           WCand c;
-          c.g = m.g; c.alpha = 0.0; c.idx = m.idx; c.flags = (m.flags & 7) | ((from & 15) << 8);   // + the warp it came from
+          c.g = m.g; c.alpha = 0.0; c.idx = m.idx; c.flags = (m.flags & 7) | (from << 8);   // + the warp it came from
           sh->cw[k] = c;
         }
       }
       __syncwarp();
+      stamp(7);   // CTA winners known
       // ... pushed into the mailbox of every GPU: one lane per (rank, type), the record first ...
       const int pr = lane / ntypes, pk = lane - pr * ntypes;
       uint4* rp = nullptr;
@@ -656,28 +656,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       int wsrc[NCAND];
 #pragma unroll
       for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; wsrc[k] = 0; }
-      for (int k0 = 0; k0 < ntypes; k0 += 2) {
-        const int k = k0 + (lane >> 4), src = lane & 15;
-        const unsigned half = lane < 16 ? 0x0000ffffu : 0xffff0000u;
+      for (int k = 0; k < ntypes; ++k) {   // full-warp collectives, one type at a time (see the CTA-level reduce)
         Cand m;
         m.g = 0.0; m.idx = -1; m.flags = 0;
         int msrc = 0;
-        if (src < NW) {
-          const WCand c = sh->ws[src][k];
+        if (lane < NW) {
+          const WCand c = sh->ws[lane][k];
           m.g = c.g; m.idx = c.idx; m.flags = c.flags;
-          msrc = sh->wsrc[src][k];
+          msrc = sh->wsrc[lane][k];
         }
         const int mine = m.idx;
-        redux_select(half, (k & 1) == 0, m);
-        const unsigned holders = __ballot_sync(half, m.idx >= 0 && mine == m.idx) & half;
-        const int from = holders ? __ffs(holders) - 1 : (lane & 16);
-        msrc = __shfl_sync(half, msrc, from);
-        // hand both halves' results to every lane
-        const Cand lo = {__shfl_sync(0xffffffffu, m.g, 0), __shfl_sync(0xffffffffu, m.idx, 0), __shfl_sync(0xffffffffu, m.flags, 0)};
-        const Cand hi = {__shfl_sync(0xffffffffu, m.g, 16), __shfl_sync(0xffffffffu, m.idx, 16), __shfl_sync(0xffffffffu, m.flags, 16)};
-        const int slo = __shfl_sync(0xffffffffu, msrc, 0), shi = __shfl_sync(0xffffffffu, msrc, 16);
-        if (k0 == 0) { w[0] = lo; w[1] = hi; wsrc[0] = slo; wsrc[1] = shi; }
-        else { w[2] = lo; w[3] = hi; wsrc[2] = slo; wsrc[3] = shi; }
+        redux_select(0xffffffffu, (k & 1) == 0, m);
+        const unsigned holders = __ballot_sync(0xffffffffu, m.idx >= 0 && mine == m.idx);
+        const int from = holders ? __ffs(holders) - 1 : 0;
+        msrc = __shfl_sync(0xffffffffu, msrc, from);
+#pragma unroll
+        for (int q = 0; q < NCAND; ++q)
+          if (q == k) { w[q] = m; wsrc[q] = msrc; }
       }
       // alpha of a winner: the 16-byte unit its CTA pushed next to the record (polled until it carries the epoch)
       const uint4* abase = P.mbox + (size_t)par * world * ncta * NCAND * 2;
@@ -800,11 +795,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         const int gri = (int)((mirror && si >= lg) ? si - lg : si), grj = (int)((mirror && sj >= lg) ? sj - lg : sj);
         int raw_si = -1, raw_sj = -1;
         if (CACHE && P.cache_slots > 0) { raw_si = __ldcg(P.slot_of + gri); raw_sj = __ldcg(P.slot_of + grj); }
+        stamp(8);
         if (!have_k) pair_k(si, sj, xi, xj, ni, nj, Kii, Kjj, Kij);
+        stamp(9);
         if (from_records) { ai = settle_alpha(ua, ti); aj = settle_alpha(ub, tj); }
+        stamp(10);
         const double yi = (fi & F_YPOS) ? 1.0 : -1.0;
         const double yj = (fj & F_YPOS) ? 1.0 : -1.0;
         const StepOut so = smo_step(nu, (double)Kii, (double)Kjj, (double)Kij, yi, yj, gi, gj, ai, aj, Cbox);
+        stamp(11);
         // ---- Q-column cache: which of the two columns are already resident, which get stored now --------
         int slot_i = -1, slot_j = -1, store_i = 0, store_j = 0;
         if (CACHE && P.cache_slots > 0) {

@@ -19,14 +19,14 @@ def run(n, d, iters, dtype=np.float32):
     st = sol.solve(iters)
     print(f"   timed solve: {st.n_iter} it, cold sweeps {st.cold_sweeps}, warm {st.cache_hits // 2}")
     lib = N.load()
-    NT_ALL = 64 * 8 + 64 + 320
+    NT_ALL = 64 * 16 + 64 + 320
     buf = (C.c_longlong * NT_ALL)()
     lib.b2svm_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     N.check(lib.b2svm_debug_timeline(sol._engine.h, buf, NT_ALL))
     allb = np.array(buf[:], dtype=np.int64)
-    t = allb[:512].reshape(64, 8)
-    wt = allb[512:576].reshape(16, 4)
-    ct = allb[576:].reshape(160, 2)[:st.n_ctas]
+    t = allb[:1024].reshape(64, 16)
+    wt = allb[1024:1088].reshape(16, 4)
+    ct = allb[1088:].reshape(160, 2)[:st.n_ctas]
     for e in (0, 1):
         c = ct[:, e]
         print('   per-CTA sweep cycles (epoch %d): min %d median %d p90 %d max %d' % (10 + 30 * e, c.min(), np.median(c), np.percentile(c, 90), c.max()))
@@ -47,6 +47,10 @@ def run(n, d, iters, dtype=np.float32):
         print(f"   {nm:18s} {np.median(v):9.0f}")
         tot += np.median(v)
     print(f"   total {tot:.0f} cycles -> {tot/us:.0f} cycles/us")
+    fine = [("join->CTA winners (1->7)", seg[:, 7] - seg[:, 1]), ("push record (7->2)", seg[:, 2] - seg[:, 7]), ("decide + issue loads (4->8)", seg[:, 8] - seg[:, 4]),
+            ("rows + pair kernels (8->9)", seg[:, 9] - seg[:, 8]), ("alpha settled (9->10)", seg[:, 10] - seg[:, 9]), ("smo_step (10->11)", seg[:, 11] - seg[:, 10]), ("cache plan + publish (11->5)", seg[:, 5] - seg[:, 11])]
+    for nm, v in fine:
+        print(f"      {nm:30s} {np.median(v):9.0f}")
     base = wt[:11, 0].min()
     print("   per-warp sweep at epoch 10 (start, end rel. cycles; tiles; wait cycles):")
     for w in range(11):
