@@ -182,6 +182,12 @@ int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles /* world * 64 
  * are then local reads and only 16-byte candidate records cross NVLink. */
 int b2svm_prepare(b2svm_handle* h);
 
+/* Host helper of register_kernel (svc.py:212-217): gamma='scale' is 1 / (n_features * X.std()).  Population
+ * standard deviation of n_elements contiguous host values, bit-identical to numpy's X.std() on a C-contiguous
+ * array (same pairwise summation tree, evaluated on several host threads).  *out holds the float32 result
+ * exactly when x_dtype is B2SVM_F32. */
+int b2svm_host_std(const void* x_host, int64_t n_elements, int32_t x_dtype, double* out);
+
 #ifdef __cplusplus
 }
 #endif

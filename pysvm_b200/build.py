@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libb2svm.so")
-SOURCES = ["b2svm_api.cu", "b2svm_dense.cu", "b2svm_matvec_tc.cu", "b2svm_launch_f32_plain.cu", "b2svm_launch_f32_generic.cu",
+SOURCES = ["b2svm_api.cu", "b2svm_dense.cu", "b2svm_matvec_tc.cu", "b2svm_host.cu", "b2svm_launch_f32_plain.cu", "b2svm_launch_f32_generic.cu",
            "b2svm_launch_f64_plain.cu", "b2svm_launch_f64_generic.cu"]
 HEADERS = ["b2svm_device.cuh", "b2svm_smo.cuh", "b2svm_launch.cuh", "b2svm_internal.h", os.path.join("..", "..", "include", "b2svm.h")]
 

@@ -39,6 +39,18 @@ class KernelSpec:
         return N.KernelDesc(N.KERNEL_IDS[self.kind], 0, float(self.gamma), float(self.coef0), float(self.degree))
 
 
+def host_std(X) -> float:
+    """``X.std()`` of the reference's register_kernel (svc.py:212-217), bit-identical to numpy but evaluated
+    on several host threads for large C-contiguous float matrices (``b2svm_host_std``).  Returns a NumPy
+    scalar of X's dtype, so ``1 / (n_features * std)`` rounds exactly as it does in the reference."""
+    X = np.asarray(X)
+    if X.dtype in (np.float32, np.float64) and X.flags.c_contiguous and X.size >= (1 << 20):
+        out = C.c_double()
+        N.check(N.load().b2svm_host_std(X.ctypes.data, X.size, N.F64 if X.dtype == np.float64 else N.F32, C.byref(out)))
+        return X.dtype.type(out.value)
+    return X.std()
+
+
 def default_device() -> torch.device:
     if not torch.cuda.is_available():
         raise RuntimeError("pysvm_b200 needs a CUDA device (B200); there is no CPU fallback")

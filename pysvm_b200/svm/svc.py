@@ -11,7 +11,7 @@ from sklearn.multiclass import OneVsOneClassifier, OneVsRestClassifier
 
 from .._native import B2SVMError
 from ..rff import NormalRFF, rff_decision_device
-from ..solver import (KernelSpec, NuSolverWithCache, QColumns, SolverWithCache, default_device, kernel_matvec,
+from ..solver import (KernelSpec, host_std, NuSolverWithCache, QColumns, SolverWithCache, default_device, kernel_matvec,
                       solve_batched, to_device_matrix)
 
 
@@ -178,7 +178,7 @@ class BiKernelSVC(BiLinearSVC):
 
     def _columns(self, X, y, mirror=False):
         """Device Q-column source for this estimator's kernel (the reference's ``func``)."""
-        spec, rff = self.register_kernel(X.std())
+        spec, rff = self.register_kernel(host_std(X))
         self._Z = None
         if rff is not None:
             Z = rff.transform_device(to_device_matrix(X, default_device()))       # n x D float64, like rff.py:20
@@ -239,7 +239,7 @@ class BiKernelSVC(BiLinearSVC):
     def _fit_sharded(self, X, y, sharded):
         """The same fit, row-sharded over the GPUs of the current process group (sharded.enable())."""
         group = sharded._ENABLED["group"]
-        spec, _ = self.register_kernel(X.std())
+        spec, _ = self.register_kernel(host_std(X))
         solver, shard, stats = sharded.fit_csvc_sharded(X, (y == 1).astype(int), self.C, spec, self.tol,
                                                         self.max_iter, group)
         self._report(stats)

@@ -99,3 +99,25 @@ def test_estimator_signatures_match_reference_defaults():
     from sklearn.base import clone
     est = clone(P.KernelSVC(C=3., multiclass="ovo"))
     assert est.C == 3. and est.multiclass == "ovo"
+
+
+def test_host_std_is_bit_identical_to_numpy():
+    """gamma='scale' = 1 / (n_features * X.std()) (svc.py:212-217): the threaded host helper must reproduce numpy's
+    pairwise float32 / float64 reduction to the last bit, and hand back a scalar of X's dtype."""
+    from pysvm_b200 import _native as N
+    from pysvm_b200.solver import host_std
+    import ctypes as C
+    lib = N.load()
+    rng = np.random.default_rng(7)
+    for shape, dt in [((7, 3), np.float32), ((129, 1), np.float32), ((1000, 37), np.float32), ((4096, 30), np.float64),
+                      ((100001, 13), np.float32), ((70000, 17), np.float32), ((30000, 64), np.float64),
+                      ((2100000, 1), np.float32)]:
+        X = (rng.standard_normal(shape) * 3 + 1).astype(dt)
+        out = C.c_double()
+        N.check(lib.b2svm_host_std(X.ctypes.data, X.size, N.F64 if dt == np.float64 else N.F32, C.byref(out)))
+        assert dt(out.value) == X.std(), (shape, dt)
+        got = host_std(X)
+        assert got == X.std() and type(got) is type(X.std())
+    Xf = np.asfortranarray(rng.standard_normal((1500, 900)).astype(np.float32))       # not C-contiguous: numpy's own path
+    assert host_std(Xf) == Xf.std()
+    assert host_std(Xf[::2]) == Xf[::2].std()
