@@ -16,7 +16,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .solver import KernelSpec, QColumns, SolverWithCache, kernel_matvec, to_device_matrix
+from . import _native as N
+from .solver import KernelSpec, QColumns, SolverWithCache, kernel_matvec, nu_initial_alpha, to_device_matrix
 
 
 @dataclass(frozen=True)
@@ -155,6 +156,44 @@ class ShardedSolver(SolverWithCache):
         return rho_from_partials(combine_bias_partials(parts))
 
 
+def rows_kernel_sum(func: "ShardedColumns", coef_rows: np.ndarray) -> torch.Tensor:
+    """m_t = sum over ALL training rows s of coef_s K(x_s, x_t) for this rank's rows t.  X is replicated on every
+    GPU, so the initial gradient of the nu / one-class variants (solver.py:279-281, oc_svm.py:94-95) needs no
+    communication: every rank evaluates its own slice of K alpha_0 (K7, b2svm_kernel_matvec)."""
+    coef = torch.from_numpy(np.ascontiguousarray(coef_rows, dtype=np.float64)).to(func.device)
+    return kernel_matvec(func.kernel, func.X, coef, func.local_rows())
+
+
+class ShardedNuSolver(ShardedSolver):
+    """``NuSolverWithCache`` (solver.py:422-486) row-sharded: four candidate types cross NVLink per iteration."""
+    _variant = N.SOLVER_NU
+
+    def __init__(self, p_global, y_global, t: float, C, tol, func: ShardedColumns, mirror: bool, group=None):
+        self.t = t
+        self._mirror = mirror
+        self._y_global = np.asarray(y_global, dtype=np.float64)
+        super().__init__(local_vector(np.asarray(p_global, dtype=np.float64), func.shard, mirror), func.y, C, tol, func, group)
+
+    def _init_state(self):
+        # solver.py:269-281: the sequential alpha fill runs over the GLOBAL variable order; this rank keeps its slice.
+        # neg_y_grad = -y (Q alpha0 + p) with (Q alpha0)_t = y_t sum_s y_s alpha0_s K(x_s mod l, x_t mod l)
+        func, shard = self._engine.func, self._engine.func.shard
+        a0 = nu_initial_alpha(self._y_global, self.t)
+        ya = a0 * self._y_global
+        l = shard.n_global
+        coef_rows = ya[:l] + ya[l:] if self._mirror else ya
+        m = rows_kernel_sum(func, coef_rows)
+        if self._mirror:
+            m = torch.cat([m, m])
+        self._alpha.copy_(torch.from_numpy(local_vector(a0, shard, self._mirror)))
+        self._g.copy_(-(m + self.y * self.p))
+        self._state_ready = True
+
+    def calculate_rho_b(self):
+        parts = all_gather_array(self._engine.bias_partials(), self.group)
+        return rho_b_from_partials(combine_bias_partials(parts))
+
+
 _ENABLED = {"on": False, "group": None}
 
 
@@ -221,6 +260,51 @@ def fit_svr_sharded(X: np.ndarray, z: np.ndarray, C: float, eps: float, kernel: 
     shard = plan(l, world, rank)
     func = ShardedColumns(X, local_vector(y, shard, True), kernel, shard, mirror=True)
     solver = ShardedSolver(local_vector(p, shard, True), func.y, C, tol, func, group)
+    stats = solver.solve(max_iter)
+    return solver, shard, stats
+
+
+def fit_oneclass_sharded(X: np.ndarray, nu: float, kernel: KernelSpec, tol: float, max_iter: int, group=None):
+    """Row-sharded OneClassSVM solve (oc_svm.py:59-105): y = +1, p = 0, C = 1, alpha0 per oc_svm.py:76-83 over the
+    global row order, neg_y_grad = -K alpha0."""
+    from .svm.oc_svm import oneclass_initial_alpha
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    l = X.shape[0]
+    shard = plan(l, world, rank)
+    func = ShardedColumns(X, np.ones(shard.n_local), kernel, shard)
+    solver = ShardedSolver(np.zeros(shard.n_local), func.y, 1.0, tol, func, group)
+    a0 = oneclass_initial_alpha(nu, l)
+    solver.alpha = local_vector(a0, shard, False)
+    solver.neg_y_grad = -rows_kernel_sum(func, a0)
+    stats = solver.solve(max_iter)
+    return solver, shard, stats
+
+
+def fit_nusvc_sharded(X: np.ndarray, y01: np.ndarray, nu: float, kernel: KernelSpec, tol: float, max_iter: int, group=None):
+    """Row-sharded BiNuSVC solve (svc.py:405-433): p = 0, C = 1, e'alpha = nu * l."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    y = np.array(y01, dtype=float)
+    y[y != 1] = -1
+    l = X.shape[0]
+    shard = plan(l, world, rank)
+    func = ShardedColumns(X, local_vector(y, shard, False), kernel, shard)
+    solver = ShardedNuSolver(np.zeros(l), y, nu * l, 1.0, tol, func, False, group)
+    stats = solver.solve(max_iter)
+    return solver, shard, stats
+
+
+def fit_nusvr_sharded(X: np.ndarray, z: np.ndarray, C: float, nu: float, kernel: KernelSpec, tol: float, max_iter: int,
+                      group=None):
+    """Row-sharded NuSVR solve (svr.py:256-294): 2l variables, p = [-z, z], e'alpha = C * l * nu."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    l = X.shape[0]
+    y = np.empty(2 * l)
+    y[:l], y[l:] = 1., -1.
+    p = np.empty(2 * l)
+    p[:l], p[l:] = -np.asarray(z, dtype=float), np.asarray(z, dtype=float)
+    shard = plan(l, world, rank)
+    func = ShardedColumns(X, local_vector(y, shard, True), kernel, shard, mirror=True)
+    solver = ShardedNuSolver(p, y, C * l * nu, C, tol, func, True, group)
     stats = solver.solve(max_iter)
     return solver, shard, stats
 

@@ -31,6 +31,9 @@ class OneClassSVM(BiNuSVC):
     def fit(self, X):
         X = np.array(X)
         l, self.n_features = X.shape
+        from .. import sharded
+        if sharded.active() and not self.rff:
+            return self._fit_oneclass_sharded(X, sharded)
         p = np.zeros(l)
         y = np.ones(l)
         func, spec, rff = self._columns(X, y)
@@ -39,6 +42,19 @@ class OneClassSVM(BiNuSVC):
         solver._engine.init_gradient(None)                         # oc_svm.py:94-95: g = -K alpha
         self._report(solver.solve(self.max_iter))
         self._finish(solver, func, spec, rff, X, solver.alpha.clone())
+        self.rho_ = solver.calculate_rho()
+        return self
+
+    def _fit_oneclass_sharded(self, X, sharded):
+        """The same fit, row-sharded over the GPUs of the current process group (sharded.enable())."""
+        from ..solver import host_std
+        group = sharded._ENABLED["group"]
+        spec, _ = self.register_kernel(host_std(X))
+        solver, shard, stats = sharded.fit_oneclass_sharded(X, self.nu, spec, self.tol, self.max_iter, group)
+        self._report(stats)
+        self._fitted = sharded.ShardedFit(solver, shard, solver.alpha.clone(), False, group)
+        self.alpha_ = sharded.gather_variables(solver.alpha.cpu().numpy(), shard, False, group)
+        self.support_ = np.flatnonzero(self.alpha_ > 0)
         self.rho_ = solver.calculate_rho()
         return self
 

@@ -303,6 +303,17 @@ class BiNuSVC(BiKernelSVC):
         X, y = np.array(X), np.array(y, dtype=float)
         y[y != 1] = -1
         l, self.n_features = X.shape
+        from .. import sharded
+        if sharded.active() and not self.rff:
+            group = sharded._ENABLED["group"]
+            spec, _ = self.register_kernel(host_std(X))
+            solver, shard, stats = sharded.fit_nusvc_sharded(X, (y == 1).astype(int), self.nu, spec, self.tol, self.max_iter, group)
+            self._report(stats)
+            self._fitted = sharded.ShardedFit(solver, shard, solver.alpha * solver._engine.func.y, False, group)
+            self.alpha_ = sharded.gather_variables(solver.alpha.cpu().numpy(), shard, False, group)
+            self.support_ = np.flatnonzero(self.alpha_ > 0)
+            self.rho_, self.b_ = solver.calculate_rho_b()
+            return self
         p = np.zeros(l)
         func, spec, rff = self._columns(X, y)
         solver = NuSolverWithCache(p, y, self.nu * l, self.C, func, self.tol, self.cache_size, max_iter_hint=self.max_iter)

@@ -61,6 +61,18 @@ class KernelSVR(BiKernelSVC):
     def fit(self, X, y):
         X, z = np.array(X), np.array(y)
         l, self.n_features = X.shape
+        from .. import sharded
+        if sharded.active() and not self.rff:
+            from ..solver import host_std
+            group = sharded._ENABLED["group"]
+            spec, _ = self.register_kernel(host_std(X))
+            solver, shard, stats = sharded.fit_svr_sharded(X, z, self.C, self.eps, spec, self.tol, self.max_iter, group)
+            self._report(stats)
+            nl = shard.n_local
+            self._fitted = sharded.ShardedFit(solver, shard, solver.alpha[:nl] - solver.alpha[nl:], True, group)
+            self.alpha_ = sharded.gather_variables(solver.alpha.cpu().numpy(), shard, True, group)
+            self.rho_ = solver.calculate_rho()
+            return self
         y, p = _svr_vectors(z, l, self.eps)
         func, spec, rff = self._columns(X, y, mirror=True)
         solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func, max_iter_hint=self.max_iter)
@@ -88,6 +100,18 @@ class NuSVR(KernelSVR):
     def fit(self, X, y):
         X, z = np.array(X), np.array(y)
         l, self.n_features = X.shape
+        from .. import sharded
+        if sharded.active() and not self.rff:
+            from ..solver import host_std
+            group = sharded._ENABLED["group"]
+            spec, _ = self.register_kernel(host_std(X))
+            solver, shard, stats = sharded.fit_nusvr_sharded(X, z, self.C, self.nu, spec, self.tol, self.max_iter, group)
+            self._report(stats)
+            nl = shard.n_local
+            self._fitted = sharded.ShardedFit(solver, shard, solver.alpha[:nl] - solver.alpha[nl:], True, group)
+            self.alpha_ = sharded.gather_variables(solver.alpha.cpu().numpy(), shard, True, group)
+            self.rho_, self.b_ = solver.calculate_rho_b()
+            return self
         y = np.empty(2 * l)
         y[:l], y[l:] = 1, -1
         p = np.empty(2 * l)

@@ -48,4 +48,51 @@ if rank == 0:
     assert np.array_equal(a_all, ref.alpha_), float(np.abs(a_all - ref.alpha_).max())
     print("sharded worker ok: world", world, "csvc iters", est.n_iter_, flush=True)
 dist.barrier()
+
+# ---- nu variants and one-class: four candidate types per iteration, initial gradient from the replicated X --------
+# (the single-GPU and the sharded initial mat-vec split their float64 sums differently, so the start gradients agree
+#  to ~1e-15 rather than bit for bit: solutions are compared within 1e-7, iteration counts within 1 %)
+import contextlib, io
+from pysvm_b200.svm.svc import BiNuSVC
+from pysvm_b200.svm.svr import NuSVR
+from pysvm_b200.svm.oc_svm import OneClassSVM
+
+
+def quiet(f):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return f()
+
+
+Xo = O.synth_oneclass(n=5000, d=32, seed=1)
+SH.enable()
+oc = quiet(lambda: OneClassSVM(max_iter=10 ** 6).fit(Xo))
+oc_dec = oc.decision_function(Xo[:200])
+Xn, yn = O.synth_classification(n=4000, d=20, seed=2)
+nus = quiet(lambda: BiNuSVC(max_iter=4000).fit(Xn, yn))
+nus_dec = nus.decision_function(Xn[:200])
+nur = quiet(lambda: NuSVR(max_iter=3000).fit(Xr, z))
+nur_dec = nur.decision_function(Xr[:200])
+ksr = quiet(lambda: KernelSVR(max_iter=3000).fit(Xr, z))
+ksr_dec = ksr.decision_function(Xr[:200])
+SH.disable()
+if rank == 0:
+    ref = quiet(lambda: OneClassSVM(max_iter=10 ** 6).fit(Xo))
+    assert abs(oc.n_iter_ - ref.n_iter_) <= max(1, 0.01 * ref.n_iter_), (oc.n_iter_, ref.n_iter_)
+    np.testing.assert_allclose(oc.alpha_, ref.alpha_, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(oc.rho_, ref.rho_, rtol=1e-6)
+    np.testing.assert_allclose(oc_dec, ref.decision_function(Xo[:200]), rtol=0, atol=1e-5)
+    ref = quiet(lambda: BiNuSVC(max_iter=4000).fit(Xn, yn))
+    assert nus.n_iter_ == ref.n_iter_ == 4000
+    np.testing.assert_allclose(nus.alpha_, ref.alpha_, rtol=0, atol=1e-7)
+    np.testing.assert_allclose([nus.rho_, nus.b_], [ref.rho_, ref.b_], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(nus_dec, ref.decision_function(Xn[:200]), rtol=1e-6, atol=1e-7)
+    ref = quiet(lambda: NuSVR(max_iter=3000).fit(Xr, z))
+    assert nur.n_iter_ == ref.n_iter_ == 3000
+    np.testing.assert_allclose(nur.alpha_, ref.alpha_, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(nur_dec, ref.decision_function(Xr[:200]), rtol=1e-6, atol=1e-7)
+    ref = quiet(lambda: KernelSVR(max_iter=3000).fit(Xr, z))
+    assert np.array_equal(ksr.alpha_, ref.alpha_)
+    np.testing.assert_allclose(ksr_dec, ref.decision_function(Xr[:200]), rtol=0, atol=1e-12)
+    print("sharded worker ok: nu-SVC, nu-SVR, one-class, KernelSVR estimators", flush=True)
+dist.barrier()
 dist.destroy_process_group()
