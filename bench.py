@@ -302,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": value_launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic_per_launch(ITERS), "peak_source": peak_src,
+                     "traffic": traffic_per_launch(ITERS) if world == 1 else None, "peak_source": peak_src,
                      "kernel": "b2svm::smo_persistent<float,32>", "algorithmic_bytes_per_iteration": algorithmic_bytes_per_iter(),
                      "kernel_ms_per_launch": kernel_ms / args.steps},
         "cpu_baseline": cpu,

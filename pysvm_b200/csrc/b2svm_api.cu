@@ -376,7 +376,9 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
     const int skip = getenv("B2SVM_L2_PIN_SKIP") ? atoi(getenv("B2SVM_L2_PIN_SKIP")) : 0;
     P.pin_lo = skip;
     P.pin_hi = skip + (int)std::min<long long>(per_cta, 1 << 30);
-    if (mb <= 0) P.pin_lo = P.pin_hi = 0;
+    // a slice that fits L2 comfortably stays resident on its own: hints would only push its tail out
+    const double slice_mb = (double)h->ntiles * h->tile_bytes / 1048576.0;
+    if (mb <= 0 || (slice_mb <= 64.0 && !getenv("B2SVM_L2_PIN_MB"))) P.pin_lo = P.pin_hi = 0;
   }
   P.abort_flag = h->abort_flag;
   P.result = h->result;
