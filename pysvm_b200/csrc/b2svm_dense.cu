@@ -147,8 +147,9 @@ static int matvec_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, cons
   const int dp = (d + CK::N - 1) / CK::N * CK::N;
   int* idx = nullptr;
   int* count_dev = nullptr;
-  B2_CUDA(cudaMalloc(&idx, sizeof(int) * (size_t)na));
-  B2_CUDA(cudaMalloc(&count_dev, sizeof(int)));
+  keep_pool_memory();
+  B2_CUDA(cudaMallocAsync(&idx, sizeof(int) * (size_t)na, stream));
+  B2_CUDA(cudaMallocAsync(&count_dev, sizeof(int), stream));
   compact_nonzero_kernel<<<1, 1024, 0, stream>>>(coef, na, idx, count_dev);
   int nsv = 0;
   B2_CUDA(cudaMemcpyAsync(&nsv, count_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -157,7 +158,8 @@ static int matvec_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, cons
   T *sv = nullptr, *svn = nullptr;
   double *svc = nullptr, *partial = nullptr;
   auto done = [&](int code) {
-    cudaFree(idx); cudaFree(count_dev); cudaFree(sv); cudaFree(svn); cudaFree(svc); cudaFree(partial);
+    for (void* ptr : {(void*)idx, (void*)count_dev, (void*)sv, (void*)svn, (void*)svc, (void*)partial})
+      if (ptr) cudaFreeAsync(ptr, stream);
     return code;
   };
   if (nsv == 0) {
@@ -175,9 +177,9 @@ static int matvec_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, cons
     cudaError_t _e = (expr);                                                             \
     if (_e != cudaSuccess) return done(fail(B2SVM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e))); \
   } while (0)
-  MV_TRY(cudaMalloc(&sv, sizeof(T) * (size_t)nsv * dp));
-  MV_TRY(cudaMalloc(&svn, sizeof(T) * (size_t)nsv));
-  MV_TRY(cudaMalloc(&svc, sizeof(double) * (size_t)nsv));
+  MV_TRY(cudaMallocAsync(&sv, sizeof(T) * (size_t)nsv * dp, stream));
+  MV_TRY(cudaMallocAsync(&svn, sizeof(T) * (size_t)nsv, stream));
+  MV_TRY(cudaMallocAsync(&svc, sizeof(double) * (size_t)nsv, stream));
   {
     int g = (int)std::min<int64_t>(148 * 8, ((int64_t)nsv * 32 + 255) / 256);
     gather_rows_kernel<T><<<std::max(g, 1), 256, 0, stream>>>(Xa, lda, d, dp, idx, nsv, coef, sv, svn, svc);
@@ -197,7 +199,7 @@ static int matvec_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, cons
   ny = std::min(ny, 65535);
   const int slice = ((tiles + ny - 1) / ny) * MV_TS;
   ny = (nsv + slice - 1) / slice;
-  MV_TRY(cudaMalloc(&partial, sizeof(double) * (size_t)ny * nb));
+  MV_TRY(cudaMallocAsync(&partial, sizeof(double) * (size_t)ny * nb, stream));
   const size_t smem = smem_for(TQ);
   dim3 grid(gx, ny);
 #define MV_LAUNCH2(TQV, KIND)                                                                                      \
@@ -345,6 +347,16 @@ int b2svm_rff_transform(int32_t device, void* stream, int32_t x_dtype, const voi
 int b2svm_rff_decision(int32_t device, void* stream, int32_t x_dtype, const void* Xq, int64_t nq, int64_t ldx, int32_t d,
                        const double* W, const double* b, int32_t D, const double* wz, double* out) {
   if (!Xq || !W || !b || !wz || !out) return fail(B2SVM_E_INVALID, "null argument");
+  {
+    // float32 queries, enough work for 128 x 128 tiles: the GEMM + cos epilogue runs on the tensor cores (3xTF32,
+    // argument error ~1e-6); B2SVM_RFF_TC=0 keeps the float64 kernel, =2 forces the tensor path
+    int mode = matvec_tc_mode(x_dtype, d);
+    if (const char* e = getenv("B2SVM_RFF_TC")) mode = std::min(mode ? 2 : 0, atoi(e));
+    if (mode == 2 || (mode == 1 && nq >= 1024 && D >= 256)) {
+      B2_CUDA(cudaSetDevice(device));
+      return rff_decision_tc((cudaStream_t)stream, d, W, b, D, wz, (const float*)Xq, nq, ldx, out);
+    }
+  }
   return rff_launch<true>(device, stream, x_dtype, Xq, nq, ldx, d, W, b, D, wz, out);
 }
 

@@ -33,6 +33,12 @@ int matvec_tc_mode(int x_dtype, int d);
 int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const float* Xa, int64_t lda, const int* idx, int nsv,
               const double* coef, const float* Xb, int64_t nb, int64_t ldb, double* out);
 
+// z(x_q) . wz = sqrt(2/D) sum_j wz_j cos(w_j . x_q + b_j) on the tensor cores (float32 queries, d <= 128)
+int rff_decision_tc(cudaStream_t stream, int d, const double* W, const double* b, int D, const double* wz, const float* Xq,
+                    int64_t nq, int64_t ldq, double* out);
+
+void keep_pool_memory();   // stream-ordered allocator: keep up to 4 GB of work buffers between calls
+
 struct ProblemDev;
 #define B2_DECL_LAUNCH(name)                                                                                  \
   int name(int ch, bool cache, const ProblemDev* p, int nprob, int ncta_pp, int stages, size_t smem, cudaStream_t stream)

@@ -21,6 +21,7 @@
 
 namespace b2svm {
 
+constexpr int K_RFFCOS = 16;   // internal epilogue: cos(dot + phase_s), the random-Fourier-feature form (rff.py:19-20)
 constexpr int TC_M = 128, TC_N = 128, TC_KBLK = 32;           // tile: 128 x 128, K blocks of 32 floats = 128 B
 constexpr int TC_TILE_BYTES = TC_M * TC_KBLK * 4;              // one [128 rows][128 B] swizzled operand block
 constexpr int TC_EPI_WARPS = 16;                                // four per TMEM lane quarter, 32 columns each
@@ -101,6 +102,28 @@ __global__ void split_rows_kernel(const float* __restrict__ X, int64_t ld, int d
   }
 }
 
+// float64 rows (the RFF projection matrix W): hi = float(w) with the low 13 bits cleared, lo = float(w - hi)
+__global__ void split_rows_f64_kernel(const double* __restrict__ W, int d, int dp, int64_t rows, int64_t rows_pad,
+                                      float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t total = rows_pad * dp;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = e / dp;
+    const int c = (int)(e - k * dp);
+    const double w = (k < rows && c < d) ? W[k * d + c] : 0.0;
+    const float h = __uint_as_float(__float_as_uint((float)w) & 0xffffe000u);
+    hi[e] = h;
+    lo[e] = (float)(w - (double)h);
+  }
+}
+
+__global__ void rff_meta_kernel(const double* __restrict__ b, const double* __restrict__ wz, int D, int D_pad, double scale,
+                                float* __restrict__ phase, double* __restrict__ coef) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < D_pad; k += gridDim.x * blockDim.x) {
+    phase[k] = k < D ? (float)b[k] : 0.f;
+    coef[k] = k < D ? wz[k] * scale : 0.0;
+  }
+}
+
 __global__ void gather_coef_kernel(const double* __restrict__ coef, const int* __restrict__ idx, int n, int n_pad,
                                    double* __restrict__ out) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_pad; k += gridDim.x * blockDim.x)
@@ -135,6 +158,15 @@ __device__ __forceinline__ float epi_value(const TcParams& p, uint32_t dot_bits,
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(p.c2, dot, norm_s + norm_q)));
     return r;
+  } else if constexpr (KIND == K_RFFCOS) {
+    // cos(w_s . x_q + b_s): reduce to [-pi, pi] with a two-term 2 pi, then MUFU.COS (abs error ~5e-7)
+    const float t = dot + norm_s;
+    const float k = rintf(t * 0.15915494309189535f);
+    float u = fmaf(k, -6.2831854820251465f, t);
+    u = fmaf(k, 1.7484555e-7f, u);
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(u));
+    return r;
   } else {
     return kernel_value_k<KIND>(p.kp, dot, norm_s, norm_q);
   }
@@ -150,6 +182,9 @@ __device__ __forceinline__ double widen(float x) {
   if constexpr (KIND == K_RBF) {
     const uint32_t b = __float_as_uint(x);
     return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+  } else if constexpr (KIND == K_RFFCOS) {   // signed, |x| <= 1, flushed denormals: same trick with the sign carried over
+    const uint32_t b = __float_as_uint(x);
+    return __hiloint2double((int)((((b & 0x7fffffffu) >> 3) + 0x38000000u) | (b & 0x80000000u)), (int)(b << 29));
   } else {
     return (double)x;
   }
@@ -342,6 +377,21 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Work buffers come from the stream-ordered allocator and its pool keeps them between calls: a prediction over
+// millions of queries is many calls, and cudaMalloc / cudaFree (a device-wide synchronisation each) cost more than
+// the kernel.
+void keep_pool_memory() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = 4ull << 30;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+}
+
 static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int dp) {
   const cuuint64_t dims[2] = {(cuuint64_t)dp, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)dp * sizeof(float)};
@@ -360,9 +410,19 @@ int matvec_tc_mode(int x_dtype, int d) {
   return encode_fn() != nullptr ? std::min(mode, 2) : 0;
 }
 
-// idx / nsv: ordered list of rows of Xa with a non-zero coefficient (device), from the caller's compaction
-int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const float* Xa, int64_t lda, const int* idx, int nsv,
-              const double* coef, const float* Xb, int64_t nb, int64_t ldb, double* out) {
+// idx / nsv: ordered list of rows of Xa with a non-zero coefficient (device), from the caller's compaction.
+// rff != nullptr: the "support rows" are the D rows of the float64 projection matrix W, the per-row scalar is the
+// phase b, the coefficient wz * sqrt(2 / D), and the epilogue is cos (b2svm_rff_decision on the tensor cores).
+struct RffOperands {
+  const double* W;
+  const double* b;
+  const double* wz;
+};
+
+static int matvec_tc_core(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const float* Xa, int64_t lda, const int* idx,
+                          int nsv, const double* coef, const RffOperands* rff, const float* Xb, int64_t nb, int64_t ldb,
+                          double* out) {
+  keep_pool_memory();
   const int dp = (d + TC_KBLK - 1) / TC_KBLK * TC_KBLK;
   const int KB = dp / TC_KBLK;
   const int64_t nsv_pad = ((int64_t)nsv + TC_N - 1) / TC_N * TC_N;
@@ -370,7 +430,8 @@ int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const floa
   float *s_hi = nullptr, *s_lo = nullptr, *q_hi = nullptr, *q_lo = nullptr, *svn = nullptr, *qn = nullptr;
   double *svc = nullptr, *partial = nullptr;
   auto done = [&](int code) {
-    cudaFree(s_hi); cudaFree(s_lo); cudaFree(q_hi); cudaFree(q_lo); cudaFree(svn); cudaFree(qn); cudaFree(svc); cudaFree(partial);
+    for (void* ptr : {(void*)s_hi, (void*)s_lo, (void*)q_hi, (void*)q_lo, (void*)svn, (void*)qn, (void*)svc, (void*)partial})
+      if (ptr) cudaFreeAsync(ptr, stream);
     return code;
   };
 #define TC_TRY(expr)                                                                                             \
@@ -378,18 +439,24 @@ int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const floa
     cudaError_t _e = (expr);                                                                                     \
     if (_e != cudaSuccess) return done(fail(B2SVM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)));  \
   } while (0)
-  TC_TRY(cudaMalloc(&s_hi, sizeof(float) * nsv_pad * dp));
-  TC_TRY(cudaMalloc(&s_lo, sizeof(float) * nsv_pad * dp));
-  TC_TRY(cudaMalloc(&q_hi, sizeof(float) * nq_pad * dp));
-  TC_TRY(cudaMalloc(&q_lo, sizeof(float) * nq_pad * dp));
-  TC_TRY(cudaMalloc(&svn, sizeof(float) * nsv_pad));
-  TC_TRY(cudaMalloc(&qn, sizeof(float) * nq_pad));
-  TC_TRY(cudaMalloc(&svc, sizeof(double) * nsv_pad));
+  TC_TRY(cudaMallocAsync(&s_hi, sizeof(float) * nsv_pad * dp, stream));
+  TC_TRY(cudaMallocAsync(&s_lo, sizeof(float) * nsv_pad * dp, stream));
+  TC_TRY(cudaMallocAsync(&q_hi, sizeof(float) * nq_pad * dp, stream));
+  TC_TRY(cudaMallocAsync(&q_lo, sizeof(float) * nq_pad * dp, stream));
+  TC_TRY(cudaMallocAsync(&svn, sizeof(float) * nsv_pad, stream));
+  TC_TRY(cudaMallocAsync(&qn, sizeof(float) * nq_pad, stream));
+  TC_TRY(cudaMallocAsync(&svc, sizeof(double) * nsv_pad, stream));
   const float norm_scale = k.kind == K_RBF ? (float)(-(double)(float)k.gamma * 1.4426950408889634) : 1.0f;
   auto grid_rows = [](int64_t rows) { return (int)std::max<int64_t>(1, std::min<int64_t>(148 * 8, (rows * 32 + 255) / 256)); };
-  split_rows_kernel<<<grid_rows(nsv_pad), 256, 0, stream>>>(Xa, lda, d, dp, idx, nsv, nsv_pad, s_hi, s_lo, svn, norm_scale);
-  split_rows_kernel<<<grid_rows(nq_pad), 256, 0, stream>>>(Xb, ldb, d, dp, nullptr, nb, nq_pad, q_hi, q_lo, qn, norm_scale);
-  gather_coef_kernel<<<std::max(1, (int)std::min<int64_t>(1184, (nsv_pad + 255) / 256)), 256, 0, stream>>>(coef, idx, nsv, (int)nsv_pad, svc);
+  if (rff) {
+    split_rows_f64_kernel<<<grid_rows(nsv_pad), 256, 0, stream>>>(rff->W, d, dp, nsv, nsv_pad, s_hi, s_lo);
+    rff_meta_kernel<<<std::max(1, (int)((nsv_pad + 255) / 256)), 256, 0, stream>>>(rff->b, rff->wz, nsv, (int)nsv_pad,
+                                                                               std::sqrt(2.0 / (double)nsv), svn, svc);
+  } else {
+    split_rows_kernel<<<grid_rows(nsv_pad), 256, 0, stream>>>(Xa, lda, d, dp, idx, nsv, nsv_pad, s_hi, s_lo, svn, norm_scale);
+    gather_coef_kernel<<<std::max(1, (int)std::min<int64_t>(1184, (nsv_pad + 255) / 256)), 256, 0, stream>>>(coef, idx, nsv, (int)nsv_pad, svc);
+  }
+  split_rows_kernel<<<grid_rows(nq_pad), 256, 0, stream>>>(Xb, ldb, d, dp, nullptr, nb, nq_pad, q_hi, q_lo, qn, rff ? 0.f : norm_scale);
   TC_TRY(cudaGetLastError());
 
   CUtensorMap m_qh, m_ql, m_sh, m_sl;
@@ -415,7 +482,7 @@ int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const floa
   p.stages = (int)std::min<size_t>(6, (200 * 1024 - a_bytes) / b_stage);
   if (p.stages < 2) return done(fail(B2SVM_E_UNSUPPORTED, "kernel_matvec (tensor path): n_features too large"));
   p.kp = KernelParams<float>{k.kind, (float)k.gamma, (float)k.coef0, (float)k.degree};
-  TC_TRY(cudaMalloc(&partial, sizeof(double) * (size_t)ny * nb));
+  TC_TRY(cudaMallocAsync(&partial, sizeof(double) * (size_t)ny * nb, stream));
   p.partial = partial;
   const size_t smem = a_bytes + p.stages * b_stage + (size_t)(2 * p.stages + 8) * sizeof(uint64_t) + 1024;
 #define TC_LAUNCH(KIND)                                                                                             \
@@ -423,7 +490,8 @@ int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const floa
     TC_TRY(cudaFuncSetAttribute(matvec_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     matvec_tc_kernel<KIND><<<dim3(gx, ny), TC_THREADS, smem, stream>>>(m_qh, m_ql, m_sh, m_sl, p);                  \
   } while (0)
-  switch (k.kind) {
+  switch (rff ? K_RFFCOS : k.kind) {
+    case K_RFFCOS: TC_LAUNCH(K_RFFCOS); break;
     case K_RBF: TC_LAUNCH(K_RBF); break;
     case K_POLY: TC_LAUNCH(K_POLY); break;
     case K_SIGMOID: TC_LAUNCH(K_SIGMOID); break;
@@ -436,6 +504,19 @@ int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const floa
   TC_TRY(cudaStreamSynchronize(stream));
 #undef TC_TRY
   return done(B2SVM_OK);
+}
+
+int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const float* Xa, int64_t lda, const int* idx, int nsv,
+              const double* coef, const float* Xb, int64_t nb, int64_t ldb, double* out) {
+  return matvec_tc_core(stream, k, d, Xa, lda, idx, nsv, coef, nullptr, Xb, nb, ldb, out);
+}
+
+int rff_decision_tc(cudaStream_t stream, int d, const double* W, const double* b, int D, const double* wz, const float* Xq,
+                    int64_t nq, int64_t ldq, double* out) {
+  b2svm_kernel_desc k{};
+  k.kind = K_LINEAR;
+  const RffOperands r{W, b, wz};
+  return matvec_tc_core(stream, k, d, nullptr, 0, nullptr, D, nullptr, &r, Xq, nq, ldq, out);
 }
 
 }  // namespace b2svm

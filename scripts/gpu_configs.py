@@ -43,3 +43,17 @@ if "c5" in which:
     r = NormalRFF(gamma=est.gamma_, D=4096).fit(X[:1])
     Z, dt = timed(lambda: r.transform_device(torch.from_numpy(X[:200_000]).cuda()))
     log(f"C5 NormalRFF.transform 200k x 32 -> 4096 (float64): {dt:.2f} s -> {200_000/dt:.3e} rows/s (reference CPU: 5.8e3)")
+    # RFF decision form over the 10M queries: z(x_q) . wz, never materialising z (tensor cores, then the float64 kernel)
+    from pysvm_b200.rff import rff_decision_device
+    w, b = r._device_params(torch.device("cuda", 0))
+    wz = torch.randn(4096, dtype=torch.float64, device="cuda")
+    for mode, nblk in (("1", 10), ("0", 1)):
+        os.environ["B2SVM_RFF_TC"] = mode
+        g = torch.Generator(device="cuda").manual_seed(2)
+        tot = 0.0
+        for _ in range(nblk):
+            Xd = torch.randn(1_000_000, 32, generator=g, device="cuda")
+            rff_decision_device(Xd[:2048], w, b, wz)
+            _, dt = timed(lambda: rff_decision_device(Xd, w, b, wz))
+            tot += dt
+        log(f"C5 RFF decision (D=4096) {nblk}M queries, {'tcgen05 3xTF32' if mode == '1' else 'float64 CUDA cores'}: {tot:.3f} s -> {nblk*1e6/tot:.3e} rows/s, {nblk*1e6*4096/tot:.3e} cos/s")

@@ -594,3 +594,26 @@ def test_macro_tiles_are_bit_identical(monkeypatch, n, d, dtype, max_ctas):
         out.append((sol.alpha.cpu().numpy().copy(), sol.neg_y_grad.cpu().numpy().copy()))
     for a, g in out[1:]:
         assert np.array_equal(a, out[0][0]) and np.array_equal(g, out[0][1])
+
+
+@pytest.mark.parametrize("nq,d,D", [(3000, 30, 1000), (1500, 32, 4096), (2049, 7, 300), (1100, 100, 512)])
+def test_rff_decision_on_tensor_cores(monkeypatch, nq, d, D):
+    """z(x_q) . wz (rff.py:19-20 + the coefficient product): the tcgen05 GEMM + cos epilogue (float32 queries,
+    3xTF32, argument error ~1e-6) against the float64 kernel, 2e-5 of the output scale; both against NumPy."""
+    torch, _, S, *_ = _mods()
+    from pysvm_b200.rff import NormalRFF, rff_decision_device
+    rng = np.random.default_rng(nq + D)
+    Xq = rng.standard_normal((nq, d)).astype(np.float32)
+    np.random.seed(3)
+    r = NormalRFF(gamma=1.0 / d, D=D).fit(Xq[:1])
+    wz = rng.standard_normal(D)
+    want = (np.sqrt(2 / D) * np.cos(Xq.astype(np.float64) @ r.w.T + r.b)) @ wz
+    dev = torch.device("cuda:0")
+    w, b = r._device_params(dev)
+    outs = {}
+    for mode in ("0", "2"):
+        monkeypatch.setenv("B2SVM_RFF_TC", mode)
+        outs[mode] = rff_decision_device(torch.from_numpy(Xq).to(dev), w, b, torch.from_numpy(wz).to(dev)).cpu().numpy()
+    scale = np.abs(want).max()
+    assert np.abs(outs["0"] - want).max() / scale < 1e-12
+    assert np.abs(outs["2"] - want).max() / scale < 2e-5
