@@ -194,6 +194,19 @@ class ShardedNuSolver(ShardedSolver):
         return rho_b_from_partials(combine_bias_partials(parts))
 
 
+def schedule_subproblems(sizes, world: int):
+    """Owner rank of each independent sub-problem (one-vs-one / one-vs-rest fits): longest processing time first --
+    largest sub-problem to the least loaded GPU, ties to the lower rank / lower index -- a pure function of the sizes,
+    so every rank computes the same assignment without talking."""
+    load = [0] * world
+    owner = [0] * len(sizes)
+    for k in sorted(range(len(sizes)), key=lambda k: (-sizes[k], k)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[k] = r
+        load[r] += sizes[k]
+    return owner
+
+
 _ENABLED = {"on": False, "group": None}
 
 

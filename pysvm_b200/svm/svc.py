@@ -1,6 +1,7 @@
 """Classification estimators with PySVM's API (reference ``pysvm/svm/svc.py``), solved on the GPU."""
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 import numpy as np
@@ -38,8 +39,47 @@ class deferred_solves:
     def run(self, max_iter):
         if not self.items:
             return
+        from .. import sharded
+        if sharded.active():
+            return self._run_across_gpus(max_iter, sharded)
         stats = solve_batched([it[1] for it in self.items], max_iter)
         for (est, solver, finish), st in zip(self.items, stats):
+            finish(st)
+
+    def _run_across_gpus(self, max_iter, sharded):
+        """The independent sub-problems of sklearn.multiclass scheduled over the GPUs of the process group with no
+        communication during the solves: longest-processing-time assignment by row count (the same on
+        every rank), one batched launch per GPU, then one all-gather of (stats, alpha, gradient) so that every rank
+        ends with every fitted sub-estimator."""
+        import torch.distributed as dist
+        from .. import _native as N
+        group = sharded._ENABLED["group"]
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        sizes = [int(it[1].alpha.shape[0]) for it in self.items]
+        owner = sharded.schedule_subproblems(sizes, world)
+        mine = [k for k in range(len(sizes)) if owner[k] == rank]
+        stats = solve_batched([self.items[k][1] for k in mine], max_iter) if mine else []
+        nstat = C.sizeof(N.SolveStats) // 8
+        lengths = [sum(nstat + 2 * sizes[k] for k in range(len(sizes)) if owner[k] == r) for r in range(world)]
+        payload = np.zeros(max(lengths))
+        o = 0
+        for k, st in zip(mine, stats):
+            solver = self.items[k][1]
+            payload[o:o + nstat] = np.frombuffer(bytes(st), dtype=np.float64)
+            payload[o + nstat:o + nstat + sizes[k]] = solver.alpha.cpu().numpy()
+            payload[o + nstat + sizes[k]:o + nstat + 2 * sizes[k]] = solver.neg_y_grad.cpu().numpy()
+            o += nstat + 2 * sizes[k]
+        everything = sharded.all_gather_array(payload, group)            # [world][max length]
+        offs = [0] * world
+        for k, (est, solver, finish) in enumerate(self.items):
+            r, o = owner[k], offs[owner[k]]
+            row = everything[r]
+            st = N.SolveStats.from_buffer_copy(row[o:o + nstat].tobytes())
+            if r != rank:
+                solver.alpha = row[o + nstat:o + nstat + sizes[k]]
+                solver.neg_y_grad = row[o + nstat + sizes[k]:o + nstat + 2 * sizes[k]]
+                solver.last_stats = st
+            offs[r] = o + nstat + 2 * sizes[k]
             finish(st)
 
 
@@ -202,7 +242,7 @@ class BiKernelSVC(BiLinearSVC):
         l, self.n_features = X.shape
         p = -np.ones(l)
         from .. import sharded
-        if sharded.active() and not self.rff:
+        if sharded.active() and not self.rff and not (_PENDING is not None and l <= BATCH_MAX_ROWS):
             return self._fit_sharded(X, y, sharded)
         func, spec, rff = self._columns(X, y)
         solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func, max_iter_hint=self.max_iter)
@@ -304,7 +344,7 @@ class BiNuSVC(BiKernelSVC):
         y[y != 1] = -1
         l, self.n_features = X.shape
         from .. import sharded
-        if sharded.active() and not self.rff:
+        if sharded.active() and not self.rff and not (_PENDING is not None and l <= BATCH_MAX_ROWS):
             group = sharded._ENABLED["group"]
             spec, _ = self.register_kernel(host_std(X))
             solver, shard, stats = sharded.fit_nusvc_sharded(X, (y == 1).astype(int), self.nu, spec, self.tol, self.max_iter, group)

@@ -95,4 +95,23 @@ if rank == 0:
     np.testing.assert_allclose(ksr_dec, ref.decision_function(Xr[:200]), rtol=0, atol=1e-12)
     print("sharded worker ok: nu-SVC, nu-SVR, one-class, KernelSVR estimators", flush=True)
 dist.barrier()
+
+# ---- one-vs-one sub-problems scheduled across the GPUs (no communication during the solves) -----------------------
+from sklearn.datasets import load_digits
+from pysvm_b200.svm.svc import KernelSVC
+Xd, yd = load_digits(return_X_y=True)
+SH.enable()
+ovo = quiet(lambda: KernelSVC(multiclass="ovo", max_iter=10 ** 5).fit(Xd, yd))
+pred = ovo.predict(Xd)
+SH.disable()
+ref = quiet(lambda: KernelSVC(multiclass="ovo", max_iter=10 ** 5).fit(Xd, yd))
+it_sh = sum(e.n_iter_ for e in ovo.multiclass_model.estimators_)
+it_ref = sum(e.n_iter_ for e in ref.multiclass_model.estimators_)
+assert it_sh == it_ref, (it_sh, it_ref)
+for a, b in zip(ovo.multiclass_model.estimators_, ref.multiclass_model.estimators_):
+    assert np.array_equal(a.alpha_, b.alpha_) and a.rho_ == b.rho_
+assert np.array_equal(pred, ref.predict(Xd))
+if rank == 0:
+    print("sharded worker ok: 45 one-vs-one sub-problems over", world, "GPUs,", it_sh, "iterations", flush=True)
+dist.barrier()
 dist.destroy_process_group()

@@ -116,3 +116,19 @@ def test_gloo_world_size_2_plumbing():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, "ok"), (1, "ok")], res
+
+
+def test_subproblem_schedule_is_balanced_and_deterministic():
+    """One-vs-one sub-problems are dealt to the GPUs by size (largest first, least loaded rank): every rank derives the
+    same owners, every sub-problem has exactly one owner, and the load is within one sub-problem of even."""
+    from pysvm_b200.sharded import schedule_subproblems
+    rng = np.random.default_rng(0)
+    sizes = [int(s) for s in rng.integers(300, 400, size=45)]          # digits: 45 pairs of ~360 rows
+    for world in (1, 2, 4, 8):
+        owner = schedule_subproblems(sizes, world)
+        assert owner == schedule_subproblems(list(sizes), world)
+        assert len(owner) == 45 and set(owner) <= set(range(world))
+        load = [sum(s for s, o in zip(sizes, owner) if o == r) for r in range(world)]
+        assert max(load) - min(load) <= max(sizes)
+    assert schedule_subproblems([5, 5, 5], 2) == [0, 1, 0]
+    assert schedule_subproblems([], 4) == []
