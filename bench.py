@@ -120,6 +120,15 @@ def synth():
     return X, y01
 
 
+def use_all_host_threads(n):
+    """BLAS / OpenMP pools of this process back to n threads (the launcher may have pinned them to 1)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank, world):
     """The reference algorithm on the host: oracle port (NumPy/OpenBLAS, all cores), bounded sample."""
@@ -128,6 +137,7 @@ def run_reference(args, rank, world):
     from oracle import smo_oracle as O
     X, y01 = synth()
     cores = os.cpu_count()
+    use_all_host_threads(cores)        # torchrun exports OMP_NUM_THREADS=1 to every rank
     O.fit_csvc(X, y01, max_iter=2)                                   # touch everything once
     for _ in range(args.warmup):
         O.fit_csvc(X, y01, max_iter=2)
@@ -272,6 +282,7 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import smo_oracle as O
+        use_all_host_threads(os.cpu_count())
         O.fit_csvc(X, y01, max_iter=2)
         t0 = time.perf_counter()
         ref = O.fit_csvc(X, y01, max_iter=100)
