@@ -115,8 +115,8 @@ class ClockSampler:
 
 
 def synth():
-    from oracle import smo_oracle as O          # generators only (shared with the tests)
-    X, y01 = O.synth_classification(n=N_ROWS, d=N_FEATURES, seed=0)
+    from pysvm_b200 import synth as gen         # seeded NumPy generators of SURVEY 8d (no oracle on this arm)
+    X, y01 = gen.classification(n=N_ROWS, d=N_FEATURES, seed=0)
     return X, y01
 
 

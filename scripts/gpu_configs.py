@@ -3,7 +3,7 @@ import os, sys, time, contextlib, io
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import smo_oracle as O
+from pysvm_b200 import synth as G
 import pysvm_b200 as P
 from pysvm_b200.rff import NormalRFF
 t00 = time.time()
@@ -15,7 +15,7 @@ def timed(f):
     torch.cuda.synchronize(); return r, time.perf_counter() - t
 which = sys.argv[1:] or ["c4", "c5"]
 if "c4" in which:
-    X, z = O.synth_regression(n=100_000, d=64, seed=0)
+    X, z = G.regression(n=100_000, d=64, seed=0)
     est, dt = timed(lambda: P.KernelSVR(max_iter=10 ** 7).fit(X, z))
     s = est.solve_stats_
     log(f"C4 KernelSVR l=100k d=64: fit {dt:.2f} s, {s['n_iter']} it ({s['device_ms']*1e3/max(1,s['n_iter']):.2f} us/it), cold {s['cold_sweeps']} warm {s['cache_hits']//2}, converged {s['converged']}, R2(first 20k) {est.score(X[:20000], z[:20000]):.4f}")
@@ -23,7 +23,7 @@ if "c4" in which:
     s = est.solve_stats_
     log(f"C4 NuSVR l=100k d=64 max_iter=2e5: fit {dt:.2f} s, {s['n_iter']} it ({s['device_ms']*1e3/max(1,s['n_iter']):.2f} us/it), cold {s['cold_sweeps']} warm {s['cache_hits']//2}, sum(alpha) {est.alpha_.sum():.3f} (C*l*nu = 50000)")
 if "c5" in which:
-    X = O.synth_oneclass(n=1_000_000, d=32, seed=1)
+    X = G.oneclass(n=1_000_000, d=32, seed=1)
     est, dt = timed(lambda: P.OneClassSVM(max_iter=10 ** 7).fit(X))
     s = est.solve_stats_
     log(f"C5 OneClassSVM n=1M d=32: fit {dt:.2f} s, {s['n_iter']} it ({s['device_ms']*1e3/max(1,s['n_iter']):.2f} us/it), cold {s['cold_sweeps']} warm {s['cache_hits']//2}, nSV {int((est.alpha_>0).sum())}, converged {s['converged']}")

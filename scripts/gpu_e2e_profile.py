@@ -3,10 +3,10 @@ import os, sys, time, contextlib, io
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import smo_oracle as O
+from pysvm_b200 import synth as G
 from pysvm_b200 import solver as S
 from pysvm_b200.svm.svc import BiKernelSVC
-X, y01 = O.synth_classification(n=200000, d=128, seed=0)
+X, y01 = G.classification(n=200000, d=128, seed=0)
 Xp = torch.from_numpy(X).pin_memory().numpy()
 def T(label, f):
     torch.cuda.synchronize(); t = time.perf_counter(); r = f(); torch.cuda.synchronize()

@@ -2,10 +2,10 @@
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import smo_oracle as O
+from pysvm_b200 import synth as G
 from pysvm_b200 import solver as S
 def run(n, d, iters, cache):
-    X, y01 = O.synth_classification(n=n, d=d, seed=0)
+    X, y01 = G.classification(n=n, d=d, seed=0)
     y = np.where(y01 == 1, 1.0, -1.0)
     sol = S.SolverWithCache(-np.ones(n), y, 1.0, func=S.QColumns(X, y, S.KernelSpec("rbf", 1 / (d * X.std())), cache_bytes=cache))
     sol.solve(50)

@@ -6,11 +6,11 @@ os.environ["B2SVM_TIMELINE"] = "1"
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import smo_oracle as O
+from pysvm_b200 import synth as G
 from pysvm_b200 import solver as S, _native as N
 
 def run(n, d, iters, dtype=np.float32):
-    Xs, ys = O.synth_classification(n=n, d=d, seed=0)
+    Xs, ys = G.classification(n=n, d=d, seed=0)
     Xs = Xs.astype(dtype)
     yv = np.where(ys == 1, 1.0, -1.0)
     func = S.QColumns(Xs, yv, S.KernelSpec("rbf", 1 / (d * Xs.std())), cache_bytes=int(os.environ.get("CACHE_BYTES", "0")))

@@ -8,7 +8,7 @@ import torch.distributed as dist
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-from oracle import smo_oracle as O
+from pysvm_b200 import synth as G
 from pysvm_b200 import solver as S, sharded as SH
 
 def log(*a):
@@ -16,7 +16,7 @@ def log(*a):
         print(*a, flush=True)
 
 for n, iters in ((20000, 1500), (200000, 4000)):
-    X, y01 = O.synth_classification(n=n, d=128, seed=0)
+    X, y01 = G.classification(n=n, d=128, seed=0)
     y = np.where(y01 == 1, 1.0, -1.0)
     spec = S.KernelSpec("rbf", 1 / (128 * X.std()))
     solver, shard, st = SH.fit_csvc_sharded(X, y01, 1.0, spec, 1e-5, iters)

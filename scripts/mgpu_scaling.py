@@ -13,11 +13,11 @@ import torch.distributed as dist
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-from oracle import smo_oracle as O
+from pysvm_b200 import synth as G
 from pysvm_b200 import solver as S, sharded as SH
 
 n, iters, d = int(os.environ.get("N_ROWS", 1_600_000)), int(os.environ.get("ITERS", 3000)), 128
-X, y01 = O.synth_classification(n=n, d=d, seed=0)
+X, y01 = G.classification(n=n, d=d, seed=0)
 y = np.where(y01 == 1, 1.0, -1.0)
 spec = S.KernelSpec("rbf", float(1 / (d * S.host_std(X))))
 out = {"n_rows": n, "d": d, "iterations": iters, "world": world}

@@ -7,10 +7,10 @@ import torch, torch.distributed as dist
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-from oracle import smo_oracle as O
+from pysvm_b200 import synth as G
 from pysvm_b200 import solver as S, sharded as SH, _native as N
 n = int(os.environ.get("N", 200000))
-X, y01 = O.synth_classification(n=n, d=128, seed=0)
+X, y01 = G.classification(n=n, d=128, seed=0)
 spec = S.KernelSpec("rbf", 1 / (128 * X.std()))
 solver, shard, st = SH.fit_csvc_sharded(X, y01, 1.0, spec, 1e-5, 200)
 solver._engine.init_state(solver.p)

@@ -121,3 +121,17 @@ def test_host_std_is_bit_identical_to_numpy():
     Xf = np.asfortranarray(rng.standard_normal((1500, 900)).astype(np.float32))       # not C-contiguous: numpy's own path
     assert host_std(Xf) == Xf.std()
     assert host_std(Xf[::2]) == Xf[::2].std()
+
+
+def test_package_generators_equal_the_oracles():
+    """bench.py's own arm draws its inputs from pysvm_b200.synth (the oracle is only the checker / the CPU baseline):
+    the arrays must be the ones the fixtures and the oracle-side tests were made from."""
+    from oracle import smo_oracle as O
+    from pysvm_b200 import synth
+    Xa, ya = synth.classification(n=3000, d=128, seed=0)
+    Xb, yb = O.synth_classification(n=3000, d=128, seed=0)
+    assert np.array_equal(Xa, Xb) and np.array_equal(ya, yb)
+    Xa, za = synth.regression(n=2000, d=64, seed=0)
+    Xb, zb = O.synth_regression(n=2000, d=64, seed=0)
+    assert np.array_equal(Xa, Xb) and np.array_equal(za, zb)
+    assert np.array_equal(synth.oneclass(n=1000, d=32, seed=1), O.synth_oneclass(n=1000, d=32, seed=1))
