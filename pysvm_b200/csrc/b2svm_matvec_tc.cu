@@ -174,34 +174,25 @@ __device__ __forceinline__ float epi_value(const TcParams& p, uint32_t dot_bits,
 
 // 32 accumulator columns (registers v) against the 32 support rows whose metadata (norm / phase, coefficient) the
 // warp staged in shared memory (n4, c2): broadcast vector reads, two independent float64 accumulation chains
-// float32 -> float64 of a kernel value.  F2F.F64.F32 issues at a fraction of the MUFU rate and was the epilogue's
-// bound; an rbf value is a non-negative normal (ex2.approx.ftz flushes denormals) or zero, so the widening is
-// three integer ops: exponent rebias (+896) and a 29-bit mantissa shift.  Zero maps to 2^-127 (1e-38 x coef: noise).
+// 32 accumulator columns (registers v) against the 32 support rows whose metadata (norm / phase, coefficient) the
+// warp staged in shared memory: broadcast vector reads.  The 32 products coef * k are summed in float32 (four
+// independent chains, coefficients rounded to float32) and the chunk sum is added to the float64 accumulator: the
+// rounding this adds (~1e-7 of the chunk) is below the 3xTF32 error of the dot products, and the per-pair work drops
+// from {FADD, FFMA, MUFU, 3 integer ops, DFMA} to {FADD, FFMA, MUFU, FFMA} -- the epilogue is issue- and MUFU-bound.
 template <int KIND>
-__device__ __forceinline__ double widen(float x) {
-  if constexpr (KIND == K_RBF) {
-    const uint32_t b = __float_as_uint(x);
-    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
-  } else if constexpr (KIND == K_RFFCOS) {   // signed, |x| <= 1, flushed denormals: same trick with the sign carried over
-    const uint32_t b = __float_as_uint(x);
-    return __hiloint2double((int)((((b & 0x7fffffffu) >> 3) + 0x38000000u) | (b & 0x80000000u)), (int)(b << 29));
-  } else {
-    return (double)x;
-  }
-}
-
-template <int KIND>
-__device__ __forceinline__ void accum32(const TcParams& p, const uint32_t (&v)[32], const float4* n4, const double2* c2,
-                                        float nq, double& s0, double& s1) {
+__device__ __forceinline__ double accum32(const TcParams& p, const uint32_t (&v)[32], const float4* n4, const float4* c4,
+                                          float nq) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 n = n4[j];                                      // shared-memory broadcast reads
-    const double2 ca = c2[2 * j], cb = c2[2 * j + 1];
-    s0 = fma(ca.x, widen<KIND>(epi_value<KIND>(p, v[4 * j + 0], n.x, nq)), s0);
-    s1 = fma(ca.y, widen<KIND>(epi_value<KIND>(p, v[4 * j + 1], n.y, nq)), s1);
-    s0 = fma(cb.x, widen<KIND>(epi_value<KIND>(p, v[4 * j + 2], n.z, nq)), s0);
-    s1 = fma(cb.y, widen<KIND>(epi_value<KIND>(p, v[4 * j + 3], n.w, nq)), s1);
+    const float4 c = c4[j];
+    s0 = fmaf(c.x, epi_value<KIND>(p, v[4 * j + 0], n.x, nq), s0);
+    s1 = fmaf(c.y, epi_value<KIND>(p, v[4 * j + 1], n.y, nq), s1);
+    s2 = fmaf(c.z, epi_value<KIND>(p, v[4 * j + 2], n.z, nq), s2);
+    s3 = fmaf(c.w, epi_value<KIND>(p, v[4 * j + 3], n.w, nq), s3);
   }
+  return (double)((s0 + s1) + (s2 + s3));
 }
 
 template <int KIND>
@@ -222,7 +213,7 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
   uint64_t* t_full = b_empty + ST;    // 2
   uint64_t* t_empty = t_full + 2;     // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  unsigned char* meta = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [epilogue warp][32 floats | 32 doubles], 16-byte aligned
+  unsigned char* meta = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [epilogue warp][32 norms | 32 coefficients] float32, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TC_M;
@@ -306,15 +297,14 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
     const float nq = p.qn[q0 + qrow];
     // the metadata of this warp's 32 support rows is fetched one tile ahead (coalesced, one value per lane) and
     // staged in shared memory: the per-pair reads are then short-latency broadcasts instead of L1/L2 round trips
-    float* wn = reinterpret_cast<float*>(meta + (size_t)(warp - 2) * 384);
-    double* wc = reinterpret_cast<double*>(wn + 32);
-    float mn = 0.f;
-    double mc = 0.0;
+    float* wn = reinterpret_cast<float*>(meta + (size_t)(warp - 2) * 256);
+    float* wc = wn + 32;
+    float mn = 0.f, mc = 0.f;
     if (ntile > 0) {
       mn = __ldg(p.svn + tile_begin * TC_N + part * 32 + lane);
-      mc = __ldg(p.svc + tile_begin * TC_N + part * 32 + lane);
+      mc = (float)__ldg(p.svc + tile_begin * TC_N + part * 32 + lane);
     }
-    double sum = 0.0, sum1 = 0.0;
+    double sum = 0.0;
     for (int it = 0; it < ntile; ++it) {
       const int acc = it & 1;
       mbar_wait(&t_full[acc], (uint32_t)((it >> 1) & 1));
@@ -333,7 +323,7 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
       __syncwarp();
       if (it + 1 < ntile) {
         mn = __ldg(p.svn + s0 + TC_N + lane);
-        mc = __ldg(p.svc + s0 + TC_N + lane);
+        mc = (float)__ldg(p.svc + s0 + TC_N + lane);
       }
       if (p.debug & 1) {
 #pragma unroll
@@ -342,15 +332,14 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
         continue;
       }
       if (s0 + 32 <= p.nsv) {
-        accum32<KIND>(p, v, reinterpret_cast<const float4*>(wn), reinterpret_cast<const double2*>(wc), nq, sum, sum1);
+        sum += accum32<KIND>(p, v, reinterpret_cast<const float4*>(wn), reinterpret_cast<const float4*>(wc), nq);
       } else {   // last, ragged tile: padding rows carry coefficient 0, but their kernel value need not be finite
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (s0 + j < p.nsv) sum = fma(__ldg(p.svc + s0 + j), widen<KIND>(epi_value<KIND>(p, v[j], __ldg(p.svn + s0 + j), nq)), sum);
+          if (s0 + j < p.nsv) sum = fma(__ldg(p.svc + s0 + j), (double)epi_value<KIND>(p, v[j], __ldg(p.svn + s0 + j), nq), sum);
       }
       __syncwarp();   // every lane is done with the staged metadata before the next tile overwrites it
     }
-    sum += sum1;
     // the column parts of a query row meet in shared memory (the A tiles are dead by now: every MMA that read
     // them completed before the last t_full flipped)
     double* red = reinterpret_cast<double*>(a_hi);      // [3][128]
@@ -502,7 +491,7 @@ static int matvec_tc_core(cudaStream_t stream, const b2svm_kernel_desc& k, int d
   p.kp = KernelParams<float>{k.kind, (float)k.gamma, (float)k.coef0, (float)k.degree};
   TC_TRY(cudaMallocAsync(&partial, sizeof(double) * (size_t)ny * nb, stream));
   p.partial = partial;
-  const size_t smem = a_bytes + p.stages * b_stage + (size_t)(2 * p.stages + 8) * sizeof(uint64_t) + 32 + TC_EPI_WARPS * 384 + 1024;
+  const size_t smem = a_bytes + p.stages * b_stage + (size_t)(2 * p.stages + 8) * sizeof(uint64_t) + 32 + TC_EPI_WARPS * 256 + 1024;
 #define TC_LAUNCH(KIND)                                                                                             \
   do {                                                                                                              \
     TC_TRY(cudaFuncSetAttribute(matvec_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
