@@ -617,3 +617,30 @@ def test_rff_decision_on_tensor_cores(monkeypatch, nq, d, D):
     scale = np.abs(want).max()
     assert np.abs(outs["0"] - want).max() / scale < 1e-12
     assert np.abs(outs["2"] - want).max() / scale < 2e-5
+
+
+@pytest.mark.parametrize("variant", ["svr", "nusvc"])
+def test_macro_tiles_generic_kernel(monkeypatch, variant):
+    """The same grouping under the run-time-generic kernel: mirror problems (2l variables share l rows) and the nu
+    variant (four candidate types).  Grouped and ungrouped runs must agree bit for bit."""
+    torch, _, S, *_ = _mods()
+    monkeypatch.setenv("B2SVM_MAX_CTAS", "3")
+    out = []
+    for sub in ("1", "4"):
+        monkeypatch.setenv("B2SVM_SUB", sub)
+        if variant == "svr":
+            X, z = O.synth_regression(n=6001, d=24, seed=4)
+            l = X.shape[0]
+            y = np.r_[np.ones(l), -np.ones(l)]
+            p = np.r_[-z.astype(float), z.astype(float)]
+            func = S.QColumns(X, y, S.KernelSpec("rbf", 1.0 / 24), mirror=True, cache_bytes=0)
+            sol = S.SolverWithCache(p, y, 1.0, func=func)
+        else:
+            X, y01 = O.synth_classification(n=5003, d=20, seed=5)
+            y = np.where(y01 == 1, 1.0, -1.0)
+            func = S.QColumns(X, y, S.KernelSpec("rbf", 1.0 / 20), cache_bytes=0)
+            sol = S.NuSolverWithCache(np.zeros(len(y)), y, 0.5 * len(y), 1.0, func)
+        st = sol.solve(300)
+        assert st.n_iter == 300
+        out.append((sol.alpha.cpu().numpy().copy(), sol.neg_y_grad.cpu().numpy().copy()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
