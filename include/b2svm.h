@@ -148,7 +148,9 @@ int b2svm_bias_partials(b2svm_handle* h, double* out);
 /* decision_function core (svc.py:269-272, :436-439; svr.py:191-194, :297-300; oc_svm.py:108-111):
  *   out[q] = sum_s coef[s] * K(Xa[s], Xb[q])      (no n_a x n_b matrix is materialised)
  * Xa: dev [na][lda], Xb: dev [nb][ldb] (dtype x_dtype), coef: dev float64 [na], out: dev float64 [nb].
- * Rows with coef == 0 are skipped. */
+ * Rows with coef == 0 are skipped.  float32 rows with n_features <= 128 and at least 1024 queries and non-zero
+ * coefficients run on the tensor cores (tcgen05, 3xTF32: ~1e-6 of the output scale against float64); everything else
+ * on the FP32 / FP64 pipes.  The call synchronises the stream before it returns. */
 int b2svm_kernel_matvec(int32_t device, void* stream, const b2svm_kernel_desc* k, int32_t x_dtype,
                         int32_t n_features, const void* Xa, int64_t na, int64_t lda,
                         const void* Xb, int64_t nb, int64_t ldb, const double* coef, double* out);
@@ -158,7 +160,9 @@ int b2svm_kernel_matvec(int32_t device, void* stream, const b2svm_kernel_desc* k
 int b2svm_rff_transform(int32_t device, void* stream, int32_t x_dtype, const void* X, int64_t n,
                         int64_t ldx, int32_t d, const double* W, const double* b, int32_t D, double* out);
 
-/* z(q) . wz  without materialising z(q):  out[q] = sum_k sqrt(2/D) cos(x_q . W_k + b_k) * wz[k]. */
+/* z(q) . wz  without materialising z(q):  out[q] = sum_k sqrt(2/D) cos(x_q . W_k + b_k) * wz[k].
+ * float32 queries (n_features <= 128, nq >= 1024, D >= 256) run as a tcgen05 GEMM with a cos epilogue, argument error
+ * ~1e-6; float64 queries and small problems in float64 like b2svm_rff_transform. */
 int b2svm_rff_decision(int32_t device, void* stream, int32_t x_dtype, const void* Xq, int64_t nq,
                        int64_t ldx, int32_t d, const double* W, const double* b, int32_t D,
                        const double* wz, double* out);
