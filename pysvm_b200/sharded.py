@@ -207,6 +207,34 @@ def schedule_subproblems(sizes, world: int):
     return owner
 
 
+def exchange_subproblem_results(results: dict, sizes, owner, nstat: int, group=None) -> list:
+    """After the independent solves: ``results[k] = (stats_words, alpha, gradient)`` for the sub-problems this rank
+    solved (stats_words = the solve statistics as ``nstat`` float64 words).  One all-gather of a flat float64 payload
+    per rank -- laid out in sub-problem order, padded to the longest rank -- hands every rank every result.  Returns
+    the list of (stats_words, alpha, gradient) for ALL sub-problems, in sub-problem order."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lengths = [sum(nstat + 2 * sizes[k] for k in range(len(sizes)) if owner[k] == r) for r in range(world)]
+    payload = np.zeros(max(lengths) if lengths else 0)
+    o = 0
+    for k in range(len(sizes)):
+        if owner[k] != rank:
+            continue
+        st, a, g = results[k]
+        payload[o:o + nstat] = st
+        payload[o + nstat:o + nstat + sizes[k]] = a
+        payload[o + nstat + sizes[k]:o + nstat + 2 * sizes[k]] = g
+        o += nstat + 2 * sizes[k]
+    everything = all_gather_array(payload, group)                     # [world][max length]
+    out, offs = [], [0] * world
+    for k in range(len(sizes)):
+        r, o = owner[k], offs[owner[k]]
+        row = everything[r]
+        out.append((row[o:o + nstat].copy(), row[o + nstat:o + nstat + sizes[k]].copy(),
+                    row[o + nstat + sizes[k]:o + nstat + 2 * sizes[k]].copy()))
+        offs[r] = o + nstat + 2 * sizes[k]
+    return out
+
+
 _ENABLED = {"on": False, "group": None}
 
 

@@ -60,26 +60,19 @@ class deferred_solves:
         mine = [k for k in range(len(sizes)) if owner[k] == rank]
         stats = solve_batched([self.items[k][1] for k in mine], max_iter) if mine else []
         nstat = C.sizeof(N.SolveStats) // 8
-        lengths = [sum(nstat + 2 * sizes[k] for k in range(len(sizes)) if owner[k] == r) for r in range(world)]
-        payload = np.zeros(max(lengths))
-        o = 0
+        results = {}
         for k, st in zip(mine, stats):
             solver = self.items[k][1]
-            payload[o:o + nstat] = np.frombuffer(bytes(st), dtype=np.float64)
-            payload[o + nstat:o + nstat + sizes[k]] = solver.alpha.cpu().numpy()
-            payload[o + nstat + sizes[k]:o + nstat + 2 * sizes[k]] = solver.neg_y_grad.cpu().numpy()
-            o += nstat + 2 * sizes[k]
-        everything = sharded.all_gather_array(payload, group)            # [world][max length]
-        offs = [0] * world
+            results[k] = (np.frombuffer(bytes(st), dtype=np.float64), solver.alpha.cpu().numpy(),
+                          solver.neg_y_grad.cpu().numpy())
+        everything = sharded.exchange_subproblem_results(results, sizes, owner, nstat, group)
         for k, (est, solver, finish) in enumerate(self.items):
-            r, o = owner[k], offs[owner[k]]
-            row = everything[r]
-            st = N.SolveStats.from_buffer_copy(row[o:o + nstat].tobytes())
-            if r != rank:
-                solver.alpha = row[o + nstat:o + nstat + sizes[k]]
-                solver.neg_y_grad = row[o + nstat + sizes[k]:o + nstat + 2 * sizes[k]]
+            words, alpha, grad = everything[k]
+            st = N.SolveStats.from_buffer_copy(words.tobytes())
+            if owner[k] != rank:
+                solver.alpha = alpha
+                solver.neg_y_grad = grad
                 solver.last_stats = st
-            offs[r] = o + nstat + 2 * sizes[k]
             finish(st)
 
 

@@ -94,6 +94,16 @@ def _worker(rank, world, port, q):
         # bias partials merged over the group
         parts = SH.all_gather_array(np.full(18, float(rank)))
         assert parts.shape == (world, 18) and parts[:, 0].tolist() == list(range(world))
+        # results of independent sub-problems (one-vs-one fits) solved on different ranks reach every rank
+        sizes = [5, 3, 4, 6, 2]
+        owner = SH.schedule_subproblems(sizes, world)
+        mine = {k: (np.full(11, 100.0 * k), np.arange(sizes[k]) + 10.0 * k, -np.arange(sizes[k]) - 10.0 * k)
+                for k in range(len(sizes)) if owner[k] == rank}
+        allres = SH.exchange_subproblem_results(mine, sizes, owner, 11)
+        assert len(allres) == len(sizes)
+        for k, (st, a, g) in enumerate(allres):
+            assert np.array_equal(st, np.full(11, 100.0 * k))
+            assert np.array_equal(a, np.arange(sizes[k]) + 10.0 * k) and np.array_equal(g, -a)
         SH.enable()
         assert SH.active()
         SH.disable()
