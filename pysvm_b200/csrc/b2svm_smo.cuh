@@ -16,7 +16,9 @@
 // SASS UBLKCP) issued by a dedicated producer thread that runs ahead of the consumers across
 // iteration boundaries, so HBM keeps streaming while the exchange and the serial
 // select -> step chain are in flight.  When a CTA's slice fits in the ring it is loaded once and
-// stays resident in shared memory for the whole solve (small problems, multi-GPU shards).
+// stays resident in shared memory for the whole solve (small problems, multi-GPU shards).  Narrow rows move several
+// 32-row tiles per ring stage (one bulk copy, one ticket); the copies of the leading 48 MB of X carry an L2
+// evict_last hint so that part of every sweep is served from the 126 MB L2.
 //
 // Candidate exchange (one level, same code on one GPU and on a row-sharded box).  Every CTA writes, per
 // candidate type, one 16-byte record {g, idx, epoch<<3 | flags} and one 16-byte unit {alpha, epoch} into the
@@ -37,7 +39,6 @@ constexpr int NW = 11;                     // consumer warps per CTA (+1 produce
 constexpr int NTHREADS = (NW + 1) * 32;    // + one producer warp
 constexpr int MAX_STAGES = 64;
 constexpr int NCAND = 4;                   // up/low (C variant) or up+/low+/up-/low- (nu variant)
-constexpr int REC_STRIDE = 1;              // one 128-byte line per record (uint4 units): spreads the polling over L2 slices
 constexpr int TL_ITERS = 64, TL_SLOTS = 16; // debug timeline
 constexpr int DBG_EPOCHS = 2048;
 constexpr int TL_WARP_SLOTS = 4;           // + per-warp {start, end, tiles, wait} of one sweep
