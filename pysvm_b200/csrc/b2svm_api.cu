@@ -339,8 +339,6 @@ int launch(bool f64, int ch, bool cache, bool generic, const ProblemDev* probs_d
                  : launch_f32_plain(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream);
 }
 
-inline bool needs_generic(const b2svm_handle* h);
-
 inline bool needs_generic(const b2svm_handle* h) {
   return h->d.variant == B2SVM_SOLVER_NU || h->d.n_vars > h->d.n_rows;
 }
