@@ -135,3 +135,19 @@ def test_package_generators_equal_the_oracles():
     Xb, zb = O.synth_regression(n=2000, d=64, seed=0)
     assert np.array_equal(Xa, Xb) and np.array_equal(za, zb)
     assert np.array_equal(synth.oneclass(n=1000, d=32, seed=1), O.synth_oneclass(n=1000, d=32, seed=1))
+
+
+def test_host_std_every_small_length_and_block_edges():
+    """The pairwise tree has special cases below 8 elements, at the 128-element block size and at every halving
+    (sub-trees are rounded down to multiples of 8): sweep all short lengths and a few awkward long ones."""
+    from pysvm_b200 import _native as N
+    import ctypes as C
+    lib = N.load()
+    rng = np.random.default_rng(11)
+    lengths = list(range(1, 300)) + [1023, 1024, 1025, 4097, 65535, 65537, 131071, 262145, 1000003]
+    for dt, code in ((np.float32, N.F32), (np.float64, N.F64)):
+        for n in lengths:
+            x = (rng.standard_normal(n) * 2 - 0.5).astype(dt)
+            out = C.c_double()
+            N.check(lib.b2svm_host_std(x.ctypes.data, n, code, C.byref(out)))
+            assert dt(out.value) == x.std(), (dt, n)
