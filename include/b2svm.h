@@ -34,6 +34,9 @@ extern "C" {
 #endif
 
 #define B2SVM_ABI_VERSION 1
+/* b2svm_solve / b2svm_solve_batched accept max_iter in [0, B2SVM_MAX_ITER): the candidate records of the in-kernel
+ * exchange carry a 29-bit iteration tag.  Longer solves are chunked by the caller (state lives in alpha / neg_y_grad). */
+#define B2SVM_MAX_ITER (1ll << 29)
 
 enum {
   B2SVM_OK = 0,

@@ -8,6 +8,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_lib", "libb2svm.so")
 ABI_VERSION = 1
+MAX_ITER = 1 << 29          # B2SVM_MAX_ITER: iterations per b2svm_solve call (29-bit epoch tag in the exchange records)
 
 F32, F64 = 0, 1
 KERNEL_IDS = {"linear": 0, "poly": 1, "rbf": 2, "sigmoid": 3, "precomputed": 4}

@@ -28,6 +28,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-fmad=false",            # fused multiply-adds are explicit fma()/fmaf() calls only
     "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-ffp-contract=off",   # host code too: b2svm_host_std must round like numpy (no FMA contraction on aarch64 / -march=native)
     "-Xptxas", "-v",
 ]
 if os.environ.get("B2SVM_TIMELINE"):      # per-phase clock stamps inside the persistent kernel (scripts/gpu_timeline.py)

@@ -639,6 +639,7 @@ int b2svm_init_state(b2svm_handle* h, const double* p) {
 
 int b2svm_init_gradient(b2svm_handle* h, const double* p) {
   if (!h) return fail(B2SVM_E_INVALID, "null handle");
+  if (h->d.world > 1) return fail(B2SVM_E_UNSUPPORTED, "init_gradient is single-GPU only (a sharded handle holds its own rows of X; see sharded.rows_kernel_sum)");
   B2_CUDA(cudaSetDevice(h->d.device));
   const int64_t l = h->d.n_rows, nv = h->d.n_vars;
   const double* pu;
@@ -686,6 +687,7 @@ int b2svm_update(b2svm_handle* h, int64_t i, int64_t j, double* delta_i, double*
 int b2svm_kernel_column(b2svm_handle* h, int64_t i, double* out) {
   if (!h || !out) return fail(B2SVM_E_INVALID, "null argument");
   if (i < 0 || i >= h->d.n_vars) return fail(B2SVM_E_INVALID, "index out of range");
+  if (h->d.world > 1) return fail(B2SVM_E_UNSUPPORTED, "kernel_column is single-GPU only (a sharded handle holds its own rows of X)");
   B2_CUDA(cudaSetDevice(h->d.device));
   const int64_t l = h->d.n_rows;
   if (h->precomputed) {
@@ -711,6 +713,7 @@ int b2svm_kernel_column(b2svm_handle* h, int64_t i, double* out) {
 int b2svm_solve(b2svm_handle* h, int64_t max_iter, b2svm_solve_stats* stats) {
   if (!h) return fail(B2SVM_E_INVALID, "null handle");
   if (max_iter < 0) return fail(B2SVM_E_INVALID, "max_iter < 0");
+  if (max_iter >= B2SVM_MAX_ITER) return fail(B2SVM_E_UNSUPPORTED, "max_iter must be below 2^29 per call (mailbox records carry a 29-bit epoch tag)");
   SolveResult r;
   float ms = 0.f;
   int rc = run_solver(h, max_iter, -1, -1, &r, &ms);
@@ -805,6 +808,7 @@ int b2svm_rho_b(b2svm_handle* h, double* rho, double* b) {
 
 int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max_iter, b2svm_solve_stats* stats) {
   if (!handles || count <= 0) return fail(B2SVM_E_INVALID, "empty batch");
+  if (max_iter < 0 || max_iter >= B2SVM_MAX_ITER) return fail(B2SVM_E_UNSUPPORTED, "max_iter must be in [0, 2^29) per call");
   b2svm_handle* h0 = handles[0];
   B2_CUDA(cudaSetDevice(h0->d.device));
   for (int k = 0; k < count; ++k) {
@@ -848,6 +852,7 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h0->ev0, h0->ev1);
     for (int k = 0; rc == B2SVM_OK && k < count; ++k) {
+      handles[k]->cache_used = R[k].cache_used;   // the device slot table persists across launches (as in run_solver)
       if (R[k].status != 0) rc = fail(B2SVM_E_TIMEOUT, "device watchdog tripped in a batched solve");
       if (stats) {
         memset(&stats[k], 0, sizeof(stats[k]));

@@ -39,13 +39,22 @@ class Shard:
         return slice(self.row_offset, self.row_offset + self.n_local)
 
 
+def rows_per_rank(n_global: int, world: int) -> int:
+    return (-(-n_global // world) + 31) // 32 * 32
+
+
+def shardable(n_global: int, world: int) -> bool:
+    """True when EVERY rank of `world` owns at least one row.  A pure function of (n, world): all ranks take the
+    same decision without talking (a rank that raised on its own would leave its peers waiting in a collective)."""
+    return world >= 1 and (world - 1) * rows_per_rank(n_global, world) < n_global
+
+
 def plan(n_global: int, world: int, rank: int) -> Shard:
-    """Equal slices of whole 32-row tiles: rank r owns rows [r*rpr, min(n, (r+1)*rpr))."""
-    rpr = (-(-n_global // world) + 31) // 32 * 32
-    s = Shard(rank, world, n_global, rpr)
-    if s.n_local <= 0:
-        raise ValueError(f"rank {rank} of {world} would own no rows of {n_global}")
-    return s
+    """Equal slices of whole 32-row tiles: rank r owns rows [r*rpr, min(n, (r+1)*rpr)).  Raises on every rank alike
+    when the problem is too small for this many GPUs (estimators check `active_for` first and stay on one GPU)."""
+    if not shardable(n_global, world):
+        raise ValueError(f"{n_global} rows cannot be dealt to {world} GPUs in whole 32-row tiles without an empty rank")
+    return Shard(rank, world, n_global, rows_per_rank(n_global, world))
 
 
 def local_vector(v: np.ndarray, shard: Shard, mirror: bool) -> np.ndarray:
@@ -145,9 +154,12 @@ class ShardedSolver(SolverWithCache):
 
     def solve(self, max_iter: int, func=None):
         eng = self._need(func)
-        eng.prepare()                          # clear mailbox, publish alpha slice (synchronises the stream)
-        dist.barrier(group=self.group)         # no peer may start before every mailbox is clean
-        st = eng.solve(max_iter)
+
+        def sync_ranks():
+            eng.prepare()                          # clear mailbox, publish alpha slice (synchronises the stream)
+            dist.barrier(group=self.group)         # no peer may start before every mailbox is clean
+
+        st = eng.solve(max_iter, before_launch=sync_ranks)
         self.last_stats = st
         return st
 
@@ -250,6 +262,11 @@ def disable():
 
 def active() -> bool:
     return _ENABLED["on"] and dist.is_available() and dist.is_initialized() and dist.get_world_size(_ENABLED["group"]) > 1
+
+
+def active_for(n_rows: int) -> bool:
+    """Route a fit of `n_rows` training rows through the sharded solve?  The same answer on every rank."""
+    return active() and shardable(n_rows, dist.get_world_size(_ENABLED["group"]))
 
 
 def gather_variables(v_local: np.ndarray, shard: Shard, mirror: bool, group=None) -> np.ndarray:

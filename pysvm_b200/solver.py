@@ -198,10 +198,27 @@ class _Engine:
         N.check(self.lib.b2svm_kernel_column(self.h, int(i), out.data_ptr()))
         return out
 
-    def solve(self, max_iter: int) -> N.SolveStats:
-        st = N.SolveStats()
-        N.check(self.lib.b2svm_solve(self.h, int(max_iter), C.byref(st)))
-        return st
+    def solve(self, max_iter: int, before_launch=None) -> N.SolveStats:
+        """b2svm_solve; a loop longer than B2SVM_MAX_ITER - 1 iterations is issued in chunks (the state lives in
+        alpha / neg_y_grad, so a chunk boundary is invisible to the result).  ``before_launch`` runs ahead of every
+        launch (the sharded solver prepares the mailboxes and synchronises the ranks there)."""
+        left, total = int(max_iter), None
+        while True:
+            chunk = min(left, N.MAX_ITER - 1)
+            if before_launch is not None:
+                before_launch()
+            st = N.SolveStats()
+            N.check(self.lib.b2svm_solve(self.h, chunk, C.byref(st)))
+            done_now = st.n_iter
+            if total is None:
+                total = st
+            else:
+                for name in ("n_iter", "cold_sweeps", "cache_hits", "cache_misses", "algorithmic_bytes", "device_ms", "launches"):
+                    setattr(st, name, getattr(total, name) + getattr(st, name))
+                total = st
+            left -= chunk
+            if left <= 0 or total.converged or done_now < chunk:
+                return total
 
     def rho(self) -> float:
         r = C.c_double()

@@ -32,7 +32,7 @@ class OneClassSVM(BiNuSVC):
         X = np.array(X)
         l, self.n_features = X.shape
         from .. import sharded
-        if sharded.active() and not self.rff:
+        if sharded.active_for(X.shape[0]) and not self.rff:
             return self._fit_oneclass_sharded(X, sharded)
         p = np.zeros(l)
         y = np.ones(l)

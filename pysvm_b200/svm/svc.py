@@ -235,7 +235,7 @@ class BiKernelSVC(BiLinearSVC):
         l, self.n_features = X.shape
         p = -np.ones(l)
         from .. import sharded
-        if sharded.active() and not self.rff and not (_PENDING is not None and l <= BATCH_MAX_ROWS):
+        if sharded.active_for(l) and not self.rff and not (_PENDING is not None and l <= BATCH_MAX_ROWS):
             return self._fit_sharded(X, y, sharded)
         func, spec, rff = self._columns(X, y)
         solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func, max_iter_hint=self.max_iter)
@@ -337,7 +337,7 @@ class BiNuSVC(BiKernelSVC):
         y[y != 1] = -1
         l, self.n_features = X.shape
         from .. import sharded
-        if sharded.active() and not self.rff and not (_PENDING is not None and l <= BATCH_MAX_ROWS):
+        if sharded.active_for(l) and not self.rff and not (_PENDING is not None and l <= BATCH_MAX_ROWS):
             group = sharded._ENABLED["group"]
             spec, _ = self.register_kernel(host_std(X))
             solver, shard, stats = sharded.fit_nusvc_sharded(X, (y == 1).astype(int), self.nu, spec, self.tol, self.max_iter, group)

@@ -62,7 +62,7 @@ class KernelSVR(BiKernelSVC):
         X, z = np.array(X), np.array(y)
         l, self.n_features = X.shape
         from .. import sharded
-        if sharded.active() and not self.rff:
+        if sharded.active_for(l) and not self.rff:
             from ..solver import host_std
             group = sharded._ENABLED["group"]
             spec, _ = self.register_kernel(host_std(X))
@@ -101,7 +101,7 @@ class NuSVR(KernelSVR):
         X, z = np.array(X), np.array(y)
         l, self.n_features = X.shape
         from .. import sharded
-        if sharded.active() and not self.rff:
+        if sharded.active_for(l) and not self.rff:
             from ..solver import host_std
             group = sharded._ENABLED["group"]
             spec, _ = self.register_kernel(host_std(X))

@@ -221,6 +221,43 @@ def s5():
     save("s5_synth_oneclass_n2000", **pack(s, tr, est, X[:256], keep_trace=2000, rho=s.calculate_rho()))
 
 
+def pack_big(s, tr, est, Xq, stride=16, **more):
+    """Full-size fixtures: alpha is sparse after a capped run (indices + values), the gradient is kept at the
+    variables the run touched plus every `stride`-th variable, so the file stays small."""
+    a = s.alpha
+    nz = np.flatnonzero(a)
+    touched = np.unique(tr[:, :2].astype(np.int64).reshape(-1))
+    gidx = np.unique(np.r_[touched, np.arange(0, a.shape[0], stride)])
+    return dict(n_iter=np.int64(tr.shape[0]), n_vars=np.int64(a.shape[0]), alpha_idx=nz, alpha_val=a[nz],
+                g_idx=gidx, g_val=s.neg_y_grad[gidx], trace=tr, dec=np.asarray(est.decision_function(Xq)), **more)
+
+
+def s3full():
+    """BASELINE configs[2] at its real size (n=200000, d=128, float32), capped at 1000 iterations."""
+    X, y = O.synth_classification(n=200_000, d=128, seed=0)
+    est = BiKernelSVC(max_iter=1000)
+    s, tr, _ = run(est, X, y)
+    save("s3_full_n200000_cap1000", **pack_big(s, tr, est, X[:256], rho=s.calculate_rho()))
+
+
+def s4full():
+    """BASELINE configs[3] at its real size (l=100000, d=64 -> 200000 variables), KernelSVR capped at 200 iterations."""
+    X, z = O.synth_regression(n=100_000, d=64, seed=0)
+    est = KernelSVR(max_iter=200)
+    s, tr, _ = run(est, X, z)
+    save("s4_full_svr_l100000_cap200", **pack_big(s, tr, est, X[:256], rho=s.calculate_rho()))
+
+
+def s5big():
+    """configs[4]-shaped one-class problem at n=10000 (the largest the O(l^2) reference start finishes quickly), converged."""
+    X = O.synth_oneclass(n=10_000, d=32, seed=1)
+    est = OneClassSVM(max_iter=10 ** 7)
+    s, tr, _ = run(est, X)
+    save("s5_synth_oneclass_n10000", n_iter=np.int64(tr.shape[0]), alpha=s.alpha.copy(), g=s.neg_y_grad.copy(),
+         trace_head=tr[:4000], dec=np.asarray(est.decision_function(X[:512])), pred=est.predict(X[:512]),
+         rho=s.calculate_rho())
+
+
 def lin():
     X, y = breast_cancer()
     est = BiLinearSVC(max_iter=10 ** 6)
@@ -249,7 +286,8 @@ def rffvec():
     save("rff_vectors", X=X, w=r.w, b=r.b, Z=r.transform(X))
 
 
-ALL = dict(g1=g1, g3=g3, g4=g4, g5=g5, g6=g6, g7=g7, g8=g8, s3=s3, s4=s4, s5=s5, lin=lin, rffvec=rffvec)
+ALL = dict(g1=g1, g3=g3, g4=g4, g5=g5, g6=g6, g7=g7, g8=g8, s3=s3, s4=s4, s5=s5, lin=lin, rffvec=rffvec,
+           s3full=s3full, s4full=s4full, s5big=s5big)
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or ALL):

@@ -63,10 +63,11 @@ def test_kernel_column_mirror():
 
 # ------------------------------------------------------------------------------ step-wise API
 def test_g4_stepwise_trace(golden):
-    """select / update one step at a time reproduce the reference's (i, j, delta) trace, including
-    the lowest-index tie-break at iteration 0.  At step 8 the reference's g[5] and g[6]
-    are bit-identical (an exact tie decided by libm's rounding of exp), so the pair-for-pair check
-    covers the 8 steps before it; the solution is then compared within tolerance."""
+    """select / update one step at a time reproduce the reference's (i, j, delta) trace, including the lowest-index
+    tie-break at iteration 0.  All 22 steps are compared.  Where a pair differs from the reference's, the
+    test demands that it is a genuine tie: the two candidates' gradients in the reference trajectory (replayed by the
+    oracle up to that step) agree to a few ulp, i.e. the choice is decided by the last bit of exp (libm vs device).
+    After such a tie the trajectories may part; the solution is then compared within tolerance."""
     torch, _, S, *_ = _mods()
     g = golden("g4_tiny_trace")
     X, y01 = g["X"], g["y"]
@@ -74,14 +75,28 @@ def test_g4_stepwise_trace(golden):
     func = S.QColumns(X, y, S.KernelSpec("rbf", 0.5))
     solver = S.SolverWithCache(-np.ones(8), y, 1.0, 1e-5, func=func)
     trace = g["trace_head"]
-    for k in range(8):
+    n_ref = int(g["n_iter"])
+    assert trace.shape[0] == n_ref == 22
+    spec = O.KernelSpec(kind="rbf", gamma=0.5)
+    ost = O.fresh_state(-np.ones(8), y, 1.0, 1e-5)
+    cols = O.ColumnSource(X, y, O.make_kernel(spec), mirror=False)
+    matched = 0
+    for k in range(n_ref):
         i, j = solver.working_set_select()
-        assert (i, j) == (int(trace[k, 0]), int(trace[k, 1])), k
+        ri, rj = int(trace[k, 0]), int(trace[k, 1])
+        if (i, j) != (ri, rj):
+            assert O.select_pair(ost) == (ri, rj)                       # the oracle still follows the reference here
+            eps = 8 * np.finfo(np.float64).eps * max(1.0, np.abs(ost.g).max())
+            assert abs(ost.g[i] - ost.g[ri]) <= eps and abs(ost.g[j] - ost.g[rj]) <= eps, (k, i, j, ri, rj, ost.g)
+            break
         di, dj = solver.update(i, j)
         np.testing.assert_allclose([di, dj], trace[k, 2:], rtol=0, atol=1e-12)
+        O.take_step(ost, ri, rj, cols(ri), cols(rj))
+        matched += 1
+    assert matched >= 8                                                   # the documented exact tie sits at step 8
     st = solver.solve(10 ** 4)
     assert st.converged == 1 and solver.working_set_select() == (-1, -1)
-    iters_close(8 + st.n_iter, int(g["n_iter"]), frac=0.15)       # 22 in the reference
+    iters_close(matched + st.n_iter, n_ref, frac=0.15)
     rel_close(solver.alpha.cpu().numpy(), g["alpha"], atol=1e-5)
     rel_close(solver.calculate_rho(), float(g["rho"]), atol=1e-5)
 
@@ -302,6 +317,90 @@ def test_rff_vectors(golden):
     np.testing.assert_allclose(r.transform(g["X"]), g["Z"], rtol=0, atol=1e-13)
 
 
+# ------------------------------------------------------------------------------ BASELINE configs at their REAL sizes
+def _sparse_alpha(g):
+    a = np.zeros(int(g["n_vars"]))
+    a[g["alpha_idx"]] = g["alpha_val"]
+    return a
+
+
+def _replay(solver, trace, upto):
+    """One fused iteration per launch: stats.last_i / last_j before the launch is the pair the launch takes, so every
+    working pair and step of the device solve is observable and compared with the reference's trace."""
+    nxt = solver.working_set_select()
+    for k in range(upto):
+        assert nxt == (int(trace[k, 0]), int(trace[k, 1])), (k, nxt, trace[k])
+        st = solver.solve(1)
+        assert st.n_iter == 1
+        np.testing.assert_allclose([st.last_delta_i, st.last_delta_j], trace[k, 2:], rtol=1e-4, atol=1e-7)
+        nxt = (st.last_i, st.last_j)
+    return nxt
+
+
+def test_s3_full_size_capped_trace(golden):
+    """configs[2] at its real size (n=200000, d=128 float32, max_iter=1000, fixture from the live reference): the
+    first 300 working pairs are replayed one by one, the remaining 700 iterations run fused; alpha must be equal, the
+    gradient within the float32 kernel tolerance, rho and decision values within 1e-4."""
+    torch, _, S, svc, _, _ = _mods()
+    from pysvm_b200 import synth
+    g = golden("s3_full_n200000_cap1000")
+    X, y01 = synth.classification(n=200_000, d=128, seed=0)
+    y = np.where(y01 == 1, 1.0, -1.0)
+    tr = g["trace"]
+    func = S.QColumns(X, y, S.KernelSpec("rbf", 1 / (128 * X.std())), cache_bytes=0)
+    solver = S.SolverWithCache(-np.ones(len(y)), y, 1.0, func=func)
+    nxt = _replay(solver, tr, 300)
+    st = solver.solve(700)
+    assert st.n_iter == 700
+    a = solver.alpha.cpu().numpy()
+    np.testing.assert_allclose(a, _sparse_alpha(g), rtol=1e-4, atol=1e-6)
+    np.testing.assert_array_equal(np.flatnonzero(a), g["alpha_idx"])                 # identical support set
+    rel_close(solver.neg_y_grad.cpu().numpy()[g["g_idx"]], g["g_val"], atol=1e-4)
+    rel_close(solver.calculate_rho(), float(g["rho"]), atol=1e-4)
+    # the same fit through the estimator: 1000 fused iterations, decision values of the fixture's 256 query rows
+    est = svc.BiKernelSVC(max_iter=1000).fit(X, y01)
+    assert est.n_iter_ == 1000
+    np.testing.assert_array_equal(est.support_, g["alpha_idx"])
+    rel_close(est.alpha_[g["alpha_idx"]], g["alpha_val"], atol=1e-6)
+    rel_close(est.decision_function(X[:256]), g["dec"], atol=1e-4)
+
+
+def test_s4_full_size_svr_trace(golden):
+    """configs[3] at its real size (l=100000, d=64 -> 200000 variables), KernelSVR, the reference's 200 iterations
+    replayed pair by pair (mirror variables: one row sweep serves both halves)."""
+    torch, _, S, _, svr, _ = _mods()
+    from pysvm_b200 import synth
+    g = golden("s4_full_svr_l100000_cap200")
+    X, z = synth.regression(n=100_000, d=64, seed=0)
+    l = X.shape[0]
+    y = np.r_[np.ones(l), -np.ones(l)]
+    p = np.r_[-z.astype(np.float64), z.astype(np.float64)]          # eps = 0 (svr.py:166-172)
+    func = S.QColumns(X, y, S.KernelSpec("rbf", 1 / (64 * X.std())), mirror=True, cache_bytes=0)
+    solver = S.SolverWithCache(p, y, 1.0, func=func)
+    _replay(solver, g["trace"], 200)
+    a = solver.alpha.cpu().numpy()
+    np.testing.assert_allclose(a, _sparse_alpha(g), rtol=1e-4, atol=1e-6)
+    rel_close(solver.neg_y_grad.cpu().numpy()[g["g_idx"]], g["g_val"], atol=1e-4)
+    est = svr.KernelSVR(max_iter=200).fit(X, z)
+    assert est.n_iter_ == 200
+    rel_close(est.rho_, float(g["rho"]), atol=1e-4)
+    rel_close(est.predict(X[:256]), g["dec"], atol=1e-4)
+
+
+def test_s5_oneclass_n10000(golden):
+    """configs[4]-shaped one-class problem at n=10000 to convergence."""
+    *_, oc = _mods()
+    from pysvm_b200 import synth
+    X = synth.oneclass(n=10_000, d=32, seed=1)
+    g = golden("s5_synth_oneclass_n10000")
+    est = oc.OneClassSVM(max_iter=10 ** 7).fit(X)
+    iters_close(est.n_iter_, int(g["n_iter"]))
+    rel_close(est.alpha_, g["alpha"], atol=1e-4)
+    rel_close(est.rho_, float(g["rho"]))
+    rel_close(est.decision_function(X[:512]), g["dec"], atol=1e-4)
+    np.testing.assert_array_equal(est.predict(X[:512]), g["pred"])
+
+
 # ------------------------------------------------------------------------------ full-size properties
 def test_full_size_invariants():
     """BASELINE.json configs[2] shape (n=200k, d=128, float32): after 2000 fused iterations the
@@ -362,6 +461,31 @@ def test_column_cache_survives_a_refit_on_the_same_handle():
     assert b.cold_sweeps < a.cold_sweeps          # columns computed by the first fit are reused
 
 
+def test_batched_solve_keeps_the_cache_bookkeeping_of_every_handle():
+    """b2svm_solve_batched fills the column caches of its handles; a later solve on one of those handles must go on
+    from the slots already handed out (the device slot table persists), not restart at slot 0 and read another
+    row's column.  Re-solving after a batched solve must reproduce a fresh solve bit for bit."""
+    torch, _, S, *_ = _mods()
+    sols, fresh = [], []
+    for seed in (11, 12, 13):
+        X, y01 = O.synth_classification(n=700 + 100 * (seed - 11), d=64, seed=seed)
+        y = np.where(y01 == 1, 1.0, -1.0)
+        mk = lambda: S.SolverWithCache(-np.ones(len(y)), y, 1.0, func=S.QColumns(X, y, S.KernelSpec("rbf", 0.01)),
+                                       max_iter_hint=10 ** 6)
+        sols.append(mk())
+        fresh.append(mk())
+    stats = S.solve_batched(sols, 10 ** 6)
+    for sol, ref, st in zip(sols, fresh, stats):
+        r = ref.solve(10 ** 6)
+        assert r.n_iter == st.n_iter
+        assert torch.equal(ref.alpha, sol.alpha)
+        sol._engine.init_state(sol.p)                 # a second fit on the same handle, now through b2svm_solve
+        again = sol.solve(10 ** 6)
+        assert again.n_iter == r.n_iter and torch.equal(ref.alpha, sol.alpha)
+        assert torch.equal(ref.neg_y_grad, sol.neg_y_grad)
+        assert again.cold_sweeps <= r.cold_sweeps     # columns cached by the batched solve are found again
+
+
 # ------------------------------------------------------------------------------ batched one-vs-one
 def test_ovo_subproblems_are_solved_in_one_batched_launch(golden, digits):
     """KernelSVC(ovo) on digits: sklearn builds the 45 sub-problems, one persistent launch solves them
@@ -408,10 +532,10 @@ def test_readme_accuracy_table_digits_and_breast_cancer():
         for j, model in enumerate((P.LinearSVC, P.KernelSVC, P.NuSVC)):
             with contextlib.redirect_stdout(io.StringIO()):
                 acc = model(n_jobs=6, max_iter=1000).fit(trX, trY).score(teX, teY)
-            # RBF estimators: at most one test sample of slack.  LinearSVC stops at max_iter=1000 far from
-            # convergence on a kernel whose SMO trajectory is chaotic: the truncated
+            # RBF estimators: the README figure exactly (identical test labels).  LinearSVC stops at max_iter=1000
+            # far from convergence on a kernel whose SMO trajectory is chaotic: the truncated
             # iterate differs, so its accuracy is held to 1.5 points.
-            slack = 0.015 if model is P.LinearSVC else 1.5 / len(teY)
+            slack = 0.015 if model is P.LinearSVC else 1e-8
             assert abs(acc - want[name][j]) <= slack + 1e-9, (name, model.__name__, acc, want[name][j])
 
 

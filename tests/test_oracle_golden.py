@@ -147,3 +147,42 @@ def test_oneclass_alpha0_quirk():
     assert a[:19].tolist() == [1.0] * 19 and a[19] == 0.0 and a[20] == 1.0 and a[21:].sum() == 0
     with pytest.raises(UnboundLocalError):
         O.oneclass_alpha0(0.001, 100)
+
+
+# ------------------------------------------------------------------------------ BASELINE configs at their real sizes
+def test_s3_full_size_head(golden):
+    """configs[2] at n=200000: the oracle's first 40 working pairs / steps equal the reference's (the full 1000
+    iterations of the fixture take minutes on the host; the GPU parity test replays all of them)."""
+    from pysvm_b200 import synth
+    g = golden("s3_full_n200000_cap1000")
+    X, y = synth.classification(n=200_000, d=128, seed=0)
+    fit = O.fit_csvc(X, y, max_iter=40, trace=True)
+    tr = np.array(fit.trace, dtype=np.float64).reshape(-1, 4)
+    np.testing.assert_array_equal(tr[:, :2], g["trace"][:40, :2])
+    np.testing.assert_allclose(tr[:, 2:], g["trace"][:40, 2:], **TIGHT)
+
+
+def test_s4_full_size_svr(golden):
+    """configs[3] at l=100000 (200000 variables), KernelSVR capped at 200 iterations: all pairs, steps, alpha, gradient."""
+    from pysvm_b200 import synth
+    g = golden("s4_full_svr_l100000_cap200")
+    X, z = synth.regression(n=100_000, d=64, seed=0)
+    fit = O.fit_svr(X, z, max_iter=200, trace=True)
+    tr = np.array(fit.trace, dtype=np.float64).reshape(-1, 4)
+    np.testing.assert_array_equal(tr[:, :2], g["trace"][:, :2])
+    np.testing.assert_allclose(tr[:, 2:], g["trace"][:, 2:], **TIGHT)
+    alpha = np.zeros(int(g["n_vars"]))
+    alpha[g["alpha_idx"]] = g["alpha_val"]
+    np.testing.assert_allclose(fit.alpha, alpha, **TIGHT)
+    np.testing.assert_allclose(fit.g[g["g_idx"]], g["g_val"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(fit.rho, float(g["rho"]), rtol=0, atol=1e-10)
+
+
+def test_s5_oneclass_n10000(golden):
+    """configs[4]-shaped one-class problem at n=10000, converged (2545 iterations in the reference)."""
+    from pysvm_b200 import synth
+    g = golden("s5_synth_oneclass_n10000")
+    X = synth.oneclass(n=10_000, d=32, seed=1)
+    fit = O.fit_oneclass(X, max_iter=10 ** 7, trace=True)
+    check(fit, g, X[:512])
+    np.testing.assert_array_equal(fit.predict(X[:512]), g["pred"])
