@@ -73,7 +73,7 @@ typedef struct b2svm_problem_desc {
   int64_t n_rows;          /* l: rows of X                                                  */
   int32_t n_features;      /* d                                                             */
   int32_t x_dtype;         /* B2SVM_F32 / B2SVM_F64: kernel values are evaluated in this type */
-  const void* X;           /* dev, row-major [n_rows][ldx]; with world > 1: ALL n_rows_global rows  */
+  const void* X;           /* dev, row-major [n_rows][ldx] (with world > 1: this shard's rows only)  */
   int64_t ldx;             /* leading dimension of X in elements                            */
   int64_t n_vars;          /* n_rows, or 2*n_rows (mirror: vars t and t+l share row t)      */
   int32_t variant;         /* B2SVM_SOLVER_C / B2SVM_SOLVER_NU                              */
@@ -185,9 +185,18 @@ int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles /* world * 64 
  * Shards are equal slices of whole 32-row tiles: rank r sweeps global rows
  * [r*rpr, min(n, (r+1)*rpr)), rpr = roundup32(ceil(n_rows_global / world)), and owns the matching slices of
  * y, alpha, neg_y_grad (a mirror problem keeps [first half | second half] of its LOCAL rows) and of every
- * cached column.  X itself (read-only) is given in full to every rank: the two winning rows of an iteration
- * are then local reads and only 16-byte candidate records cross NVLink. */
+ * cached column, AND ONLY THOSE ROWS of X (desc.X = the shard's rows, n_rows of them): the CTA that owns a GPU's
+ * winning candidate pushes record + alpha + norm + the row itself into every GPU's box, so the two selected rows
+ * reach all ranks with the exchange and nothing else crosses NVLink. */
 int b2svm_prepare(b2svm_handle* h);
+
+/* Test / bring-up entry: the `world` ranks of a row-sharded solve emulated on ONE GPU.  handles[r] must have been
+ * created with rank = r, world = `world`, all on the same device and stream, with max_ctas <= num_sms / world; they run
+ * as the CTA groups of one cooperative launch and exchange candidates through each other's level-2 boxes in local
+ * memory (no CUDA IPC, no b2svm_mailbox_attach / b2svm_prepare needed).  Same device code as the multi-GPU solve.
+ * stats: [world]. */
+int b2svm_solve_ranks_on_one_gpu(b2svm_handle* const* handles, int32_t world, int64_t max_iter,
+                                 b2svm_solve_stats* stats);
 
 /* Host helper of register_kernel (svc.py:212-217): gamma='scale' is 1 / (n_features * X.std()).  Population
  * standard deviation of n_elements contiguous host values, bit-identical to numpy's X.std() on a C-contiguous

@@ -39,21 +39,40 @@ __global__ void pad_rows_kernel(const T* __restrict__ src, int64_t ld, T* __rest
   }
 }
 
-// |x_r|^2 in T, one warp per row (reference: (x**2).sum(1), svc.py:231)
+// |x_r|^2 in T (reference: (x**2).sum(1), svc.py:231) and K(x_r, x_r) in T, one warp per row.  The diagonal is
+// constant over the solve, so the select -> step chain reads it instead of re-evaluating it for every winner.
 template <typename T>
-__global__ void row_norms_kernel(const T* __restrict__ X, int64_t l, int dp, T* __restrict__ norms) {
+__global__ void row_norms_kernel(const T* __restrict__ X, int64_t l, int dp, T* __restrict__ norms, T* __restrict__ kdiag,
+                                 KernelParams<T> kp) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int EPC = 16 / (int)sizeof(T);   // elements per 16-byte chunk
   for (int64_t r = warp; r < l; r += nwarps) {
-    T s = 0;
+    T s = 0, dd = 0;
     for (int c = lane; c < dp; c += 32) {
       const T v = X[r * dp + c];
       s += v * v;
     }
+    // x.x for the diagonal in the summation order the persistent kernel uses for x_i.x_j (lane owns the 16-byte
+    // chunks lane, lane + 32, ...; fused multiply-add along each chunk; xor-butterfly over the lanes)
+    for (int cc = lane; cc * EPC < dp; cc += 32)
+      for (int e = 0; e < EPC; ++e) {
+        const T v = X[r * dp + cc * EPC + e];
+        dd = fma(v, v, dd);
+      }
     s = warp_sum(s);
-    if (lane == 0) norms[r] = s;
+    dd = warp_sum(dd);
+    if (lane == 0) {
+      norms[r] = s;
+      kdiag[r] = kernel_value(kp, dd, s, s);
+    }
   }
+}
+
+template <typename T>
+__global__ void diag_precomputed_kernel(const T* __restrict__ K, int64_t l, T* __restrict__ kdiag) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < l; r += (int64_t)gridDim.x * blockDim.x) kdiag[r] = K[r * l + r];
 }
 
 __global__ void refresh_flags_kernel(const double* __restrict__ y, const double* __restrict__ alpha, double C,
@@ -225,6 +244,7 @@ struct b2svm_handle {
   void* Xown = nullptr;         // padded copy (nullptr when the caller's X is used in place)
   const void* Xuse = nullptr;
   void* norms = nullptr;
+  void* kdiag = nullptr;
   uint8_t* flags = nullptr;
   int* abort_flag = nullptr;
   SolveResult* result = nullptr;
@@ -240,12 +260,12 @@ struct b2svm_handle {
   long long ntiles = 0;
   size_t smem_bytes = 0;
   int launches = 0;
-  // ---- candidate mailbox [2][world * num_sms][NCAND][2] x 16 B; with several GPUs it is shared over CUDA IPC
+  // ---- level-1 mailbox (MBOX_L1_BYTES) + level-2 box (MBOX_L2_BYTES, world > 1: shared over CUDA IPC)
   unsigned char* block = nullptr;
   size_t block_bytes = 0;
   long long rows_per_rank = 0;
   std::vector<void*> peer_blocks;          // opened IPC mappings (nullptr for this rank)
-  void** peer_tables = nullptr;            // device: [world] mailbox pointer of every rank (own entry = block)
+  void** peer_tables = nullptr;            // device: [world] level-2 box of every rank (own entry = block + MBOX_L1_BYTES)
   bool attached = false, prepared = false;
   bool precomputed = false;       // kernel.kind == 4: X is the kernel matrix itself and doubles as a full cache
   void* cache = nullptr;          // Q-column cache [cache_slots][n_rows] in the input dtype
@@ -256,6 +276,37 @@ struct b2svm_handle {
 };
 
 namespace {
+
+// Handle buffers come from the stream-ordered allocator, whose pool keeps freed memory for the next handle: a fit is
+// create -> solve -> destroy, and ~15 cudaMalloc / cudaFree pairs (each a device-wide synchronisation, and slow on
+// some hosts) used to cost more than the data transfer.  Only the level-2 box of a multi-GPU handle stays a plain
+// cudaMalloc: CUDA IPC exports whole cudaMalloc allocations.
+template <typename P>
+inline cudaError_t pool_alloc(P** p, size_t bytes, cudaStream_t stream) {
+  if (getenv("B2SVM_NO_POOL")) return cudaMalloc(reinterpret_cast<void**>(p), bytes ? bytes : 1);
+  keep_pool_memory();
+  return cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 1, stream);
+}
+inline void pool_free(void* p, cudaStream_t stream) {
+  if (!p) return;
+  if (getenv("B2SVM_NO_POOL")) cudaFree(p);
+  else cudaFreeAsync(p, stream);
+}
+inline int sm_count(int device) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device] > 0) return cached[device];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) n = 0;
+  if (device >= 0 && device < 64) cached[device] = n;
+  return n;
+}
+// pinned landing zone for the small device -> host result copies, one per host thread (handles of different threads
+// run concurrently; a handle is not thread-safe)
+inline SolveResult* pinned_result() {
+  static thread_local SolveResult* buf = nullptr;
+  if (!buf && cudaMallocHost(&buf, sizeof(SolveResult) * 16) != cudaSuccess) buf = nullptr;
+  return buf;
+}
 
 inline int grid_for(int64_t n, int block = 256, int cap = 148 * 8) {
   int64_t g = (n + block - 1) / block;
@@ -269,7 +320,7 @@ struct Geometry {
   using C = Cfg<T, CH>;
   static size_t smem_for(int stages, int sub) {
     return PROBLEM_SMEM_BYTES + (size_t)stages * sub * C::TILE_BYTES + 2 * MAX_STAGES * sizeof(uint64_t) + MAX_STAGES * sizeof(unsigned) +
-           2 * (size_t)C::ROWB +
+           NCAND * (size_t)C::ROWB +
            sizeof(Shared<T>) + 128;
   }
 };
@@ -317,6 +368,7 @@ int plan_T(b2svm_handle* h) {
   // ... and, when the GPU has room, one tile per consumer warp (no intra-CTA imbalance)
   const long long one_each = (plan_tiles + NW - 1) / NW;
   if (one_each <= max_ctas) ncta = std::max(ncta, one_each);
+  if (ncta > MAX_CTAS) ncta = MAX_CTAS;   // the level-1 poll reads at most MAX_CTAS records per type
   h->ncta = (int)ncta;
   h->tiles_per_cta = (int)((plan_tiles + ncta - 1) / ncta);   // informational: the kernel deals tiles out evenly
   return B2SVM_OK;
@@ -334,11 +386,11 @@ int plan(b2svm_handle* h) {
 // The 48 instantiations of the persistent kernel are compiled in four translation units
 // (b2svm_launch_{f32,f64}_{plain,generic}.cu) so the build parallelises.
 int launch(bool f64, int ch, bool cache, bool generic, const ProblemDev* probs_dev, int nprob, int ncta_pp, int stages,
-           size_t smem, cudaStream_t stream) {
-  if (f64) return generic ? launch_f64_generic(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream)
-                          : launch_f64_plain(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream);
-  return generic ? launch_f32_generic(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream)
-                 : launch_f32_plain(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream);
+           size_t smem, cudaStream_t stream, bool coop = false) {
+  if (f64) return generic ? launch_f64_generic(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream, coop)
+                          : launch_f64_plain(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream, coop);
+  return generic ? launch_f32_generic(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream, coop)
+                 : launch_f32_plain(ch, cache, probs_dev, nprob, ncta_pp, stages, smem, stream, coop);
 }
 
 inline bool needs_generic(const b2svm_handle* h) {
@@ -348,6 +400,7 @@ inline bool needs_generic(const b2svm_handle* h) {
 void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long long fi, long long fj) {
   P.X = h->Xuse;
   P.norms = h->norms;
+  P.kdiag = h->kdiag;
   P.alpha = h->d.alpha;
   P.G = h->d.neg_y_grad;
   P.flags = h->flags;
@@ -395,7 +448,8 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.l_global = h->d.world > 1 ? h->d.n_rows_global : h->d.n_rows;
   P.rows_per_rank = h->d.world > 1 ? h->rows_per_rank : h->d.n_rows;
   P.mbox = reinterpret_cast<uint4*>(h->block);
-  P.peer_mbox = reinterpret_cast<uint4* const*>(h->peer_tables);
+  P.box = reinterpret_cast<uint4*>(h->block + MBOX_L1_BYTES);
+  P.peer_box = reinterpret_cast<uint4* const*>(h->peer_tables);
   P.timeline = h->timeline;
   P.dbg_steps = h->dbg_steps;
   P.debug_flags = getenv("B2SVM_DEBUG_FLAGS") ? atoi(getenv("B2SVM_DEBUG_FLAGS")) : 0;
@@ -449,6 +503,29 @@ int run_solver(b2svm_handle* h, long long max_iter, long long fi, long long fj, 
 
 }  // namespace
 
+static void fill_stats(const b2svm_handle* h, const SolveResult& r, int n_ctas, float ms, int launches, b2svm_solve_stats* stats) {
+  memset(stats, 0, sizeof(*stats));
+  stats->n_iter = r.n_iter;
+  stats->converged = r.converged;
+  stats->n_ctas = n_ctas;
+  stats->last_i = r.last_i;
+  stats->last_j = r.last_j;
+  stats->last_delta_i = r.di;
+  stats->last_delta_j = r.dj;
+  stats->cold_sweeps = r.cold_sweeps;
+  stats->cache_hits = 2 * r.warm_sweeps;                 // both columns read from the cache
+  stats->cache_misses = 2 * r.cold_sweeps;               // cold sweep: both columns recomputed in one pass over X
+  const double esz = h->f64 ? 8.0 : 4.0;
+  // DESIGN.md section 4 / SURVEY 8(d): B_cold = l d sizeof(T) + n_vars 18 (+ sizeof(T) l per stored column);
+  // B_warm = n_vars 18 + 2 sizeof(T) l
+  stats->algorithmic_bytes =
+      (double)r.cold_sweeps * ((double)h->d.n_rows * h->d.n_features * esz + (double)h->d.n_vars * 18.0) +
+      (double)r.cols_stored * (double)h->d.n_rows * esz +
+      (double)r.warm_sweeps * ((double)h->d.n_vars * 18.0 + 2.0 * (double)h->d.n_rows * esz);
+  stats->device_ms = ms;
+  stats->launches = launches;
+}
+
 // ------------------------------------------------------------------------------------------
 // exported functions
 // ------------------------------------------------------------------------------------------
@@ -487,9 +564,8 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
   h->precomputed = precomputed;
   const int esz = h->f64 ? 8 : 4;
   h->dp = ch * 16 / esz;
-  cudaDeviceProp prop;
-  B2_CUDA(cudaGetDeviceProperties(&prop, desc->device));
-  h->num_sms = prop.multiProcessorCount;
+  h->num_sms = sm_count(desc->device);
+  if (h->num_sms <= 0) { delete h; return fail(B2SVM_E_CUDA, "cannot query the SM count"); }
   const int64_t l = desc->n_rows, nv = desc->n_vars;
 
   auto cleanup_fail = [&](int code, const std::string& msg) {
@@ -510,16 +586,18 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     if (desc->row_offset != (long long)desc->rank * rpr || desc->n_rows != want)
       return cleanup_fail(B2SVM_E_INVALID, "shard must be rows [rank*rpr, min(n,(rank+1)*rpr)), rpr = roundup32(ceil(n/world))");
   }
-  h->block_bytes = sizeof(uint4) * 2 * (size_t)std::max(1, desc->world) * h->num_sms * NCAND * 2;
-  B2_TRY(cudaMalloc(&h->block, h->block_bytes));
+  h->block_bytes = MBOX_L1_BYTES + (desc->world > 1 ? MBOX_L2_BYTES : 0);
+  if (desc->world > 1) B2_TRY(cudaMalloc(&h->block, h->block_bytes));
+  else B2_TRY(pool_alloc(&h->block, h->block_bytes, h->stream));
   B2_TRY(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
-  // rows of X held by this GPU: its own slice on one GPU, ALL rows (replicated, read-only) in a sharded solve
-  const int64_t lx = desc->world > 1 ? desc->n_rows_global : l;
+  // rows of X held by this GPU: its own slice only, also in a row-sharded solve (the winning rows of an iteration
+  // travel with their candidate records)
+  const int64_t lx = l;
   const bool in_place = precomputed || (desc->ldx == h->dp && desc->n_features == h->dp && ((uintptr_t)desc->X % 16 == 0));
   if (in_place) {
     h->Xuse = desc->X;
   } else {
-    B2_TRY(cudaMalloc(&h->Xown, (size_t)lx * h->dp * esz));
+    B2_TRY(pool_alloc(&h->Xown, (size_t)lx * h->dp * esz, h->stream));
     void* xdst = h->Xown;
     if (h->f64)
       pad_rows_kernel<double><<<grid_for(lx * h->dp), 256, 0, h->stream>>>((const double*)desc->X, desc->ldx,
@@ -530,18 +608,25 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     B2_TRY(cudaGetLastError());
     h->Xuse = xdst;
   }
-  B2_TRY(cudaMalloc(&h->norms, (size_t)lx * esz));
-  if (precomputed) B2_TRY(cudaMemsetAsync(h->norms, 0, (size_t)lx * esz, h->stream));
-  else if (h->f64)
-    row_norms_kernel<double><<<grid_for(lx * 32), 256, 0, h->stream>>>((const double*)h->Xuse, lx, h->dp, (double*)h->norms);
-  else
-    row_norms_kernel<float><<<grid_for(lx * 32), 256, 0, h->stream>>>((const float*)h->Xuse, lx, h->dp, (float*)h->norms);
+  B2_TRY(pool_alloc(&h->norms, (size_t)lx * esz, h->stream));
+  B2_TRY(pool_alloc(&h->kdiag, (size_t)lx * esz, h->stream));
+  if (precomputed) {
+    B2_TRY(cudaMemsetAsync(h->norms, 0, (size_t)lx * esz, h->stream));
+    if (h->f64) diag_precomputed_kernel<double><<<grid_for(lx), 256, 0, h->stream>>>((const double*)h->Xuse, lx, (double*)h->kdiag);
+    else diag_precomputed_kernel<float><<<grid_for(lx), 256, 0, h->stream>>>((const float*)h->Xuse, lx, (float*)h->kdiag);
+  } else if (h->f64) {
+    KernelParams<double> kp{desc->kernel.kind, desc->kernel.gamma, desc->kernel.coef0, desc->kernel.degree};
+    row_norms_kernel<double><<<grid_for(lx * 32), 256, 0, h->stream>>>((const double*)h->Xuse, lx, h->dp, (double*)h->norms, (double*)h->kdiag, kp);
+  } else {
+    KernelParams<float> kp{desc->kernel.kind, (float)desc->kernel.gamma, (float)desc->kernel.coef0, (float)desc->kernel.degree};
+    row_norms_kernel<float><<<grid_for(lx * 32), 256, 0, h->stream>>>((const float*)h->Xuse, lx, h->dp, (float*)h->norms, (float*)h->kdiag, kp);
+  }
   B2_TRY(cudaGetLastError());
-  B2_TRY(cudaMalloc(&h->flags, (size_t)nv));
+  B2_TRY(pool_alloc(&h->flags, (size_t)nv, h->stream));
   if (precomputed) {
     // the kernel matrix IS a completely filled column cache: every iteration takes the warm path
     h->cache = const_cast<void*>(desc->X);
-    B2_TRY(cudaMalloc(&h->slot_of, sizeof(int) * (size_t)l));
+    B2_TRY(pool_alloc(&h->slot_of, sizeof(int) * (size_t)l, h->stream));
     iota_kernel<<<grid_for(l), 256, 0, h->stream>>>(h->slot_of, l);
     B2_TRY(cudaGetLastError());
     h->cache_slots = l;
@@ -553,27 +638,23 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     const long long lglob = desc->world > 1 ? desc->n_rows_global : l;
     slots = std::min<long long>(slots, lglob);
     if (slots > 0) {
-      B2_TRY(cudaMalloc(&h->cache, (size_t)slots * col_bytes));
-      B2_TRY(cudaMalloc(&h->slot_of, sizeof(int) * (size_t)lglob));
+      B2_TRY(pool_alloc(&h->cache, (size_t)slots * col_bytes, h->stream));
+      B2_TRY(pool_alloc(&h->slot_of, sizeof(int) * (size_t)lglob, h->stream));
       B2_TRY(cudaMemsetAsync(h->slot_of, 0xff, sizeof(int) * (size_t)lglob, h->stream));
       h->cache_slots = slots;
     }
   }
-  if (desc->world <= 1) {   // the peer table of a single GPU is just its own mailbox
-    void* self = h->block;
-    B2_TRY(cudaMalloc(&h->peer_tables, sizeof(void*)));
-    B2_TRY(cudaMemcpy(h->peer_tables, &self, sizeof(void*), cudaMemcpyHostToDevice));
-  }
-  B2_TRY(cudaMalloc(&h->abort_flag, sizeof(int)));
-  B2_TRY(cudaMalloc(&h->result, sizeof(SolveResult)));
-  B2_TRY(cudaMallocHost(&h->result_host, sizeof(SolveResult)));
-  B2_TRY(cudaMalloc(&h->prob_dev, sizeof(ProblemDev)));
-  B2_TRY(cudaMalloc(&h->bias_dev, sizeof(BiasStats)));
+  B2_TRY(pool_alloc(&h->abort_flag, sizeof(int), h->stream));
+  B2_TRY(pool_alloc(&h->result, sizeof(SolveResult), h->stream));
+  h->result_host = pinned_result();
+  if (!h->result_host) return cleanup_fail(B2SVM_E_CUDA, "cudaMallocHost failed");
+  B2_TRY(pool_alloc(&h->prob_dev, sizeof(ProblemDev), h->stream));
+  B2_TRY(pool_alloc(&h->bias_dev, sizeof(BiasStats), h->stream));
   B2_TRY(cudaEventCreate(&h->ev0));
   B2_TRY(cudaEventCreate(&h->ev1));
   if (getenv("B2SVM_DEBUG_STEPS")) {
-    B2_TRY(cudaMalloc(&h->dbg_steps, sizeof(double) * DBG_EPOCHS * (h->num_sms * 6 + 2)));
-    B2_TRY(cudaMemset(h->dbg_steps, 0, sizeof(double) * DBG_EPOCHS * (h->num_sms * 6 + 2)));
+    B2_TRY(cudaMalloc(&h->dbg_steps, sizeof(double) * DBG_EPOCHS * (h->num_sms * DBG_W + 2)));
+    B2_TRY(cudaMemset(h->dbg_steps, 0, sizeof(double) * DBG_EPOCHS * (h->num_sms * DBG_W + 2)));
   }
   if (getenv("B2SVM_TIMELINE")) {
     B2_TRY(cudaMalloc(&h->timeline, sizeof(long long) * TL_TOTAL));
@@ -593,22 +674,22 @@ int b2svm_destroy(b2svm_handle* h) {
   if (!h) return B2SVM_OK;
   cudaSetDevice(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream); else cudaDeviceSynchronize();
-  cudaFree(h->Xown);
-  cudaFree(h->norms);
+  pool_free(h->Xown, h->stream);
+  pool_free(h->norms, h->stream);
+  pool_free(h->kdiag, h->stream);
   for (void* pb : h->peer_blocks)
     if (pb) cudaIpcCloseMemHandle(pb);
   cudaFree(h->peer_tables);
-  cudaFree(h->block);
-  cudaFree(h->flags);
-  if (!h->precomputed) cudaFree(h->cache);
-  cudaFree(h->slot_of);
-  cudaFree(h->abort_flag);
-  cudaFree(h->result);
-  if (h->result_host) cudaFreeHost(h->result_host);
-  cudaFree(h->prob_dev);
-  cudaFree(h->bias_dev);
-  cudaFree(h->scratch);
-  cudaFree(h->p_dev);
+  if (h->d.world > 1) cudaFree(h->block); else pool_free(h->block, h->stream);
+  pool_free(h->flags, h->stream);
+  if (!h->precomputed) pool_free(h->cache, h->stream);
+  pool_free(h->slot_of, h->stream);
+  pool_free(h->abort_flag, h->stream);
+  pool_free(h->result, h->stream);
+  pool_free(h->prob_dev, h->stream);
+  pool_free(h->bias_dev, h->stream);
+  pool_free(h->scratch, h->stream);
+  pool_free(h->p_dev, h->stream);
   cudaFree(h->timeline);
   cudaFree(h->dbg_steps);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -620,7 +701,7 @@ int b2svm_destroy(b2svm_handle* h) {
 static int stage_p(b2svm_handle* h, const double* p, const double** p_use) {
   // p may live on the host or the device: stage through a device buffer (UVA-aware copy)
   if (!p) { *p_use = nullptr; return B2SVM_OK; }
-  if (!h->p_dev) B2_CUDA(cudaMalloc(&h->p_dev, sizeof(double) * h->d.n_vars));
+  if (!h->p_dev) B2_CUDA(pool_alloc(&h->p_dev, sizeof(double) * h->d.n_vars, h->stream));
   B2_CUDA(cudaMemcpyAsync(h->p_dev, p, sizeof(double) * h->d.n_vars, cudaMemcpyDefault, h->stream));
   *p_use = h->p_dev;
   return B2SVM_OK;
@@ -645,7 +726,7 @@ int b2svm_init_gradient(b2svm_handle* h, const double* p) {
   const double* pu;
   int rc = stage_p(h, p, &pu);
   if (rc) return rc;
-  if (!h->scratch) B2_CUDA(cudaMalloc(&h->scratch, sizeof(double) * 2 * l));
+  if (!h->scratch) B2_CUDA(pool_alloc(&h->scratch, sizeof(double) * 2 * l, h->stream));
   double* w = h->scratch;
   double* m = h->scratch + l;
   row_weights_kernel<<<grid_for(l), 256, 0, h->stream>>>(h->d.y, h->d.alpha, l, nv, w);
@@ -718,29 +799,75 @@ int b2svm_solve(b2svm_handle* h, int64_t max_iter, b2svm_solve_stats* stats) {
   float ms = 0.f;
   int rc = run_solver(h, max_iter, -1, -1, &r, &ms);
   if (rc) return rc;
-  if (stats) {
-    memset(stats, 0, sizeof(*stats));
-    stats->n_iter = r.n_iter;
-    stats->converged = r.converged;
-    stats->n_ctas = h->ncta;
-    stats->last_i = r.last_i;
-    stats->last_j = r.last_j;
-    stats->last_delta_i = r.di;
-    stats->last_delta_j = r.dj;
-    stats->cold_sweeps = r.cold_sweeps;
-    stats->cache_hits = 2 * r.warm_sweeps;                 // both columns read from the cache
-    stats->cache_misses = 2 * r.cold_sweeps;               // cold sweep: both columns recomputed in one pass over X
-    const double esz = h->f64 ? 8.0 : 4.0;
-    // DESIGN.md section 4 / SURVEY 8(d): B_cold = l d sizeof(T) + n_vars 18 (+ sizeof(T) l per stored column);
-    // B_warm = n_vars 18 + 2 sizeof(T) l
-    stats->algorithmic_bytes =
-        (double)r.cold_sweeps * ((double)h->d.n_rows * h->d.n_features * esz + (double)h->d.n_vars * 18.0) +
-        (double)r.cols_stored * (double)h->d.n_rows * esz +
-        (double)r.warm_sweeps * ((double)h->d.n_vars * 18.0 + 2.0 * (double)h->d.n_rows * esz);
-    stats->device_ms = ms;
-    stats->launches = h->launches;
-  }
+  if (stats) fill_stats(h, r, h->ncta, ms, h->launches, stats);
   return B2SVM_OK;
+}
+
+/* The ranks of a row-sharded solve emulated on ONE GPU: `world` handles (created with rank = 0..world-1 of `world`,
+ * all on this device, max_ctas <= num_sms / world) run as the CTA groups of one cooperative launch, their level-2
+ * boxes attached to each other in local memory instead of over CUDA IPC.  Kernels that wait on one another must never
+ * be separate launches on one GPU; this entry point is how the two-level exchange protocol is tested on a 1-GPU box. */
+int b2svm_solve_ranks_on_one_gpu(b2svm_handle* const* handles, int32_t world, int64_t max_iter, b2svm_solve_stats* stats) {
+  if (!handles || world < 2 || world > BOX_RANKS) return fail(B2SVM_E_INVALID, "need 2..8 rank handles");
+  if (max_iter < 0 || max_iter >= B2SVM_MAX_ITER) return fail(B2SVM_E_UNSUPPORTED, "max_iter must be in [0, 2^29) per call");
+  b2svm_handle* h0 = handles[0];
+  if (!h0) return fail(B2SVM_E_INVALID, "null handle");
+  B2_CUDA(cudaSetDevice(h0->d.device));
+  for (int r = 0; r < world; ++r) {
+    b2svm_handle* h = handles[r];
+    if (!h) return fail(B2SVM_E_INVALID, "null handle");
+    if (h->d.world != world || h->d.rank != r) return fail(B2SVM_E_INVALID, "handle r must be rank r of `world`");
+    if (h->f64 != h0->f64 || h->ch != h0->ch || h->d.device != h0->d.device || h->stream != h0->stream ||
+        h->ncta != h0->ncta || h->stages != h0->stages || h->sub != h0->sub || (h->cache_slots > 0) != (h0->cache_slots > 0) ||
+        needs_generic(h) != needs_generic(h0))
+      return fail(B2SVM_E_INVALID, "emulated ranks must share dtype, row width, device, stream and launch geometry");
+  }
+  if ((long long)world * h0->ncta > h0->num_sms)
+    return fail(B2SVM_E_INVALID, "world * n_ctas exceeds the SM count: create the handles with max_ctas <= num_sms / world");
+  std::vector<void*> tab((size_t)world);
+  for (int r = 0; r < world; ++r) tab[r] = handles[r]->block + MBOX_L1_BYTES;
+  std::vector<ProblemDev> P((size_t)world);
+  ProblemDev* pd = nullptr;
+  B2_CUDA(pool_alloc(&pd, sizeof(ProblemDev) * world, h0->stream));
+  int rc = B2SVM_OK;
+  for (int r = 0; r < world && rc == B2SVM_OK; ++r) {
+    b2svm_handle* h = handles[r];
+    if (!h->peer_tables) {
+      cudaError_t e = cudaMalloc(&h->peer_tables, sizeof(void*) * world);
+      if (e != cudaSuccess) { rc = fail(B2SVM_E_CUDA, cudaGetErrorString(e)); break; }
+    }
+    cudaMemcpyAsync(h->peer_tables, tab.data(), sizeof(void*) * world, cudaMemcpyHostToDevice, h0->stream);
+    h->attached = true;
+    rc = prepare_launch(h);
+    h->prepared = false;
+    memset(&P[r], 0, sizeof(ProblemDev));
+    fill_problem(h, P[r], max_iter, -1, -1);
+  }
+  if (rc == B2SVM_OK) {
+    cudaMemcpyAsync(pd, P.data(), sizeof(ProblemDev) * world, cudaMemcpyHostToDevice, h0->stream);
+    cudaEventRecord(h0->ev0, h0->stream);
+    rc = launch(h0->f64, h0->ch, h0->cache_slots > 0, needs_generic(h0), pd, world, h0->ncta, h0->stages, h0->smem_bytes,
+                h0->stream, true);
+  }
+  if (rc == B2SVM_OK) {
+    cudaEventRecord(h0->ev1, h0->stream);
+    for (int r = 0; r < world; ++r)
+      cudaMemcpyAsync(pinned_result() + r, handles[r]->result, sizeof(SolveResult), cudaMemcpyDeviceToHost, h0->stream);
+    cudaError_t e = cudaStreamSynchronize(h0->stream);
+    if (e != cudaSuccess) rc = fail(B2SVM_E_CUDA, cudaGetErrorString(e));
+  }
+  if (rc == B2SVM_OK) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h0->ev0, h0->ev1);
+    for (int r = 0; r < world; ++r) {
+      const SolveResult& R = pinned_result()[r];
+      handles[r]->cache_used = R.cache_used;
+      if (R.status != 0) rc = fail(B2SVM_E_TIMEOUT, "device watchdog tripped in an emulated sharded solve");
+      if (stats) fill_stats(handles[r], R, h0->ncta, ms, 1, &stats[r]);
+    }
+  }
+  pool_free(pd, h0->stream);
+  return rc;
 }
 
 static int bias_stats(b2svm_handle* h, BiasStats* host) {
@@ -821,8 +948,8 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
   std::vector<ProblemDev> P(count);
   ProblemDev* pd = nullptr;
   SolveResult* rd = nullptr;
-  B2_CUDA(cudaMalloc(&pd, sizeof(ProblemDev) * count));
-  B2_CUDA(cudaMalloc(&rd, sizeof(SolveResult) * count));
+  B2_CUDA(pool_alloc(&pd, sizeof(ProblemDev) * count, h0->stream));
+  B2_CUDA(pool_alloc(&rd, sizeof(SolveResult) * count, h0->stream));
   for (int k = 0; k < count; ++k) {
     b2svm_handle* h = handles[k];
     refresh_flags_kernel<<<grid_for(h->d.n_vars), 256, 0, h0->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, h->d.n_vars);
@@ -873,8 +1000,8 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
       }
     }
   }
-  cudaFree(pd);
-  cudaFree(rd);
+  pool_free(pd, h0->stream);
+  pool_free(rd, h0->stream);
   return rc;
 }
 
@@ -887,8 +1014,8 @@ int b2svm_debug_timeline(b2svm_handle* h, long long* out, int n) {
 
 int b2svm_debug_steps(b2svm_handle* h, double* out, int epochs) {
   if (!h || !h->dbg_steps) return fail(B2SVM_E_INVALID, "debug steps not enabled (B2SVM_DEBUG_STEPS=1)");
-  B2_CUDA(cudaMemcpy(out, h->dbg_steps, sizeof(double) * (size_t)std::min(epochs, DBG_EPOCHS) * h->ncta * 6, cudaMemcpyDeviceToHost));
-  B2_CUDA(cudaMemcpy(out + (size_t)std::min(epochs, DBG_EPOCHS) * h->ncta * 6, h->dbg_steps + (size_t)DBG_EPOCHS * h->ncta * 6,
+  B2_CUDA(cudaMemcpy(out, h->dbg_steps, sizeof(double) * (size_t)std::min(epochs, DBG_EPOCHS) * h->ncta * DBG_W, cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(out + (size_t)std::min(epochs, DBG_EPOCHS) * h->ncta * DBG_W, h->dbg_steps + (size_t)DBG_EPOCHS * h->ncta * DBG_W,
                      sizeof(double) * (size_t)std::min(epochs, DBG_EPOCHS) * 2, cudaMemcpyDeviceToHost));
   return B2SVM_OK;
 }
@@ -922,7 +1049,7 @@ int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles) {
       h->peer_blocks[r] = p;
       base = reinterpret_cast<unsigned char*>(p);
     }
-    tab[r] = base;
+    tab[r] = base + MBOX_L1_BYTES;   // the level-2 box sits behind the level-1 mailbox
   }
   B2_CUDA(cudaMalloc(&h->peer_tables, sizeof(void*) * tab.size()));
   B2_CUDA(cudaMemcpy(h->peer_tables, tab.data(), sizeof(void*) * tab.size(), cudaMemcpyHostToDevice));

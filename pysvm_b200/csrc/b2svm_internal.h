@@ -41,7 +41,7 @@ void keep_pool_memory();   // stream-ordered allocator: keep up to 4 GB of work 
 
 struct ProblemDev;
 #define B2_DECL_LAUNCH(name)                                                                                  \
-  int name(int ch, bool cache, const ProblemDev* p, int nprob, int ncta_pp, int stages, size_t smem, cudaStream_t stream)
+  int name(int ch, bool cache, const ProblemDev* p, int nprob, int ncta_pp, int stages, size_t smem, cudaStream_t stream, bool coop)
 B2_DECL_LAUNCH(launch_f32_plain);
 B2_DECL_LAUNCH(launch_f32_generic);
 B2_DECL_LAUNCH(launch_f64_plain);

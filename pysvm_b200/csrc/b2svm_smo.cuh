@@ -20,16 +20,25 @@
 // 32-row tiles per ring stage (one bulk copy, one ticket); the copies of the leading 48 MB of X carry an L2
 // evict_last hint so that part of every sweep is served from the 126 MB L2.
 //
-// Candidate exchange (one level, same code on one GPU and on a row-sharded box).  Every CTA writes, per
-// candidate type, one 16-byte record {g, idx, epoch<<3 | flags} and one 16-byte unit {alpha, epoch} into the
-// mailbox of EVERY GPU (its own included; peers over NVLink through CUDA-IPC mappings), each with a single
-// relaxed 16-byte store, double-buffered by epoch parity.  A reader accepts a word only when it carries
-// the epoch it waits for, so data and "flag" travel together: no atomics and no release/acquire fences
-// (MEMBAR.SC + CCTL.IVALL cost 2-4 k cycles each on B200) on the per-iteration critical path.  All consumer
-// warps of a CTA share the polling of the world * nCTA records (one L2 round trip), reduce through shared
-// memory, and the leader warp finishes.  X (read-only) is replicated on every GPU of a sharded solve, so
-// the winning rows are local reads; only the sweep, the gradient, alpha and the column cache are sharded.
-// G / flags / alpha of a row are only ever touched by the CTA (= SM) that owns the row.
+// Candidate exchange, two levels, no atomics and no fences on the per-iteration critical path (MEMBAR.SC + CCTL.IVALL
+// cost 2-4 k cycles each on B200): every word that is polled carries the iteration ("epoch") it belongs to, so data
+// and flag travel together in single 16-byte relaxed stores, double-buffered by epoch parity.
+//   level 1 (inside a GPU): every CTA writes, per candidate type, one record {g, idx, epoch<<3 | flags} (+ a 16-byte
+//     alpha unit) into the GPU's mailbox; ONE warp per candidate type ("type warp": warp k handles type k, so the
+//     arg-max and the arg-min chains run side by side) polls the ncta records of its type -- that read IS the grid
+//     barrier -- and reduces them with REDUX.
+//   level 2 (row-sharded box, world > 1): the CTA that owns a GPU-level winner pushes it, TOGETHER WITH its alpha,
+//     norm and row x (candidates travel with their rows), into the box slot [rank][type] of every GPU
+//     over NVLink (CUDA-IPC peer mappings); the type warps of all CTAs then poll the `world` records of their type
+//     and read the winning row from local memory.  Row units are {8 payload bytes, epoch}: self-validating like the
+//     records.  Each GPU holds ONLY ITS OWN rows of X; nothing but these pushes crosses the link.
+// A polled 16-byte unit is {payload, payload, epoch, ~epoch} (records: {g, g, idx, epoch<<3 | flags}) and the reader
+// consumes ALL FOUR words: ptxas narrows a vector load whose components are partly dead into separate scalar loads
+// (observed: ld.relaxed.sys.v4 with .y/.w unused became two LDG.32), and then payload and tag are no longer read by
+// one memory transaction -- a stale payload can pass the tag check (found by comparing every leader's view per epoch).
+// The owner's row loads (world > 1) / L2 prefetch (world == 1) are issued before the level-1 poll, so the row is on
+// hand (or L2-resident) by the time the winners are known.  G / flags / alpha of a row are only ever touched by the
+// CTA (= SM) that owns the row; when every consumer warp owns at most one tile they stay in registers across sweeps.
 #pragma once
 #include "b2svm_device.cuh"
 
@@ -41,6 +50,7 @@ constexpr int MAX_STAGES = 64;
 constexpr int NCAND = 4;                   // up/low (C variant) or up+/low+/up-/low- (nu variant)
 constexpr int TL_ITERS = 64, TL_SLOTS = 16; // debug timeline
 constexpr int DBG_EPOCHS = 2048;
+constexpr int DBG_W = 16;                  // debug record per (epoch, CTA): leader inputs, kernel values, consumer-side view
 constexpr int TL_WARP_SLOTS = 4;           // + per-warp {start, end, tiles, wait} of one sweep
 constexpr int TL_CTA_BASE = TL_ITERS * TL_SLOTS + 16 * TL_WARP_SLOTS;   // + per-CTA {sweep cycles, tiles} of one sweep
 constexpr int TL_TOTAL = TL_CTA_BASE + 2 * 160;
@@ -59,6 +69,7 @@ struct SolveResult {
 struct ProblemDev {
   const void* X;        // [l][CH*16 bytes]
   const void* norms;    // T[l] squared row norms
+  const void* kdiag;    // T[l] K(x_r, x_r): constant over the solve, so it is not recomputed on the select -> step chain
   double* alpha;        // [nv]
   double* G;            // [nv]  neg_y_grad
   uint8_t* flags;       // [nv]
@@ -72,8 +83,9 @@ struct ProblemDev {
   int pin_lo, pin_hi;   // macro tiles [pin_lo, pin_hi) of every CTA's slice are fetched with L2 evict_last, the rest evict_first
   int sub;              // 32-row tiles per ring stage (narrow rows: several tiles travel in one bulk copy)
   long long ntiles;
-  uint4* mbox;          // local mailbox [2][world * ncta][NCAND][2] {record, alpha unit} (zeroed before every launch)
-  uint4* const* peer_mbox;   // [world] every rank's mailbox (peer mapping; own entry = mbox)
+  uint4* mbox;          // level-1 mailbox of this GPU [2][ncta][NCAND][2] {record, alpha unit} (zeroed before every launch)
+  uint4* box;           // level-2 box of this GPU [2][8 ranks][NCAND][BOX_UNITS] (world > 1; peers write into it over NVLink)
+  uint4* const* peer_box;    // [world] every rank's level-2 box (peer mapping; own entry = box)
   int* abort_flag;
   SolveResult* result;
   long long max_iter;
@@ -84,13 +96,19 @@ struct ProblemDev {
   int* slot_of;                   // [l_global] slot of global row r, -1 = not cached (replicated per GPU)
   long long cache_slots;          // 0 = cache off
   long long cache_used;           // slots already filled by earlier solves on this handle
-  // ---- row-sharded multi-GPU (world > 1): this GPU sweeps global rows [row_offset, row_offset + l); X and
-  // norms hold ALL l_global rows on every GPU
+  // ---- row-sharded multi-GPU (world > 1): this GPU holds and sweeps global rows [row_offset, row_offset + l) ONLY
+  // (X, norms, alpha, G, flags and cached columns are all indexed by local row)
   int world, rank;
   long long row_offset, l_global, rows_per_rank;   // every rank's slice starts at rank * rows_per_rank
-  double* dbg_steps;              // optional [DBG_EPOCHS][ncta][6] = si, sj, gi, gj, ai, aj seen by each leader
+  double* dbg_steps;              // optional [DBG_EPOCHS][ncta][DBG_W]: si, sj, gi, gj, ai, aj, Kii, Kjj, Kij, ci, cj, row checksum | consumer view
   int debug_flags;                // B2SVM_DEBUG_FLAGS: 1 = static tile assignment, 2 = L2 loads for G/flags
 };
+// level-2 box slot: {record, alpha unit, norm unit, K(x,x) unit, 2 half-chunk units per 16-byte chunk of the widest row (CH = 128)}
+constexpr int BOX_UNITS = 4 + 2 * 128;
+constexpr int BOX_RANKS = 8;
+constexpr int MAX_CTAS = 160;              // level-1 poll: 5 records per lane
+constexpr size_t MBOX_L1_BYTES = sizeof(uint4) * 2 * MAX_CTAS * NCAND * 2;
+constexpr size_t MBOX_L2_BYTES = sizeof(uint4) * 2 * BOX_RANKS * NCAND * BOX_UNITS;
 constexpr size_t PROBLEM_SMEM_BYTES = (sizeof(ProblemDev) + 127) / 128 * 128;   // descriptor copy in front of the ring
 
 // Tile geometry.  A tile is one contiguous bulk copy of BR rows of CH 16-byte chunks.  LPR lanes share
@@ -116,6 +134,11 @@ struct Cfg {
   static constexpr int TILE_BYTES = BR * ROWB;
 };
 
+// a 16-byte exchange unit is valid for `epoch` when both tags match; using z AND w keeps every component of the
+// vector load alive, so it stays one 128-bit memory transaction
+__device__ __forceinline__ bool unit_ok(const uint4& u, uint32_t epoch) { return u.z == epoch && u.w == ~epoch; }
+__device__ __forceinline__ uint4 make_unit(uint32_t lo, uint32_t hi, uint32_t epoch) { return make_uint4(lo, hi, epoch, ~epoch); }
+
 struct WCand {
   double g, alpha;
   int idx, flags;
@@ -131,12 +154,22 @@ struct LeaderState {
   long long warm_cnt, stored_cnt;
 };
 
+// What a type warp found for its candidate type after the exchange (read by the leader = warp 0).
+template <typename T>
+struct Selected {
+  double g, alpha;
+  int idx, flags;
+  int raw_slot, pad;    // slot_of[] entry of the row as read from global memory (-1 = not cached)
+  T norm, kself;        // |x|^2 and K(x, x)
+};
+
 template <typename T>
 struct Shared {
   double ci, cj;        // y_i * delta_i, y_j * delta_j
   double ai, aj;        // new alpha_i, alpha_j
   T ni, nj;             // |x_i|^2, |x_j|^2
   int i, j, fi, fj;
+  int ti, tj;           // candidate types the pair came from: x_i = xs[ti], x_j = xs[tj]
   int slot_i, slot_j;   // cache slots of rows i, j (-1 = none); store_* = fill the slot during this sweep
   int store_i, store_j, warm;
   int p_ri, p_rj, p_si, p_sj;   // previous pair's rows / slots: slot_of[] is updated one sweep late, like alpha
@@ -145,79 +178,36 @@ struct Shared {
   volatile long long consumed;
   LeaderState leader;
   int ticket;           // next dynamically assigned tile of the current sweep
-  uint4* peer[8];       // mailbox of every rank (copied once from global memory)
+  uint4* peer[BOX_RANKS];   // level-2 box of every rank (copied once from global memory)
   volatile int status;  // a warp's watchdog tripped
   WCand wc[NW][NCAND];  // per-warp candidates of the sweep
   uint4 wa[NW][NCAND];  // ... their alpha, {lo, hi, epoch, 0}: written when the load lands, after the CTA join
-  WCand cw[NCAND];      // this CTA's winners
-  WCand ws[NW][NCAND];  // per-warp winners of the polled records (alpha field unused, flags = source slot)
-  int wsrc[NW][NCAND];  // ... and the mailbox source (rank * ncta + cta) they came from
+  Selected<T> sel[NCAND];   // the box-wide winner of every type
 };
 
-__device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (&b)[NCAND]) {
+// `pa` = address of the variable's alpha.  Whenever a lane's running best changes, the line holding that alpha is
+// pulled towards L2 (alpha is touched by two rows per iteration only, so the candidate's alpha is otherwise a DRAM
+// miss sitting on the critical path between the sweep and the exchange: ~1600 cycles; a lane's best changes ~ln(rows
+// per lane) times per sweep, so this costs a handful of prefetches).
+__device__ __forceinline__ void touch_alpha(const double* pa) {
+  if (pa) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+}
+__device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (&b)[NCAND], const double* pa) {
   const bool second = nu && !(f & F_YPOS);
   if (in_up(f)) {
     if (!second) {
-      if (better_max(g, v, b[0].g, b[0].idx)) { b[0].g = g; b[0].idx = v; b[0].flags = f; }
+      if (better_max(g, v, b[0].g, b[0].idx)) { b[0].g = g; b[0].idx = v; b[0].flags = f; touch_alpha(pa); }
     } else {
-      if (better_max(g, v, b[2].g, b[2].idx)) { b[2].g = g; b[2].idx = v; b[2].flags = f; }
+      if (better_max(g, v, b[2].g, b[2].idx)) { b[2].g = g; b[2].idx = v; b[2].flags = f; touch_alpha(pa); }
     }
   }
   if (in_low(f)) {
     if (!second) {
-      if (better_min(g, v, b[1].g, b[1].idx)) { b[1].g = g; b[1].idx = v; b[1].flags = f; }
+      if (better_min(g, v, b[1].g, b[1].idx)) { b[1].g = g; b[1].idx = v; b[1].flags = f; touch_alpha(pa); }
     } else {
-      if (better_min(g, v, b[3].g, b[3].idx)) { b[3].g = g; b[3].idx = v; b[3].flags = f; }
+      if (better_min(g, v, b[3].g, b[3].idx)) { b[3].g = g; b[3].idx = v; b[3].flags = f; touch_alpha(pa); }
     }
   }
-}
-
-// Where the leader finds variable `idx`: row and norm in the (replicated) X / norms arrays.
-template <typename T>
-struct VarRef {
-  const typename Chunk<T>::V* row;
-  const T* norm;
-};
-template <typename T, int CH>
-__device__ __forceinline__ VarRef<T> locate(const ProblemDev& P, int idx) {
-  using V = typename Chunk<T>::V;
-  VarRef<T> r;
-  const long long grow = (P.mirror && idx >= P.l_global) ? idx - P.l_global : idx;
-  r.row = reinterpret_cast<const V*>(P.X) + grow * CH;
-  r.norm = reinterpret_cast<const T*>(P.norms) + grow;
-  return r;
-}
-
-// Leader warp: load rows a, b (16-byte chunks spread over the lanes) and evaluate
-// K(a,a), K(b,b), K(a,b) in T.  Chunks stay in xa / xb for the caller.
-template <typename T, int CH>
-__device__ __forceinline__ void pair_kernels(const KernelParams<T>& kp, const VarRef<T>& A, const VarRef<T>& B,
-                                             int lane, typename Chunk<T>::V (&xa)[(CH + 31) / 32],
-                                             typename Chunk<T>::V (&xb)[(CH + 31) / 32], T& na, T& nb, T& Kaa,
-                                             T& Kbb, T& Kab) {
-  using CK = Chunk<T>;
-  constexpr int Q = (CH + 31) / 32;
-  na = *A.norm;
-  nb = *B.norm;
-#pragma unroll
-  for (int q = 0; q < Q; ++q) {
-    const int c = lane + 32 * q;
-    xa[q] = (c < CH) ? A.row[c] : CK::zero();
-    xb[q] = (c < CH) ? B.row[c] : CK::zero();
-  }
-  T daa = 0, dbb = 0, dab = 0;
-#pragma unroll
-  for (int q = 0; q < Q; ++q) {
-    daa = CK::dot(xa[q], xa[q], daa);
-    dbb = CK::dot(xb[q], xb[q], dbb);
-    dab = CK::dot(xa[q], xb[q], dab);
-  }
-  daa = warp_sum(daa);
-  dbb = warp_sum(dbb);
-  dab = warp_sum(dab);
-  Kaa = kernel_value(kp, daa, na, na);
-  Kbb = kernel_value(kp, dbb, nb, nb);
-  Kab = kernel_value(kp, dab, na, nb);
 }
 
 template <typename T>
@@ -261,8 +251,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   // full[s] only once gen[s] == u: mbarrier parity can tell neighbouring phases apart, not phases two
   // apart, and with dynamically drawn tiles a warp may otherwise run a whole ring ahead of a slow one.
   volatile unsigned* gen = reinterpret_cast<volatile unsigned*>(empty + MAX_STAGES);
-  V* xs = reinterpret_cast<V*>(const_cast<unsigned*>(gen) + MAX_STAGES);      // [2][CH]
-  Shared<T>* sh = reinterpret_cast<Shared<T>*>(xs + 2 * CH);
+  V* xs = reinterpret_cast<V*>(const_cast<unsigned*>(gen) + MAX_STAGES);      // [NCAND][CH]: the winning row of every candidate type
+  Shared<T>* sh = reinterpret_cast<Shared<T>*>(xs + NCAND * CH);
 
   const int cta = blockIdx.x % ncta_pp;
   const int warp = threadIdx.x >> 5;
@@ -297,7 +287,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     sh->consumed = 0;
     sh->ticket = NW;
     sh->status = 0;
-    for (int r = 0; r < P.world && r < 8; ++r) sh->peer[r] = const_cast<uint4*>(P.peer_mbox[r]);
+    for (int r = 0; r < BOX_RANKS; ++r) sh->peer[r] = (P.world > 1 && r < P.world) ? const_cast<uint4*>(P.peer_box[r]) : nullptr;
     LeaderState L0;
     L0.di = L0.dj = 0.0;
     L0.ri = L0.rj = L0.si = L0.sj = -1;
@@ -311,7 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   // ============================== producer warp ==============================================
   if (warp == NW) {
     if (NM > 0 && P.kind != K_PRECOMPUTED) {   // a precomputed kernel matrix is only ever read through the cache path
-      const unsigned char* Xb = reinterpret_cast<const unsigned char*>(P.X) + (size_t)P.row_offset * C::ROWB;
+      const unsigned char* Xb = reinterpret_cast<const unsigned char*>(P.X);   // this GPU's rows
       unsigned long long Tp = 0;
       unsigned stage = 0, par = 0;   // stage = Tp % S, par = (Tp / S) & 1
       int t = 0;                     // Tp % NT
@@ -371,7 +361,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   kp.gamma = (T)P.gamma;
   kp.coef0 = (T)P.coef0;
   kp.degree = (T)P.degree;
-  const T* __restrict__ norms = reinterpret_cast<const T*>(P.norms) + P.row_offset;   // this GPU's rows
+  const T* __restrict__ norms = reinterpret_cast<const T*>(P.norms);   // this GPU's rows
+  const T* __restrict__ kdiag = reinterpret_cast<const T*>(P.kdiag);
   double* __restrict__ G = P.G;
   double* __restrict__ alpha = P.alpha;
   uint8_t* __restrict__ flags = P.flags;
@@ -438,33 +429,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     return r;
   };
 
-  // K(a,a), K(b,b), K(a,b) for the leader: from the rows, or straight from a precomputed kernel matrix
-  auto pair_k = [&](int ia, int ib, V (&xa)[QL], V (&xb)[QL], T& na, T& nb, T& Kaa, T& Kbb, T& Kab) {
-    if (CACHE && P.kind == K_PRECOMPUTED) {
-      const long long ra = (mirror && ia >= lg) ? ia - lg : ia, rb = (mirror && ib >= lg) ? ib - lg : ib;
-      const T* Kc = reinterpret_cast<const T*>(P.cache);
-      na = nb = 0;
-      Kaa = __ldg(Kc + ra * l + ra);
-      Kbb = __ldg(Kc + rb * l + rb);
-      Kab = __ldg(Kc + ra * l + rb);
-    } else {
-      pair_kernels<T, CH>(kp, locate<T, CH>(P, ia), locate<T, CH>(P, ib), lane, xa, xb, na, nb, Kaa, Kbb, Kab);
-    }
-  };
-
   // ---- initial selection pass over G / flags only (no X) -------------------------------------
   reset_best();
   const bool forced = P.forced_i >= 0;
   if (!forced) {
     for (long long r = row0 + warp * 32 + lane; r < row1; r += NW * 32) {
-      consider(nu, flags[r], G[r], (int)(r + goff), best);
-      if (mirror) consider(nu, flags[r + l], G[r + l], (int)(r + goff + lg), best);
+      consider(nu, flags[r], G[r], (int)(r + goff), best, alpha + r);
+      if (mirror) consider(nu, flags[r + l], G[r + l], (int)(r + goff + lg), best, alpha + r + l);
     }
   }
   RowState<T> pf = load_row_state(warp * SUB);   // first tile of the first sweep (macro tiles 0..NW-1 are static)
 
+  // every consumer warp owns at most one tile: its gradient-side state never leaves the registers
+  const bool one_tile = SUB == 1 && NM <= NW;
+  const uint4* const l1_base = P.mbox;
+  const uint4* const box_base = P.box;
+
   for (;;) {
-    // ---- (B) warp -> CTA candidate reduce, publish to every GPU, shared polling, global reduce ----------
+    // ---- (B) warp -> CTA candidate reduce, level-1 (GPU) and level-2 (box) exchange, step -------------------
     ++epoch;
     stamp(0);   // this warp's sweep done
     const uint32_t par = epoch & 1u;
@@ -473,8 +455,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, best[k]);
     __syncwarp();
     // one lane per type also fetches the candidate's alpha (a row of this warp: same-SM coherent).  The load is
-    // only issued here: its value is parked in shared memory after the CTA join and travels in a separate 16-byte
-    // unit, so neither the join nor the candidate record waits for it (the leaders need it at step time only).
+    // only issued here: its value is parked in shared memory after the CTA join, so neither the join nor the
+    // candidate record waits for it (it is needed at step time only).
     double cand_alpha = 0.0;
     if (lane < ntypes) {
       Cand m = best[0];
@@ -494,362 +476,473 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     auto park_alpha = [&]() {
       if (lane < ntypes)
         st_volatile_shared_v4(&sh->wa[warp][lane],
-                              make_uint4((uint32_t)__double2loint(cand_alpha), (uint32_t)__double2hiint(cand_alpha), epoch, 0u));
+                              make_unit((uint32_t)__double2loint(cand_alpha), (uint32_t)__double2hiint(cand_alpha), epoch));
     };
-    if (warp != 0) park_alpha();
+    if (warp >= ntypes) park_alpha();
 
-    if (warp == 0) {
-      // CTA-level winner per type.  Full-warp collectives only: with two half-warp masks in one instruction the
-      // compiler falls back to a MATCH.ANY / WARPSYNC.EXCLUSIVE emulation that costs ~1000 cycles on this path.
-      for (int k = 0; k < ntypes; ++k) {
+    if (warp < ntypes) {
+      // =========================== type warp: everything about candidate type k = warp ======================
+      const int k = warp;
+      const bool is_max = (k & 1) == 0;
+      const bool forced_now = forced && epoch == 1;   // single GPU only (checked on the host)
+      Cand w;            // the winner of type k: first of this CTA, then of the GPU, then of the box
+      w.g = 0.0; w.idx = -1; w.flags = 0;
+      int wsrc = 0;      // where it came from: CTA (level 1), then rank (level 2)
+      double w_alpha = 0.0;
+      V row[QL];
+      T nrm = 0, kself = 0;
+#pragma unroll
+      for (int q = 0; q < QL; ++q) row[q] = CK::zero();
+      bool have_row = false, have_alpha = false;
+      int status = 0;
+
+      if (!forced_now) {
+        // ---- CTA-level winner (full-warp collectives only: two half-warp masks in one instruction compile to a
+        // MATCH.ANY / WARPSYNC.EXCLUSIVE emulation that costs ~1000 cycles on this path)
         WCand mw;
         mw.g = 0.0; mw.alpha = 0.0; mw.idx = -1; mw.flags = 0;
         if (lane < NW) mw = sh->wc[lane][k];
         Cand m;
         m.g = mw.g; m.idx = mw.idx; m.flags = mw.flags;
-        redux_select(0xffffffffu, (k & 1) == 0, m);
+        redux_select(0xffffffffu, is_max, m);
         const unsigned holders = __ballot_sync(0xffffffffu, m.idx >= 0 && mw.idx == m.idx);
-        const int from = holders ? __ffs(holders) - 1 : 0;
-        if (lane == 0) {
-          WCand c;
-          c.g = m.g; c.alpha = 0.0; c.idx = m.idx; c.flags = (m.flags & 7) | (from << 8);   // + the warp it came from
-          sh->cw[k] = c;
-        }
-      }
-      __syncwarp();
-      stamp(7);   // CTA winners known
-      // ... pushed into the mailbox of every GPU: one lane per (rank, type), the record first ...
-      const int pr = lane / ntypes, pk = lane - pr * ntypes;
-      uint4* rp = nullptr;
-      int from_warp = 0;
-      if (lane < world * ntypes) {
-        const WCand c = sh->cw[pk];
-        from_warp = c.flags >> 8;
-        rp = sh->peer[pr] + ((((size_t)par * world + P.rank) * ncta + cta) * NCAND + pk) * 2;
-        const uint4 rec = make_uint4((uint32_t)__double2loint(c.g), (uint32_t)__double2hiint(c.g), (uint32_t)c.idx,
-                                     (epoch << 3) | (uint32_t)(c.flags & 7));
-        if (world == 1) st_relaxed_v4(rp, rec);
-        else st_relaxed_sys_v4(rp, rec);
-      }
-      if (lane == 0) sh->ticket = NW;   // next sweep: tiles 0..NW-1 are static, the rest are drawn here
-      stamp(2);   // published
-      // ... then the winner's alpha, as soon as the warp that owns it has parked it
-      park_alpha();
-      __syncwarp();
-      if (lane < world * ntypes) {
-        uint4 u = ld_volatile_shared_v4(&sh->wa[from_warp][pk]);
-        while (u.z != epoch) u = ld_volatile_shared_v4(&sh->wa[from_warp][pk]);
-        const uint4 au = make_uint4(u.x, u.y, 0u, epoch);
-        if (world == 1) st_relaxed_v4(rp + 1, au);
-        else st_relaxed_sys_v4(rp + 1, au);
-      }
-#ifdef B2SVM_TIMELINE
-      if (P.timeline && threadIdx.x == 0 && (epoch == 11u || epoch == 41u) && cta < 160)   // two sweeps: is a slow CTA always slow?
-        P.timeline[TL_CTA_BASE + 2 * cta + (epoch == 41u)] = clock64() - cta_sweep_start_prev;
-#endif
-    }
-
-    // ---- every consumer warp polls its share of the world * ncta records (this is the grid / box barrier)
-    {
-      const int NS = world * ncta;
-      const int per = (NS + NW - 1) / NW;
-      const int s_begin = warp * per;
-      const int s_end = min(NS, s_begin + per);
-      constexpr int MAXM = 4;   // per <= ceil(8 * 148 / 11) = 108 <= 4 * 32
-      const uint4* rbase = P.mbox + (size_t)par * NS * NCAND * 2;
-      Cand w[NCAND];
-      int wsrc[NCAND];
-      const uint64_t t_start = globaltimer_ns();
-      uint32_t rounds = 0;
-      for (;;) {
-        bool all = true;
+        const int from_warp = holders ? __ffs(holders) - 1 : 0;
+        stamp(7);   // CTA winner known
+        // ---- level 1: one tagged record into this GPU's mailbox
+        uint4* const l1 = const_cast<uint4*>(l1_base) + ((((size_t)par * ncta + cta) * NCAND + k) * 2);
+        if (lane == 0)
+          st_relaxed_v4(l1, make_uint4((uint32_t)__double2loint(m.g), (uint32_t)__double2hiint(m.g), (uint32_t)m.idx,
+                                       (epoch << 3) | (uint32_t)(m.flags & 7)));
+        // the candidate's row, requested now and used after the poll: real loads when it may have to travel to the
+        // other GPUs (world > 1), an L2 prefetch otherwise (the leaders' fetch of the winning row then hits)
+        V myrow[QL];
+        T mynorm = 0, mykself = 0;
 #pragma unroll
-        for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; wsrc[k] = 0; }
-        // all loads of a pass are issued before any is looked at: one round trip per pass, not one per record
-        for (int k0 = 0; k0 < ntypes; k0 += 2) {
-          uint4 h[MAXM][2];
+        for (int q = 0; q < QL; ++q) myrow[q] = CK::zero();
+        if (m.idx >= 0 && P.kind != K_PRECOMPUTED) {
+          const long long lrow = ((mirror && m.idx >= lg) ? m.idx - lg : m.idx) - goff;
+          const V* src = reinterpret_cast<const V*>(P.X) + lrow * CH;
+          if (world > 1) {
 #pragma unroll
-          for (int m = 0; m < MAXM; ++m) {
-            const int sidx = s_begin + lane + 32 * m;
-            if (sidx < s_end) {
-              if (world == 1) {   // gpu scope is enough (and cheaper) when no peer writes into this mailbox
-                h[m][0] = ld_relaxed_v4(rbase + ((size_t)sidx * NCAND + k0) * 2);
-                h[m][1] = ld_relaxed_v4(rbase + ((size_t)sidx * NCAND + k0 + 1) * 2);
-              } else {
-                h[m][0] = ld_relaxed_sys_v4(rbase + ((size_t)sidx * NCAND + k0) * 2);
-                h[m][1] = ld_relaxed_sys_v4(rbase + ((size_t)sidx * NCAND + k0 + 1) * 2);
-              }
+            for (int q = 0; q < QL; ++q) {
+              const int c = lane + 32 * q;
+              if (c < CH) myrow[q] = src[c];
             }
+            mynorm = norms[lrow];
+            mykself = kdiag[lrow];
+          } else if (lane * 128 < C::ROWB) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(src) + lane * 128));
           }
+        }
+        if (k == 0 && lane == 0) sh->ticket = NW;   // next sweep: tiles 0..NW-1 are static, the rest are drawn here
+        stamp(2);   // published
+#ifdef B2SVM_TIMELINE
+        if (P.timeline && threadIdx.x == 0 && (epoch == 11u || epoch == 41u) && cta < 160)   // two sweeps: is a slow CTA always slow?
+          P.timeline[TL_CTA_BASE + 2 * cta + (epoch == 41u)] = clock64() - cta_sweep_start_prev;
+#endif
+        // ---- the CTA winner's alpha, as soon as the warp that owns it has parked it
+        park_alpha();
+        __syncwarp();
+        uint4 ua = ld_volatile_shared_v4(&sh->wa[from_warp][k]);
+        while (!unit_ok(ua, epoch)) ua = ld_volatile_shared_v4(&sh->wa[from_warp][k]);
+        if (world == 1 && lane == 0) st_relaxed_v4(l1 + 1, make_unit(ua.x, ua.y, epoch));
+
+        // ---- poll the ncta level-1 records of this type (this read is the grid barrier)
+        {
+          constexpr int MAXM = MAX_CTAS / 32;
+          const uint4* rbase = l1_base + (size_t)par * ncta * NCAND * 2 + (size_t)k * 2;
+          uint64_t t_start = 0;   // (the timer is only read once the poll has been spinning for a while)
+          uint32_t rounds = 0;
+          for (;;) {
+            bool all = true;
+            w.g = 0.0; w.idx = -1; w.flags = 0;
+            wsrc = 0;
+            uint4 h[MAXM];
+            // all loads of a pass are issued before any is looked at: one L2 round trip per pass
 #pragma unroll
-          for (int m = 0; m < MAXM; ++m) {
-            const int sidx = s_begin + lane + 32 * m;
-            if (sidx < s_end) {
+            for (int mm = 0; mm < MAXM; ++mm) {
+              const int c = lane + 32 * mm;
+              if (c < ncta) h[mm] = ld_relaxed_v4(rbase + (size_t)c * NCAND * 2);
+            }
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint4 hh = h[m][kk];
+            for (int mm = 0; mm < MAXM; ++mm) {
+              const int c = lane + 32 * mm;
+              if (c < ncta) {
+                const uint4 hh = h[mm];
                 if ((hh.w >> 3) != epoch) {
                   all = false;
                 } else {
                   const double g = __hiloint2double((int)hh.y, (int)hh.x);
                   const int idx = (int)hh.z;
-                  Cand& wk = (k0 == 0) ? w[kk] : w[2 + kk];
-                  int& ws = (k0 == 0) ? wsrc[kk] : wsrc[2 + kk];
-                  const bool take = kk == 0 ? better_max(g, idx, wk.g, wk.idx) : better_min(g, idx, wk.g, wk.idx);
-                  if (take) { wk.g = g; wk.idx = idx; wk.flags = (int)(hh.w & 7u); ws = sidx; }
+                  const bool take = is_max ? better_max(g, idx, w.g, w.idx) : better_min(g, idx, w.g, w.idx);
+                  if (take) { w.g = g; w.idx = idx; w.flags = (int)(hh.w & 7u); wsrc = c; }
                 }
               }
             }
-          }
-        }
-        if (__all_sync(0xffffffffu, all)) break;
-        if ((++rounds & 63u) == 0) {
-          int bad = *(volatile int*)P.abort_flag | sh->status;
-          if (!bad && globaltimer_ns() - t_start > 6000000000ull) {
-            *(volatile int*)P.abort_flag = 1;
-            bad = 1;
-          }
-          if (__any_sync(0xffffffffu, bad)) { sh->status = 1; break; }
-        }
-      }
-      // warp winner per type, with the mailbox source it came from
-#pragma unroll
-      for (int k = 0; k < NCAND; ++k) {
-        if (k < ntypes) {
-          const int mine = w[k].idx;
-          redux_select(0xffffffffu, (k & 1) == 0, w[k]);
-          const unsigned holders = __ballot_sync(0xffffffffu, w[k].idx >= 0 && mine == w[k].idx);
-          const int from = holders ? __ffs(holders) - 1 : 0;
-          wsrc[k] = __shfl_sync(0xffffffffu, wsrc[k], from);
-        }
-      }
-      // CTA 0 pulls the rows of its warp winners towards L2 now (a row of another GPU's slice is never swept here,
-      // a local one may have been streamed out): the leaders' fetch of the pair's rows after the exchange then hits
-      if (cta == 0 && P.kind != K_PRECOMPUTED) {
-#pragma unroll
-        for (int k = 0; k < NCAND; ++k) {
-          if (k < ntypes && w[k].idx >= 0) {
-            const long long grow = (mirror && w[k].idx >= lg) ? w[k].idx - lg : w[k].idx;
-            if (lane * 128 < C::ROWB)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(P.X) + (size_t)grow * C::ROWB + lane * 128));
-          }
-        }
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < NCAND; ++k) {
-          WCand c;
-          c.g = w[k].g; c.alpha = 0.0; c.idx = w[k].idx; c.flags = w[k].flags;
-          sh->ws[warp][k] = c;
-          sh->wsrc[warp][k] = wsrc[k];
-        }
-      }
-    }
-    named_bar_sync(3, NW * 32);
-    stamp(3);   // every record of the box read
-
-    if (warp == 0) {
-      LeaderState L = sh->leader;
-      int status = sh->status;
-      const long long n_iter = (long long)epoch - 1;
-      // global winners: reduce the NW warp winners (16 lanes per type), keep the source slot of each
-      Cand w[NCAND];
-      int wsrc[NCAND];
-#pragma unroll
-      for (int k = 0; k < NCAND; ++k) { w[k].g = 0.0; w[k].idx = -1; w[k].flags = 0; wsrc[k] = 0; }
-      for (int k = 0; k < ntypes; ++k) {   // full-warp collectives, one type at a time (see the CTA-level reduce)
-        Cand m;
-        m.g = 0.0; m.idx = -1; m.flags = 0;
-        int msrc = 0;
-        if (lane < NW) {
-          const WCand c = sh->ws[lane][k];
-          m.g = c.g; m.idx = c.idx; m.flags = c.flags;
-          msrc = sh->wsrc[lane][k];
-        }
-        const int mine = m.idx;
-        redux_select(0xffffffffu, (k & 1) == 0, m);
-        const unsigned holders = __ballot_sync(0xffffffffu, m.idx >= 0 && mine == m.idx);
-        const int from = holders ? __ffs(holders) - 1 : 0;
-        msrc = __shfl_sync(0xffffffffu, msrc, from);
-#pragma unroll
-        for (int q = 0; q < NCAND; ++q)
-          if (q == k) { w[q] = m; wsrc[q] = msrc; }
-      }
-      // alpha of a winner: the 16-byte unit its CTA pushed next to the record (polled until it carries the epoch)
-      const uint4* abase = P.mbox + (size_t)par * world * ncta * NCAND * 2;
-      auto alpha_unit = [&](int type) -> const uint4* { return abase + ((size_t)wsrc[type] * NCAND + type) * 2 + 1; };
-      auto load_unit = [&](int type) -> uint4 {
-        return world == 1 ? ld_relaxed_v4(alpha_unit(type)) : ld_relaxed_sys_v4(alpha_unit(type));
-      };
-      auto settle_alpha = [&](uint4 u, int type) -> double {   // re-poll until the unit carries this epoch
-        uint32_t spins = 0;
-        while (u.w != epoch) {
-          u = load_unit(type);
-          if ((++spins & 4095u) == 0 && *(volatile int*)P.abort_flag) break;
-        }
-        return __hiloint2double((int)u.y, (int)u.x);
-      };
-      stamp(4);   // global winners known
-
-      // ---- decide the next pair (working_set_select) ------------------------------------------
-      int si = -1, sj = -1;
-      double gi = 0, gj = 0, ai = 0, aj = 0;
-      int fi = 0, fj = 0;
-      bool stop_sel = false;
-      V xi[QL], xj[QL];
-#pragma unroll
-      for (int q = 0; q < QL; ++q) { xi[q] = CK::zero(); xj[q] = CK::zero(); }
-      T ni = 0, nj = 0, Kii = 0, Kjj = 0, Kij = 0;
-      bool have_k = false;
-      int ti = 0, tj = 1;   // candidate types the pair came from
-      if (forced && epoch == 1) {
-        si = (int)P.forced_i;     // single GPU only (checked on the host)
-        sj = (int)P.forced_j;
-        gi = __ldcg(G + si); gj = __ldcg(G + sj);
-        ai = __ldcg(alpha + si); aj = __ldcg(alpha + sj);
-        fi = __ldcg(flags + si); fj = __ldcg(flags + sj);
-      } else if (!nu) {
-        // solver.py:66-75
-        si = w[0].idx; sj = w[1].idx;
-        gi = w[0].g; gj = w[1].g; fi = w[0].flags; fj = w[1].flags;
-        stop_sel = si < 0 || sj < 0 || (gi - gj < P.tol);
-        // (alpha_i, alpha_j are fetched together with the rows in the step below)
-      } else {
-        // solver.py:300-339: no tol test, gain comparison between the class-wise pairs
-        const bool pos_ok = w[0].idx >= 0 && w[1].idx >= 0;
-        const bool neg_ok = w[2].idx >= 0 && w[3].idx >= 0;
-        int pick = -1;   // 0 = '+' pair, 1 = '-' pair
-        if (!pos_ok && !neg_ok) stop_sel = true;
-        else if (!pos_ok) pick = 1;
-        else if (!neg_ok) pick = 0;
-        else {
-          V xa[QL], xb[QL];
-          T na, nb, Kaa, Kbb, Kab;
-          pair_k(w[0].idx, w[1].idx, xa, xb, na, nb, Kaa, Kbb, Kab);
-          double quad_p = ((double)Kaa + (double)Kbb) - 2.0 * (double)Kab;
-          if (quad_p <= 0) quad_p = 1e-12;
-          const double dp = w[0].g - w[1].g;
-          const double gain_p = -(dp * dp) / quad_p;
-          pair_k(w[2].idx, w[3].idx, xi, xj, ni, nj, Kii, Kjj, Kij);
-          double quad_n = ((double)Kii + (double)Kjj) - 2.0 * (double)Kij;
-          if (quad_n <= 0) quad_n = 1e-12;
-          const double dn = w[2].g - w[3].g;
-          const double gain_n = -(dn * dn) / quad_n;
-          if (gain_p < gain_n) {
-            pick = 0;
-#pragma unroll
-            for (int q = 0; q < QL; ++q) { xi[q] = xa[q]; xj[q] = xb[q]; }
-            ni = na; nj = nb; Kii = Kaa; Kjj = Kbb; Kij = Kab;
-          } else {
-            pick = 1;
-          }
-          have_k = true;
-        }
-        if (pick >= 0) {
-          const Cand& a = pick == 0 ? w[0] : w[2];
-          const Cand& b = pick == 0 ? w[1] : w[3];
-          si = a.idx; sj = b.idx; gi = a.g; gj = b.g; fi = a.flags; fj = b.flags;
-          ti = pick == 0 ? 0 : 2;
-          tj = ti + 1;
-        }
-      }
-
-#ifdef B2SVM_TIMELINE
-      if (P.dbg_steps && lane == 0 && epoch <= (uint32_t)DBG_EPOCHS) {
-        double* o = P.dbg_steps + ((size_t)(epoch - 1) * ncta + cta) * 6;
-        o[0] = si; o[1] = sj; o[2] = gi; o[3] = gj; o[4] = ai; o[5] = aj;
-      }
-#endif
-      if (stop_sel) L.converged = 1;
-      const bool exit_now = status || stop_sel || n_iter >= P.max_iter;
-      if (exit_now) {
-        if (lane == 0) {
-          sh->stop = 1;
-          if (cta == 0) {
-            SolveResult r;
-            r.n_iter = n_iter;
-            r.last_i = stop_sel ? -1 : si;
-            r.last_j = stop_sel ? -1 : sj;
-            r.cold_sweeps = n_iter - L.warm_cnt;
-            r.warm_sweeps = L.warm_cnt;
-            r.cols_stored = L.stored_cnt;
-            r.cache_used = L.n_cached;
-            if (CACHE && P.cache_slots > 0 && L.ri >= 0) {   // pending slot-table entries of the last step
-              if (L.si >= 0) P.slot_of[L.ri] = L.si;
-              if (L.sj >= 0) P.slot_of[L.rj] = L.sj;
+            if (__all_sync(0xffffffffu, all)) break;
+            if ((++rounds & 63u) == 0) {
+              int bad = *(volatile int*)P.abort_flag | sh->status;
+              const uint64_t now = globaltimer_ns();
+              if (t_start == 0) t_start = now;
+              if (!bad && now - t_start > 6000000000ull) {
+                *(volatile int*)P.abort_flag = 1;
+                bad = 1;
+              }
+              if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
             }
-            r.di = L.di;
-            r.dj = L.dj;
-            r.converged = L.converged;
-            r.status = status;
-            r.pad[0] = r.pad[1] = 0;
-            *P.result = r;
+          }
+          const int mine = w.idx;
+          redux_select(0xffffffffu, is_max, w);
+          const unsigned hold2 = __ballot_sync(0xffffffffu, w.idx >= 0 && mine == w.idx);
+          wsrc = __shfl_sync(0xffffffffu, wsrc, hold2 ? __ffs(hold2) - 1 : 0);
+        }
+        stamp(3);   // GPU-level winner known
+
+        if (world > 1 && !status) {
+          // ---- level 2: the owner of the GPU-level winner pushes it, with alpha, norm and row, to every GPU
+          const int owner = w.idx >= 0 ? wsrc : 0;
+          if (cta == owner) {
+            const uint4 rec = make_uint4((uint32_t)__double2loint(w.g), (uint32_t)__double2hiint(w.g), (uint32_t)w.idx,
+                                         (epoch << 3) | (uint32_t)(w.flags & 7));
+            // float: one unit {norm, K(x,x)}; double: one unit each
+            uint4 un, uk;
+            if (sizeof(T) == 8) {
+              un = make_unit((uint32_t)__double2loint((double)mynorm), (uint32_t)__double2hiint((double)mynorm), epoch);
+              uk = make_unit((uint32_t)__double2loint((double)mykself), (uint32_t)__double2hiint((double)mykself), epoch);
+            } else {
+              un = make_unit(__float_as_uint((float)mynorm), __float_as_uint((float)mykself), epoch);
+              uk = un;
+            }
+            for (int rr = 0; rr < world; ++rr) {
+              const int r = (P.rank + 1 + rr) % world;   // peers first, the own box last
+              uint4* slot = sh->peer[r] + (((size_t)par * BOX_RANKS + P.rank) * NCAND + k) * BOX_UNITS;
+              if (w.idx >= 0) {
+#pragma unroll
+                for (int q = 0; q < QL; ++q) {
+                  const int c = lane + 32 * q;
+                  if (c < CH) {
+                    const uint4 bits = *reinterpret_cast<const uint4*>(&myrow[q]);
+                    st_relaxed_sys_v4(slot + 4 + 2 * c, make_unit(bits.x, bits.y, epoch));
+                    st_relaxed_sys_v4(slot + 4 + 2 * c + 1, make_unit(bits.z, bits.w, epoch));
+                  }
+                }
+                if (lane == 1) st_relaxed_sys_v4(slot + 1, make_unit(ua.x, ua.y, epoch));
+                if (lane == 2) st_relaxed_sys_v4(slot + 2, un);
+                if (sizeof(T) == 8 && lane == 3) st_relaxed_sys_v4(slot + 3, uk);
+              }
+              if (lane == 0) st_relaxed_sys_v4(slot, rec);
+            }
+          }
+          // ---- poll the `world` level-2 records of this type in the local box (this read is the box barrier)
+          {
+            const uint4* rbase = box_base + ((size_t)par * BOX_RANKS * NCAND + k) * BOX_UNITS;
+            uint64_t t_start = 0;
+            uint32_t rounds = 0;
+            for (;;) {
+              bool ok = true;
+              w.g = 0.0; w.idx = -1; w.flags = 0;
+              wsrc = 0;
+              if (lane < world) {
+                const uint4 hh = ld_relaxed_sys_v4(rbase + (size_t)lane * NCAND * BOX_UNITS);
+                if ((hh.w >> 3) != epoch) ok = false;
+                else { w.g = __hiloint2double((int)hh.y, (int)hh.x); w.idx = (int)hh.z; w.flags = (int)(hh.w & 7u); wsrc = lane; }
+              }
+              if (__all_sync(0xffffffffu, ok)) break;
+              if ((++rounds & 63u) == 0) {
+                int bad = *(volatile int*)P.abort_flag | sh->status;
+                const uint64_t now = globaltimer_ns();
+                if (t_start == 0) t_start = now;
+                if (!bad && now - t_start > 6000000000ull) {
+                  *(volatile int*)P.abort_flag = 1;
+                  bad = 1;
+                }
+                if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
+              }
+            }
+            const int mine = w.idx;
+            redux_select(0xffffffffu, is_max, w);
+            const unsigned hold2 = __ballot_sync(0xffffffffu, w.idx >= 0 && mine == w.idx);
+            wsrc = __shfl_sync(0xffffffffu, wsrc, hold2 ? __ffs(hold2) - 1 : 0);
           }
         }
-      } else {
-        // ---- Solver.update / NuSolver.update: the analytic step (solver.py:82-145, 342-373) ----
-        // alpha units and the two rows are requested together: one memory round trip, not three
-        uint4 ua = make_uint4(0u, 0u, 0u, 0u), ub = ua;
-        const bool from_records = !(forced && epoch == 1);
-        if (from_records) { ua = load_unit(ti); ub = load_unit(tj); }
-        // (the slot-table entries of the two rows ride along in the same round trip)
-        const int gri = (int)((mirror && si >= lg) ? si - lg : si), grj = (int)((mirror && sj >= lg) ? sj - lg : sj);
-        int raw_si = -1, raw_sj = -1;
-        if (CACHE && P.cache_slots > 0) { raw_si = __ldcg(P.slot_of + gri); raw_sj = __ldcg(P.slot_of + grj); }
-        stamp(8);
-        if (!have_k) pair_k(si, sj, xi, xj, ni, nj, Kii, Kjj, Kij);
-        stamp(9);
-        if (from_records) { ai = settle_alpha(ua, ti); aj = settle_alpha(ub, tj); }
-        stamp(10);
-        const double yi = (fi & F_YPOS) ? 1.0 : -1.0;
-        const double yj = (fj & F_YPOS) ? 1.0 : -1.0;
-        const StepOut so = smo_step(nu, (double)Kii, (double)Kjj, (double)Kij, yi, yj, gi, gj, ai, aj, Cbox);
-        stamp(11);
-        // ---- Q-column cache: which of the two columns are already resident, which get stored now --------
-        int slot_i = -1, slot_j = -1, store_i = 0, store_j = 0;
-        if (CACHE && P.cache_slots > 0) {
-          slot_i = gri == L.ri ? L.si : (gri == L.rj ? L.sj : raw_si);
-          slot_j = grj == L.ri ? L.si : (grj == L.rj ? L.sj : raw_sj);
-          if (slot_i < 0 && L.n_cached < P.cache_slots) { slot_i = L.n_cached++; store_i = 1; }
-          if (grj == gri) { slot_j = slot_i; }
-          else if (slot_j < 0 && L.n_cached < P.cache_slots) { slot_j = L.n_cached++; store_j = 1; }
-        }
-        const int warm = (CACHE && P.cache_slots > 0 && slot_i >= 0 && slot_j >= 0 && !store_i && !store_j) ? 1 : 0;
-        if (lane == 0) {
-          sh->slot_i = slot_i; sh->slot_j = slot_j; sh->store_i = store_i; sh->store_j = store_j; sh->warm = warm;
-          sh->p_ri = L.ri; sh->p_rj = L.rj; sh->p_si = L.si; sh->p_sj = L.sj;
-        }
-        L.ri = gri; L.rj = grj; L.si = slot_i; L.sj = slot_j;
-        if (warm) ++L.warm_cnt;
-        L.stored_cnt += store_i + store_j;
-        L.di = so.di; L.dj = so.dj;
-#ifdef B2SVM_TIMELINE
-        if (P.dbg_steps && lane == 0 && cta == 0 && epoch <= (uint32_t)DBG_EPOCHS) {
-          double* o = P.dbg_steps + (size_t)DBG_EPOCHS * ncta * 6 + (size_t)(epoch - 1) * 2;
-          o[0] = so.ai; o[1] = so.aj;
-        }
-#endif
+        stamp(4);   // box-wide winner known
+
+        // ---- the winner's alpha, norm and row
+        if (w.idx >= 0 && !status) {
+          if (world > 1) {
+            // from the box slot of the rank it came from; every unit is re-read until it carries this epoch
+            const uint4* slot = box_base + (((size_t)par * BOX_RANKS + wsrc) * NCAND + k) * BOX_UNITS;
+            uint32_t spins = 0;
+            for (;;) {
+              bool ok = true;
+              const uint4 a4 = ld_relaxed_sys_v4(slot + 1);
+              const uint4 n4 = ld_relaxed_sys_v4(slot + 2);
+              const uint4 k4 = sizeof(T) == 8 ? ld_relaxed_sys_v4(slot + 3) : n4;
+              uint4 lo[QL], hi[QL];
 #pragma unroll
-        for (int q = 0; q < QL; ++q) {
-          const int c = lane + 32 * q;
-          if (c < CH) { xs[c] = xi[q]; xs[CH + c] = xj[q]; }
+              for (int q = 0; q < QL; ++q) {
+                const int c = lane + 32 * q;
+                if (c < CH && P.kind != K_PRECOMPUTED) {
+                  lo[q] = ld_relaxed_sys_v4(slot + 4 + 2 * c);
+                  hi[q] = ld_relaxed_sys_v4(slot + 4 + 2 * c + 1);
+                }
+              }
+              ok = unit_ok(a4, epoch) && unit_ok(n4, epoch) && unit_ok(k4, epoch);
+              w_alpha = __hiloint2double((int)a4.y, (int)a4.x);
+              if (sizeof(T) == 8) { nrm = (T)__hiloint2double((int)n4.y, (int)n4.x); kself = (T)__hiloint2double((int)k4.y, (int)k4.x); }
+              else { nrm = (T)__uint_as_float(n4.x); kself = (T)__uint_as_float(n4.y); }
+#pragma unroll
+              for (int q = 0; q < QL; ++q) {
+                const int c = lane + 32 * q;
+                if (c < CH && P.kind != K_PRECOMPUTED) {
+                  ok = ok && unit_ok(lo[q], epoch) && unit_ok(hi[q], epoch);
+                  const uint4 bits = make_uint4(lo[q].x, lo[q].y, hi[q].x, hi[q].y);
+                  row[q] = *reinterpret_cast<const V*>(&bits);
+                }
+              }
+              if (__all_sync(0xffffffffu, ok)) break;
+              if ((++spins & 4095u) == 0) {
+                const int bad = *(volatile int*)P.abort_flag;
+                if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
+              }
+            }
+            have_row = have_alpha = true;
+          } else {
+            // single GPU: the alpha unit its CTA published next to the record, the row straight from X
+            const uint4* unit = l1_base + ((((size_t)par * ncta + wsrc) * NCAND + k) * 2) + 1;
+            uint4 u = ld_relaxed_v4(unit);
+            if (P.kind != K_PRECOMPUTED) {
+              const long long lrow = (mirror && w.idx >= lg) ? w.idx - lg : w.idx;
+              const V* src = reinterpret_cast<const V*>(P.X) + lrow * CH;
+#pragma unroll
+              for (int q = 0; q < QL; ++q) {
+                const int c = lane + 32 * q;
+                if (c < CH) row[q] = src[c];
+              }
+              nrm = norms[lrow];
+              have_row = true;
+            }
+            kself = kdiag[(mirror && w.idx >= lg) ? w.idx - lg : w.idx];
+            uint32_t spins = 0;
+            while (!unit_ok(u, epoch)) {   // (the unit follows its record by one shared-memory hand-over)
+              u = ld_relaxed_v4(unit);
+              if ((++spins & 4095u) == 0 && *(volatile int*)P.abort_flag) { status = 1; break; }
+            }
+            w_alpha = __hiloint2double((int)u.y, (int)u.x);
+            have_alpha = true;
+          }
+        }
+      } else if (k < 2) {
+        // forced pair of the step-wise API (b2svm_update): no selection, no exchange
+        w.idx = (int)(k == 0 ? P.forced_i : P.forced_j);
+        w.g = __ldcg(G + w.idx);
+        w.flags = __ldcg(flags + w.idx);
+        w_alpha = __ldcg(alpha + w.idx);
+        have_alpha = true;
+        if (k == 0 && lane == 0) sh->ticket = NW;
+        if (P.kind != K_PRECOMPUTED) {
+          const long long lrow = (mirror && w.idx >= lg) ? w.idx - lg : w.idx;
+          const V* src = reinterpret_cast<const V*>(P.X) + lrow * CH;
+#pragma unroll
+          for (int q = 0; q < QL; ++q) {
+            const int c = lane + 32 * q;
+            if (c < CH) row[q] = src[c];
+          }
+          nrm = norms[lrow];
+          have_row = true;
+        }
+        kself = kdiag[(mirror && w.idx >= lg) ? w.idx - lg : w.idx];
+      }
+      (void)have_alpha;
+      stamp(8);   // winner's row / alpha on hand
+      // ---- hand the winner of this type to the leader: row into shared memory, K(x, x), slot-table entry
+      {
+        Selected<T> sv;
+        sv.g = w.g; sv.alpha = w_alpha; sv.idx = w.idx; sv.flags = w.flags;
+        sv.raw_slot = -1; sv.pad = 0;
+        sv.norm = nrm; sv.kself = kself;
+        if (w.idx >= 0) {
+          const long long grow = (mirror && w.idx >= lg) ? w.idx - lg : w.idx;
+          if (CACHE && P.cache_slots > 0 && lane == 0) sv.raw_slot = __ldcg(P.slot_of + grow);
+          if (have_row) {
+#pragma unroll
+            for (int q = 0; q < QL; ++q) {
+              const int c = lane + 32 * q;
+              if (c < CH) xs[k * CH + c] = row[q];
+            }
+          }
         }
         if (lane == 0) {
-          sh->ci = yi * so.di;
-          sh->cj = yj * so.dj;
-          sh->ai = so.ai;
-          sh->aj = so.aj;
-          sh->ni = ni;
-          sh->nj = nj;
-          sh->i = si;
-          sh->j = sj;
-          sh->fi = make_flags(yi > 0, so.ai, Cbox);
-          sh->fj = make_flags(yj > 0, so.aj, Cbox);
+          sh->sel[k] = sv;
+          if (status) sh->status = 1;
         }
       }
-      __syncwarp();
-      if (lane == 0) sh->leader = L;
-      stamp(5);   // leader done: step taken, x_i / x_j staged
+      named_bar_sync(3, ntypes * 32);   // the type warps meet
+      stamp(9);
+
+      if (warp == 0) {
+        // =========================== leader: working_set_select + the analytic step =========================
+        LeaderState L = sh->leader;
+        const int st_bad = sh->status;
+        const long long n_iter = (long long)epoch - 1;
+        // K(a, b) of two selected types, from the rows in shared memory (or the precomputed kernel matrix)
+        auto cross_k = [&](int ta, int tb) -> T {
+          const Selected<T>& A = sh->sel[ta];
+          const Selected<T>& B = sh->sel[tb];
+          if (CACHE && P.kind == K_PRECOMPUTED) {
+            const long long ra = (mirror && A.idx >= lg) ? A.idx - lg : A.idx, rb = (mirror && B.idx >= lg) ? B.idx - lg : B.idx;
+            return __ldg(reinterpret_cast<const T*>(P.cache) + ra * l + rb);
+          }
+          T dab = 0;
+#pragma unroll
+          for (int q = 0; q < QL; ++q) {
+            const int c = lane + 32 * q;
+            if (c < CH) dab = CK::dot(xs[ta * CH + c], xs[tb * CH + c], dab);
+          }
+          dab = warp_sum(dab);
+          return kernel_value(kp, dab, A.norm, B.norm);
+        };
+        // ---- decide the next pair (working_set_select) ------------------------------------------
+        int ti = 0, tj = 1;   // candidate types the pair comes from
+        bool stop_sel = false;
+        T Kij = 0;
+        bool have_k = false;
+        if (forced_now) {
+          // pair given by the caller
+        } else if (!nu) {
+          // solver.py:66-75
+          const int si0 = sh->sel[0].idx, sj0 = sh->sel[1].idx;
+          stop_sel = si0 < 0 || sj0 < 0 || (sh->sel[0].g - sh->sel[1].g < P.tol);
+        } else {
+          // solver.py:300-339: no tol test, gain comparison between the class-wise pairs
+          const bool pos_ok = sh->sel[0].idx >= 0 && sh->sel[1].idx >= 0;
+          const bool neg_ok = sh->sel[2].idx >= 0 && sh->sel[3].idx >= 0;
+          int pick = -1;   // 0 = '+' pair, 1 = '-' pair
+          if (!pos_ok && !neg_ok) stop_sel = true;
+          else if (!pos_ok) pick = 1;
+          else if (!neg_ok) pick = 0;
+          else {
+            const T Kp = cross_k(0, 1), Kn = cross_k(2, 3);
+            double quad_p = ((double)sh->sel[0].kself + (double)sh->sel[1].kself) - 2.0 * (double)Kp;
+            if (quad_p <= 0) quad_p = 1e-12;
+            const double dp = sh->sel[0].g - sh->sel[1].g;
+            const double gain_p = -(dp * dp) / quad_p;
+            double quad_n = ((double)sh->sel[2].kself + (double)sh->sel[3].kself) - 2.0 * (double)Kn;
+            if (quad_n <= 0) quad_n = 1e-12;
+            const double dn = sh->sel[2].g - sh->sel[3].g;
+            const double gain_n = -(dn * dn) / quad_n;
+            if (gain_p < gain_n) { pick = 0; Kij = Kp; }
+            else { pick = 1; Kij = Kn; }
+            have_k = true;
+          }
+          if (pick >= 0) { ti = pick == 0 ? 0 : 2; tj = ti + 1; }
+        }
+        const Selected<T> SI = sh->sel[ti], SJ = sh->sel[tj];
+        const int si = stop_sel ? -1 : SI.idx, sj = stop_sel ? -1 : SJ.idx;
+#ifdef B2SVM_TIMELINE
+        if (P.dbg_steps && lane == 0 && epoch <= (uint32_t)DBG_EPOCHS) {
+          double* o = P.dbg_steps + ((size_t)(epoch - 1) * ncta + cta) * DBG_W;
+          o[0] = si; o[1] = sj; o[2] = SI.g; o[3] = SJ.g; o[4] = SI.alpha; o[5] = SJ.alpha;
+        }
+#endif
+        if (stop_sel) L.converged = 1;
+        const bool exit_now = st_bad || stop_sel || n_iter >= P.max_iter;
+        if (exit_now) {
+          if (lane == 0) {
+            sh->stop = 1;
+            if (cta == 0) {
+              SolveResult r;
+              r.n_iter = n_iter;
+              r.last_i = si;
+              r.last_j = sj;
+              r.cold_sweeps = n_iter - L.warm_cnt;
+              r.warm_sweeps = L.warm_cnt;
+              r.cols_stored = L.stored_cnt;
+              r.cache_used = L.n_cached;
+              if (CACHE && P.cache_slots > 0 && L.ri >= 0) {   // pending slot-table entries of the last step
+                if (L.si >= 0) P.slot_of[L.ri] = L.si;
+                if (L.sj >= 0) P.slot_of[L.rj] = L.sj;
+              }
+              r.di = L.di;
+              r.dj = L.dj;
+              r.converged = L.converged;
+              r.status = st_bad;
+              r.pad[0] = r.pad[1] = 0;
+              *P.result = r;
+            }
+          }
+        } else {
+          // ---- Solver.update / NuSolver.update: the analytic step (solver.py:82-145, 342-373) ----
+          if (!have_k) Kij = cross_k(ti, tj);
+          stamp(10);
+          const int fi = SI.flags, fj = SJ.flags;
+          const double yi = (fi & F_YPOS) ? 1.0 : -1.0;
+          const double yj = (fj & F_YPOS) ? 1.0 : -1.0;
+          const StepOut so = smo_step(nu, (double)SI.kself, (double)SJ.kself, (double)Kij, yi, yj, SI.g, SJ.g, SI.alpha, SJ.alpha, Cbox);
+          stamp(11);
+          // ---- Q-column cache: which of the two columns are already resident, which get stored now --------
+          const int gri = (int)((mirror && si >= lg) ? si - lg : si), grj = (int)((mirror && sj >= lg) ? sj - lg : sj);
+          int slot_i = -1, slot_j = -1, store_i = 0, store_j = 0;
+          if (CACHE && P.cache_slots > 0) {
+            slot_i = gri == L.ri ? L.si : (gri == L.rj ? L.sj : SI.raw_slot);
+            slot_j = grj == L.ri ? L.si : (grj == L.rj ? L.sj : SJ.raw_slot);
+            if (slot_i < 0 && L.n_cached < P.cache_slots) { slot_i = L.n_cached++; store_i = 1; }
+            if (grj == gri) { slot_j = slot_i; }
+            else if (slot_j < 0 && L.n_cached < P.cache_slots) { slot_j = L.n_cached++; store_j = 1; }
+          }
+          const int warm = (CACHE && P.cache_slots > 0 && slot_i >= 0 && slot_j >= 0 && !store_i && !store_j) ? 1 : 0;
+          if (lane == 0) {
+            sh->slot_i = slot_i; sh->slot_j = slot_j; sh->store_i = store_i; sh->store_j = store_j; sh->warm = warm;
+            sh->p_ri = L.ri; sh->p_rj = L.rj; sh->p_si = L.si; sh->p_sj = L.sj;
+          }
+          L.ri = gri; L.rj = grj; L.si = slot_i; L.sj = slot_j;
+          if (warm) ++L.warm_cnt;
+          L.stored_cnt += store_i + store_j;
+          L.di = so.di; L.dj = so.dj;
+#ifdef B2SVM_TIMELINE
+          if (P.dbg_steps && epoch <= (uint32_t)DBG_EPOCHS) {
+            // checksum of both rows as the leader holds them (bit pattern sum over all chunks)
+            unsigned long long cs = 0;
+#pragma unroll
+            for (int q = 0; q < QL; ++q) {
+              const int c = lane + 32 * q;
+              if (c < CH) {
+                const uint4 a = *reinterpret_cast<const uint4*>(&xs[ti * CH + c]);
+                const uint4 b = *reinterpret_cast<const uint4*>(&xs[tj * CH + c]);
+                cs += (unsigned long long)a.x + 3ull * a.y + 5ull * a.z + 7ull * a.w + 11ull * b.x + 13ull * b.y + 17ull * b.z + 19ull * b.w;
+              }
+            }
+            for (int mm = 16; mm >= 1; mm >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, mm);
+            if (lane == 0) {
+              double* o = P.dbg_steps + ((size_t)(epoch - 1) * ncta + cta) * DBG_W;
+              o[6] = (double)SI.kself; o[7] = (double)SJ.kself; o[8] = (double)Kij; o[9] = yi * so.di; o[10] = yj * so.dj;
+              o[11] = (double)(cs & 0xffffffffffffull) + (double)SI.norm * 1e-3 + (double)SJ.norm * 1e-6;
+              if (cta == 0) {
+                double* o2 = P.dbg_steps + (size_t)DBG_EPOCHS * ncta * DBG_W + (size_t)(epoch - 1) * 2;
+                o2[0] = so.ai; o2[1] = so.aj;
+              }
+            }
+          }
+#endif
+          if (lane == 0) {
+            sh->ci = yi * so.di;
+            sh->cj = yj * so.dj;
+            sh->ai = so.ai;
+            sh->aj = so.aj;
+            sh->ni = SI.norm;
+            sh->nj = SJ.norm;
+            sh->i = si;
+            sh->j = sj;
+            sh->ti = ti;
+            sh->tj = tj;
+            sh->fi = make_flags(yi > 0, so.ai, Cbox);
+            sh->fj = make_flags(yj > 0, so.aj, Cbox);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) sh->leader = L;
+        stamp(5);   // leader done: step taken
+      }
     }
     named_bar_sync(2, NW * 32);   // (A) selection + step visible to all consumer warps
     if (sh->stop) break;
@@ -861,12 +954,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     const double nai = sh->ai, naj = sh->aj;
     const T ni = sh->ni, nj = sh->nj;
     V xi[C::CPL], xj[C::CPL];
+    {
+      const V* xri = xs + sh->ti * CH;
+      const V* xrj = xs + sh->tj * CH;
 #pragma unroll
-    for (int q = 0; q < C::CPL; ++q) {
-      xi[q] = xs[lig + q * C::LPR];
-      xj[q] = xs[CH + lig + q * C::LPR];
+      for (int q = 0; q < C::CPL; ++q) {
+        xi[q] = xri[lig + q * C::LPR];
+        xj[q] = xrj[lig + q * C::LPR];
+      }
     }
     reset_best();
+#ifdef B2SVM_TIMELINE
+    if (P.dbg_steps && warp == NW - 1 && epoch <= (uint32_t)DBG_EPOCHS) {
+      unsigned long long cs = 0;
+#pragma unroll
+      for (int q = 0; q < C::CPL; ++q) {
+        const uint4 a = *reinterpret_cast<const uint4*>(&xi[q]);
+        const uint4 b = *reinterpret_cast<const uint4*>(&xj[q]);
+        cs += (unsigned long long)a.x + 3ull * a.y + 5ull * a.z + 7ull * a.w + 11ull * b.x + 13ull * b.y + 17ull * b.z + 19ull * b.w;
+      }
+      for (int mm = 16; mm >= 1; mm >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, mm);
+      if (lane == 0) {
+        double* o = P.dbg_steps + ((size_t)(epoch - 1) * ncta + cta) * DBG_W;
+        o[12] = ci; o[13] = cj;
+        o[14] = (double)(cs & 0xffffffffffffull) + (double)ni * 1e-3 + (double)nj * 1e-6;
+        o[15] = (double)wi * 1e6 + (double)wj;
+      }
+    }
+#endif
     // ---- Q-column cache plan of this sweep ---------------------------------------------------------
     const bool warm = CACHE && sh->warm != 0;
     const int store_i = CACHE ? sh->store_i : 0, store_j = CACHE ? sh->store_j : 0;
@@ -909,8 +1024,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           mn = __shfl_sync(0xffffffffu, mn, 0);
         }
       }
-      const RowState<T> cur = pf;
-      pf = load_row_state(mn * SUB + subn);
+      RowState<T> cur = pf;
+      if (!one_tile) pf = load_row_state(mn * SUB + subn);
 
       const long long row = row0 + (long long)t * C::BR + rib;
       const bool valid = lane_active && row < row1;
@@ -987,7 +1102,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           int f = cur.f0;
           if (v == wi) { f = nfi; flags[row] = (uint8_t)nfi; alpha[row] = nai; }
           else if (v == wj) { f = nfj; flags[row] = (uint8_t)nfj; alpha[row] = naj; }
-          consider(nu, f, g, v, best);
+          consider(nu, f, g, v, best, (P.debug_flags & 4) ? nullptr : alpha + row);
+          cur.g0 = g;
+          cur.f0 = f;
         }
         if (mirror) {
           const int v = (int)(row + goff + lg);
@@ -996,9 +1113,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           int f = cur.f1;
           if (v == wi) { f = nfi; flags[row + l] = (uint8_t)nfi; alpha[row + l] = nai; }
           else if (v == wj) { f = nfj; flags[row + l] = (uint8_t)nfj; alpha[row + l] = naj; }
-          consider(nu, f, g, v, best);
+          consider(nu, f, g, v, best, alpha + row + l);
+          cur.g1 = g;
+          cur.f1 = f;
         }
       }
+      if (one_tile) pf = cur;   // the warp's only tile: gradient, flags and norm stay in registers for the next sweep
       m = mn;
       sub = subn;
     }
@@ -1010,7 +1130,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     }
 #endif
     sweep_warm = false;
-    pf = load_row_state(warp * SUB);   // first tile of the next sweep (after this thread's own stores to it)
+    if (!one_tile) pf = load_row_state(warp * SUB);   // first tile of the next sweep (after this thread's own stores to it)
     if (!warm) {
       if (!resident) {
         const unsigned q = tb_mod + (unsigned)NM;

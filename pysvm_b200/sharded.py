@@ -1,11 +1,12 @@
 """Row-sharded SMO over the GPUs of one NVLink / NVSwitch box.
 
-One process per GPU (``torch.distributed``).  Each rank owns a contiguous slice of the training rows
-and the matching slices of ``alpha`` / ``neg_y_grad``; per SMO iteration the persistent kernels of all
-ranks exchange their working-set candidates through 16-byte tagged records written straight into
-each other's memory over NVLink (CUDA IPC peer mappings).  X itself is read-only and replicated on every
-GPU, so the two winning rows of an iteration are local reads.  ``torch.distributed`` is used for plumbing only: the one-off exchange of
-IPC handles, a barrier before each solve, and the final gather / reduction of results.
+One process per GPU (``torch.distributed``).  Each rank holds ONLY its contiguous slice of the training rows and
+the matching slices of ``alpha`` / ``neg_y_grad`` / cached columns.  Per SMO iteration the persistent kernels first
+agree on a winner per GPU (level 1, local memory), then the CTA that owns a GPU's winner writes it -- record, alpha,
+norm and the row x itself, as self-validating 16-byte units -- straight into every GPU's memory over NVLink (CUDA IPC
+peer mappings); every GPU picks the same box-wide pair and already holds x_i, x_j for the next sweep.
+``torch.distributed`` is plumbing only: the one-off exchange of IPC handles, a barrier before each solve, the
+transient all-gather of rows for the nu / one-class initial gradient, and the final gather / reduction of results.
 """
 from __future__ import annotations
 
@@ -127,28 +128,28 @@ def all_gather_array(a: np.ndarray, group=None) -> np.ndarray:
 
 
 class ShardedColumns(QColumns):
-    """QColumns of one rank: the FULL X (read-only, replicated on every GPU so the two winning rows of an
-    iteration are local reads) with this rank's slice of y; carries the shard geometry to b2svm_create."""
+    """QColumns of one rank: THIS RANK'S rows of X (uploaded from the host slice; the other ranks' rows never reach
+    this GPU's memory) with this rank's slice of y; carries the shard geometry to b2svm_create."""
 
     def __init__(self, X_full, y_local, kernel: KernelSpec, shard: Shard, mirror: bool = False, device=None,
                  cache_bytes=None):
         self.shard = shard
-        super().__init__(X_full, y_local, kernel, mirror=mirror, device=device, cache_bytes=cache_bytes)
-        assert self.X.shape[0] == shard.n_global
-
-    def _n_local_rows(self) -> int:
-        return self.shard.n_local
+        self.X_host = X_full if not isinstance(X_full, torch.Tensor) else None     # kept by reference (no copy)
+        X_local = X_full[shard.rows()]
+        super().__init__(X_local, y_local, kernel, mirror=mirror, device=device, cache_bytes=cache_bytes)
+        assert self.X.shape[0] == shard.n_local
+        self.h2d_bytes = self.X.numel() * self.X.element_size()
 
     def local_rows(self) -> torch.Tensor:
-        return self.X[self.shard.rows()]
+        return self.X
 
 
 class ShardedSolver(SolverWithCache):
     """``SolverWithCache`` whose ``solve`` runs row-sharded over the process group."""
 
-    def __init__(self, p_local, y_local, C, tol, func: ShardedColumns, group=None):
+    def __init__(self, p_local, y_local, C, tol, func: ShardedColumns, group=None, max_iter_hint=None):
         self.group = group
-        super().__init__(p_local, y_local, C, tol, func=func)
+        super().__init__(p_local, y_local, C, tol, func=func, max_iter_hint=max_iter_hint)
         handles = all_gather_bytes(self._engine.export_mailbox(), group)
         self._engine.attach_mailboxes(handles)
 
@@ -168,23 +169,46 @@ class ShardedSolver(SolverWithCache):
         return rho_from_partials(combine_bias_partials(parts))
 
 
-def rows_kernel_sum(func: "ShardedColumns", coef_rows: np.ndarray) -> torch.Tensor:
-    """m_t = sum over ALL training rows s of coef_s K(x_s, x_t) for this rank's rows t.  X is replicated on every
-    GPU, so the initial gradient of the nu / one-class variants (solver.py:279-281, oc_svm.py:94-95) needs no
-    communication: every rank evaluates its own slice of K alpha_0 (K7, b2svm_kernel_matvec)."""
+def all_rows(func: "ShardedColumns", group=None) -> torch.Tensor:
+    """Every rank's rows, assembled on this GPU for ONE computation (the caller drops the tensor afterwards): the
+    initial gradient of the nu / one-class starts needs K against all support rows.  NCCL: one all-gather of the
+    padded slices over NVLink; gloo (CPU tests): through the host."""
+    shard, X = func.shard, func.X
+    rpr, world = shard.rows_per_rank, shard.world
+    mine = torch.zeros((rpr, X.shape[1]), dtype=X.dtype, device=X.device)
+    mine[:shard.n_local] = X
+    if dist.get_backend(group) == "nccl":
+        out = torch.empty((world * rpr, X.shape[1]), dtype=X.dtype, device=X.device)
+        dist.all_gather_into_tensor(out, mine, group=group)
+    else:
+        parts = [torch.empty_like(mine, device="cpu") for _ in range(world)]
+        dist.all_gather(parts, mine.cpu(), group=group)
+        out = torch.cat(parts).to(X.device)
+    return out[:shard.n_global]
+
+
+def rows_kernel_sum(func: "ShardedColumns", coef_rows: np.ndarray, group=None) -> torch.Tensor:
+    """m_t = sum over ALL training rows s of coef_s K(x_s, x_t) for this rank's rows t: the initial gradient of the
+    nu / one-class variants (solver.py:279-281, oc_svm.py:94-95).  The support rows of the other ranks are gathered
+    for this one mat-vec (K7, b2svm_kernel_matvec) and released again; the solve itself only ever holds local rows."""
     coef = torch.from_numpy(np.ascontiguousarray(coef_rows, dtype=np.float64)).to(func.device)
-    return kernel_matvec(func.kernel, func.X, coef, func.local_rows())
+    Xall = all_rows(func, group)
+    out = kernel_matvec(func.kernel, Xall, coef, func.local_rows())
+    del Xall
+    return out
 
 
 class ShardedNuSolver(ShardedSolver):
     """``NuSolverWithCache`` (solver.py:422-486) row-sharded: four candidate types cross NVLink per iteration."""
     _variant = N.SOLVER_NU
 
-    def __init__(self, p_global, y_global, t: float, C, tol, func: ShardedColumns, mirror: bool, group=None):
+    def __init__(self, p_global, y_global, t: float, C, tol, func: ShardedColumns, mirror: bool, group=None,
+                 max_iter_hint=None):
         self.t = t
         self._mirror = mirror
         self._y_global = np.asarray(y_global, dtype=np.float64)
-        super().__init__(local_vector(np.asarray(p_global, dtype=np.float64), func.shard, mirror), func.y, C, tol, func, group)
+        super().__init__(local_vector(np.asarray(p_global, dtype=np.float64), func.shard, mirror), func.y, C, tol, func, group,
+                         max_iter_hint=max_iter_hint)
 
     def _init_state(self):
         # solver.py:269-281: the sequential alpha fill runs over the GLOBAL variable order; this rank keeps its slice.
@@ -194,7 +218,7 @@ class ShardedNuSolver(ShardedSolver):
         ya = a0 * self._y_global
         l = shard.n_global
         coef_rows = ya[:l] + ya[l:] if self._mirror else ya
-        m = rows_kernel_sum(func, coef_rows)
+        m = rows_kernel_sum(func, coef_rows, self.group)
         if self._mirror:
             m = torch.cat([m, m])
         self._alpha.copy_(torch.from_numpy(local_vector(a0, shard, self._mirror)))
@@ -204,6 +228,61 @@ class ShardedNuSolver(ShardedSolver):
     def calculate_rho_b(self):
         parts = all_gather_array(self._engine.bias_partials(), self.group)
         return rho_b_from_partials(combine_bias_partials(parts))
+
+
+class EmulatedRanks:
+    """The ranks of a row-sharded solve emulated on ONE GPU (``b2svm_solve_ranks_on_one_gpu``): every rank is a
+    group of CTAs of one cooperative launch and the level-2 exchange runs through local memory.  Same device code and
+    the same host-side slicing as the multi-GPU path; used to test the exchange protocol on a single-GPU box.
+
+        ranks = EmulatedRanks(X, y, p, C, tol, kernel, world=4)           # y, p: global per-variable vectors
+        stats = ranks.solve(1000); alpha = ranks.gather(ranks.alphas())
+    """
+
+    def __init__(self, X, y, p, C, tol, kernel: KernelSpec, world: int, mirror: bool = False, variant=N.SOLVER_C,
+                 cache_bytes=0, device=None):
+        from .solver import Solver, default_device
+        dev = torch.device(device) if device is not None else default_device()
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        y, p = np.asarray(y, dtype=np.float64), np.asarray(p, dtype=np.float64)
+        self.world, self.mirror = world, mirror
+        self.shards, self.solvers = [], []
+        for r in range(world):
+            shard = plan(X.shape[0], world, r)
+            func = ShardedColumns(X, local_vector(y, shard, mirror), kernel, shard, mirror=mirror, device=dev,
+                                  cache_bytes=cache_bytes)
+            func.max_ctas = max(1, sms // world)
+            sol = Solver.__new__(SolverWithCache)
+            sol._variant = variant
+            Solver.__init__(sol, None, local_vector(p, shard, mirror), func.y, C, tol, func=func)
+            self.shards.append(shard)
+            self.solvers.append(sol)
+
+    def set_state(self, alpha, neg_y_grad):
+        """Global alpha / neg_y_grad (e.g. the nu / one-class start), dealt to the ranks."""
+        for shard, sol in zip(self.shards, self.solvers):
+            sol.alpha = local_vector(np.asarray(alpha, dtype=np.float64), shard, self.mirror)
+            sol.neg_y_grad = local_vector(np.asarray(neg_y_grad, dtype=np.float64), shard, self.mirror)
+
+    def solve(self, max_iter: int):
+        import ctypes as C
+        lib = N.load()
+        handles = (C.c_void_p * self.world)(*[s._engine.h for s in self.solvers])
+        stats = (N.SolveStats * self.world)()
+        N.check(lib.b2svm_solve_ranks_on_one_gpu(handles, self.world, int(max_iter), stats))
+        return [N.SolveStats.from_buffer_copy(bytes(st)) for st in stats]
+
+    def gather(self, name: str) -> np.ndarray:
+        """'alpha' or 'neg_y_grad' of all ranks in global variable order."""
+        n = self.shards[0].n_global
+        out = np.zeros(2 * n if self.mirror else n)
+        for shard, sol in zip(self.shards, self.solvers):
+            v = getattr(sol, name).cpu().numpy()
+            r = shard.rows()
+            out[r] = v[:shard.n_local]
+            if self.mirror:
+                out[n + r.start:n + r.stop] = v[shard.n_local:]
+        return out
 
 
 def schedule_subproblems(sizes, world: int):
@@ -300,7 +379,7 @@ def fit_csvc_sharded(X: np.ndarray, y01: np.ndarray, C: float, kernel: KernelSpe
     y[y != 1] = -1
     shard = plan(X.shape[0], world, rank)
     func = ShardedColumns(X, local_vector(y, shard, False), kernel, shard, cache_bytes=cache_bytes)
-    solver = ShardedSolver(local_vector(-np.ones(X.shape[0]), shard, False), func.y, C, tol, func, group)
+    solver = ShardedSolver(local_vector(-np.ones(X.shape[0]), shard, False), func.y, C, tol, func, group, max_iter_hint=max_iter)
     stats = solver.solve(max_iter)
     return solver, shard, stats
 
@@ -317,7 +396,7 @@ def fit_svr_sharded(X: np.ndarray, z: np.ndarray, C: float, eps: float, kernel: 
     p[l:] += z
     shard = plan(l, world, rank)
     func = ShardedColumns(X, local_vector(y, shard, True), kernel, shard, mirror=True)
-    solver = ShardedSolver(local_vector(p, shard, True), func.y, C, tol, func, group)
+    solver = ShardedSolver(local_vector(p, shard, True), func.y, C, tol, func, group, max_iter_hint=max_iter)
     stats = solver.solve(max_iter)
     return solver, shard, stats
 
@@ -330,10 +409,10 @@ def fit_oneclass_sharded(X: np.ndarray, nu: float, kernel: KernelSpec, tol: floa
     l = X.shape[0]
     shard = plan(l, world, rank)
     func = ShardedColumns(X, np.ones(shard.n_local), kernel, shard)
-    solver = ShardedSolver(np.zeros(shard.n_local), func.y, 1.0, tol, func, group)
+    solver = ShardedSolver(np.zeros(shard.n_local), func.y, 1.0, tol, func, group, max_iter_hint=max_iter)
     a0 = oneclass_initial_alpha(nu, l)
     solver.alpha = local_vector(a0, shard, False)
-    solver.neg_y_grad = -rows_kernel_sum(func, a0)
+    solver.neg_y_grad = -rows_kernel_sum(func, a0, group)
     stats = solver.solve(max_iter)
     return solver, shard, stats
 
@@ -346,7 +425,7 @@ def fit_nusvc_sharded(X: np.ndarray, y01: np.ndarray, nu: float, kernel: KernelS
     l = X.shape[0]
     shard = plan(l, world, rank)
     func = ShardedColumns(X, local_vector(y, shard, False), kernel, shard)
-    solver = ShardedNuSolver(np.zeros(l), y, nu * l, 1.0, tol, func, False, group)
+    solver = ShardedNuSolver(np.zeros(l), y, nu * l, 1.0, tol, func, False, group, max_iter_hint=max_iter)
     stats = solver.solve(max_iter)
     return solver, shard, stats
 
@@ -362,7 +441,7 @@ def fit_nusvr_sharded(X: np.ndarray, z: np.ndarray, C: float, nu: float, kernel:
     p[:l], p[l:] = -np.asarray(z, dtype=float), np.asarray(z, dtype=float)
     shard = plan(l, world, rank)
     func = ShardedColumns(X, local_vector(y, shard, True), kernel, shard, mirror=True)
-    solver = ShardedNuSolver(p, y, C * l * nu, C, tol, func, True, group)
+    solver = ShardedNuSolver(p, y, C * l * nu, C, tol, func, True, group, max_iter_hint=max_iter)
     stats = solver.solve(max_iter)
     return solver, shard, stats
 

@@ -136,22 +136,22 @@ class _Engine:
         n_glob = shard.n_global if shard is not None else X.shape[0]
         full_q = int(n_glob) * int(d.n_rows) * esz
         cb = func.cache_bytes
+        if max_columns is not None and cb is None and max_columns < 2 * int(n_glob) * (2 if func.mirror else 1):
+            # automatic policy: columns are only re-used once variables get selected again, i.e. after the
+            # opening phase in which every step drives fresh variables to a bound.  A run capped below one
+            # step per variable cannot get there, so it skips the cache (and its 4 B/row store traffic).
+            cb = 0
         if cb is None:
             env = os.environ.get("B2SVM_CACHE_GB")
             if env is not None:
                 cb = int(float(env) * (1 << 30))
             else:
-                free, _total = torch.cuda.mem_get_info(func.device)
+                free, _total = torch.cuda.mem_get_info(func.device)      # (a ~3 ms driver call: only when needed)
                 cb = int(free * 0.7)
-        if max_columns is not None and func.cache_bytes is None:
-            # automatic policy: columns are only re-used once variables get selected again, i.e. after the
-            # opening phase in which every step drives fresh variables to a bound.  A run capped below one
-            # step per variable cannot get there, so it skips the cache (and its 4 B/row store traffic).
-            if max_columns < 2 * int(d.n_vars):
-                cb = 0
-            cb = min(int(cb), int(max_columns) * int(d.n_rows) * esz)
+            if max_columns is not None:
+                cb = min(int(cb), int(max_columns) * int(d.n_rows) * esz)
         d.cache_bytes = max(0, min(int(cb), full_q))
-        d.max_ctas = max_ctas
+        d.max_ctas = max_ctas or int(getattr(func, "max_ctas", 0) or 0)
         if shard is None:
             d.rank, d.world = 0, 1
             d.row_offset, d.n_rows_global = 0, X.shape[0]

@@ -1,6 +1,7 @@
 """Per-phase timeline of the persistent kernel's leader (CTA 0), B2SVM_TIMELINE=1.
-slots: 0 sweep done | 1 CTA warps joined | 2 record published | 3 all records read | 4 winners known
-       5 step taken | 6 sweep starts"""
+slots (type warp 0 of CTA 0): 0 sweep done | 1 CTA warps joined | 7 CTA winner | 2 level-1 record published |
+       3 GPU winner known (level-1 poll) | 4 box winner known (level-2, world > 1) | 8 winner's row / alpha on hand |
+       9 type warps met | 10 K_ij | 11 step | 5 leader done | 6 sweep starts"""
 import os, sys, ctypes as C
 os.environ["B2SVM_TIMELINE"] = "1"
 import numpy as np
@@ -37,20 +38,20 @@ def run(n, d, iters, dtype=np.float32):
     print('   sweep time by CTA index block of 16 (epoch 10 / 40):', [(int(ct[b:b+16, 0].mean()), int(ct[b:b+16, 1].mean())) for b in range(0, st.n_ctas, 16)])
     k = min(iters, 60)
     seg = t[2:k]      # skip first epochs
-    names = ["join(0->1)", "publish(1->2)", "poll+read(2->3)", "reduce(3->4)", "step(4->5)", "bar(5->6)", "sweep(6->next0)"]
-    d01 = [seg[:, 1] - seg[:, 0], seg[:, 2] - seg[:, 1], seg[:, 3] - seg[:, 2], seg[:, 4] - seg[:, 3],
-           seg[:, 5] - seg[:, 4], seg[:, 6] - seg[:, 5], np.r_[seg[1:, 0] - seg[:-1, 6], 0]]
+    chain = [("join (0->1)", 0, 1), ("CTA winner (1->7)", 1, 7), ("publish L1 (7->2)", 7, 2), ("alpha park + L1 poll (2->3)", 2, 3),
+             ("level 2 (3->4)", 3, 4), ("row / alpha fetch (4->8)", 4, 8), ("kself + type barrier (8->9)", 8, 9),
+             ("select + K_ij (9->10)", 9, 10), ("smo_step (10->11)", 10, 11), ("cache plan + hand-over (11->5)", 11, 5),
+             ("bar (5->6)", 5, 6)]
     us = st.device_ms * 1e3 / st.n_iter
     print(f"n={n} d={d} {np.dtype(dtype).name}: {us:.2f} us/it, ctas {st.n_ctas}; cycles per phase (median):")
     tot = 0
-    for nm, v in zip(names, d01):
-        print(f"   {nm:18s} {np.median(v):9.0f}")
-        tot += np.median(v)
-    print(f"   total {tot:.0f} cycles -> {tot/us:.0f} cycles/us")
-    fine = [("join->CTA winners (1->7)", seg[:, 7] - seg[:, 1]), ("push record (7->2)", seg[:, 2] - seg[:, 7]), ("decide + issue loads (4->8)", seg[:, 8] - seg[:, 4]),
-            ("rows + pair kernels (8->9)", seg[:, 9] - seg[:, 8]), ("alpha settled (9->10)", seg[:, 10] - seg[:, 9]), ("smo_step (10->11)", seg[:, 11] - seg[:, 10]), ("cache plan + publish (11->5)", seg[:, 5] - seg[:, 11])]
-    for nm, v in fine:
-        print(f"      {nm:30s} {np.median(v):9.0f}")
+    for nm, a, b in chain:
+        v = np.median(seg[:, b] - seg[:, a])
+        print(f"   {nm:34s} {v:9.0f}")
+        tot += v
+    sw = np.median(seg[1:, 0] - seg[:-1, 6])
+    print(f"   {'sweep (6->next 0)':34s} {sw:9.0f}")
+    print(f"   chain {tot:.0f} + sweep {sw:.0f} = {tot + sw:.0f} cycles -> {(tot + sw)/us:.0f} cycles/us")
     base = wt[:11, 0].min()
     print("   per-warp sweep at epoch 10 (start, end rel. cycles; tiles; wait cycles):")
     for w in range(11):

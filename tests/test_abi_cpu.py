@@ -151,3 +151,27 @@ def test_host_std_every_small_length_and_block_edges():
             out = C.c_double()
             N.check(lib.b2svm_host_std(x.ctypes.data, n, code, C.byref(out)))
             assert dt(out.value) == x.std(), (dt, n)
+
+
+def test_polled_exchange_units_are_read_by_single_128_bit_loads():
+    """The in-kernel exchange relies on {payload, tag} travelling in ONE 16-byte memory transaction.  ptxas narrows a
+    vector load whose components are partly dead into scalar loads (this happened: a stale payload then passed the tag
+    check once in ~10^4 iterations), so every polled unit keeps all four words alive.  Guard it in the SASS: no scalar
+    or 64-bit STRONG.SYS global load may exist in the persistent kernels (the abort flag is a generic LD, not LDG)."""
+    import shutil
+    import subprocess
+    from pysvm_b200 import build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    build.build()
+    checked = 0
+    for name in os.listdir(build.LIBDIR):
+        if not (name.startswith("b2svm_launch_") and name.endswith(".o")):
+            continue
+        sass = subprocess.run([cuobjdump, "-sass", os.path.join(build.LIBDIR, name)], capture_output=True, text=True).stdout
+        narrowed = [ln for ln in sass.splitlines() if "LDG.E.STRONG.SYS " in ln or "LDG.E.64.STRONG.SYS " in ln]
+        assert not narrowed, (name, narrowed[:3])
+        assert sass.count("LDG.E.128.STRONG.SYS") > 0 and sass.count("STG.E.128.STRONG.SYS") > 0, name
+        checked += 1
+    assert checked == 4

@@ -142,3 +142,12 @@ def test_subproblem_schedule_is_balanced_and_deterministic():
         assert max(load) - min(load) <= max(sizes)
     assert schedule_subproblems([5, 5, 5], 2) == [0, 1, 0]
     assert schedule_subproblems([], 4) == []
+
+
+def test_shardable_is_a_pure_predicate():
+    """n=200 on 8 GPUs: rpr = 32, rank 7 would be empty -> EVERY rank refuses (none blocks in a collective alone)."""
+    assert not SH.shardable(200, 8)
+    for r in range(8):
+        with pytest.raises(ValueError):
+            SH.plan(200, 8, r)
+    assert SH.shardable(200, 4) and SH.shardable(33, 2) and SH.shardable(200000, 8)
