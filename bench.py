@@ -12,8 +12,11 @@ path: every iteration sweeps X once) on the synthetic C3 problem of SURVEY secti
            HOST arrays: host->device copy of X, y, the solve, and the device->host read of alpha / rho
            are all inside the timed region
   roofline / cpu_baseline / clocks: see DESIGN.md section 4.
-`--impl reference` times the reference algorithm on the host cores (the NumPy oracle port, all BLAS
-threads) on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (Kaslanarian/PySVM, copied to oracle/_ref/ by oracle/make_ref.py;
+git-ignored, shipped to the GPU box) on the host cores, all BLAS threads, on a bounded sample of the same workload;
+if that copy is missing it falls back to the NumPy oracle port and says so (`cpu_baseline.kind`).
+Every line carries `parity`: n_iter, the next working pair and sha256(alpha) of the value leg -- identical at every N
+when the row-sharded solve is bit-identical to the single-GPU solve.
 """
 from __future__ import annotations
 
@@ -130,38 +133,153 @@ def use_all_host_threads(n):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def load_reference():
+    """The unmodified reference package from oracle/_ref (see oracle/make_ref.py), or None."""
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "pysvm")):
+        return None
+    import contextlib, io, warnings
+    sys.path.insert(0, ref_root)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            with contextlib.redirect_stderr(io.StringIO()):
+                from pysvm.svm.svc import BiKernelSVC as RefSVC      # noqa: E402
+        return RefSVC
+    except Exception:
+        return None
+    finally:
+        sys.path.remove(ref_root)
+
+
 def run_reference(args, rank, world):
-    """The reference algorithm on the host: oracle port (NumPy/OpenBLAS, all cores), bounded sample."""
+    """The reference's own CPU implementation of the path on the host cores (rank 0 only), bounded sample."""
     if rank != 0:
         return
-    from oracle import smo_oracle as O
+    import contextlib, io
     X, y01 = synth()
     cores = os.cpu_count()
     use_all_host_threads(cores)        # torchrun exports OMP_NUM_THREADS=1 to every rank
-    O.fit_csvc(X, y01, max_iter=2)                                   # touch everything once
+    RefSVC = load_reference()
+    if RefSVC is not None:
+        kind = "reference"
+        what = "the unmodified reference (oracle/_ref/pysvm: BiKernelSVC.fit, NumPy + OpenBLAS, threads = all cores)"
+
+        def fit(iters):
+            with contextlib.redirect_stdout(io.StringIO()):
+                RefSVC(max_iter=iters).fit(X, y01)
+            return iters                    # the loop runs max_iter updates unless it converges (it does not in 20)
+    else:
+        from oracle import smo_oracle as O
+        kind = "port"
+        what = "oracle/smo_oracle.py (NumPy port of the reference; oracle/_ref/pysvm is missing on this box)"
+
+        def fit(iters):
+            return O.fit_csvc(X, y01, max_iter=iters).n_iter
+    fit(2)                                                          # touch everything once
     for _ in range(args.warmup):
-        O.fit_csvc(X, y01, max_iter=2)
+        fit(2)
     t0 = time.perf_counter()
     done = 0
     for _ in range(args.steps):
-        fit = O.fit_csvc(X, y01, max_iter=REF_ITERS)
-        done += fit.n_iter
+        done += fit(REF_ITERS)
     dt = time.perf_counter() - t0
     v = done / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 kernel values, f64 alpha/gradient", "data": "synthetic",
         "config": {"workload": WORKLOAD, "iterations_per_step": REF_ITERS},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{REF_ITERS} SMO iterations per step at full n={N_ROWS}, d={N_FEATURES} "
-                                   f"(oracle/smo_oracle.py: the reference's NumPy operations, OpenBLAS threads = all cores)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{REF_ITERS} SMO iterations per step (a fresh fit each, X.std() and the kernel set-up included) "
+                                   f"at full n={N_ROWS}, d={N_FEATURES}: {what}"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def alpha_digest(alpha):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(alpha, dtype=np.float64).tobytes()).hexdigest()
+
+
+def secondary_configs(world, dev):
+    """The other BASELINE.json configs through the public estimators, each bounded to a few seconds (driver-visible
+    counterparts of scripts/gpu_configs.py).  N = 1: C2, C4, C5; N > 1: C2 (sub-problems dealt to the GPUs) only."""
+    import contextlib, io, torch
+    import pysvm_b200 as P
+    from pysvm_b200 import synth as gen
+    from sklearn.datasets import load_digits
+    from sklearn.preprocessing import StandardScaler
+    peak, _ = measured_peak()
+    out = {}
+
+    def quiet(f):
+        with contextlib.redirect_stdout(io.StringIO()):
+            return f()
+
+    def timed(f):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        r = quiet(f)
+        torch.cuda.synchronize(dev)
+        return r, time.perf_counter() - t0
+
+    Xd, yd = load_digits(return_X_y=True)
+    Xd = StandardScaler().fit_transform(Xd)
+    quiet(lambda: P.KernelSVC(multiclass="ovo", max_iter=10 ** 6).fit(Xd, yd))          # warm
+    est, dt = timed(lambda: P.KernelSVC(multiclass="ovo", max_iter=10 ** 6).fit(Xd, yd))
+    out["C2_digits_ovo"] = {"fit_seconds": dt, "sub_problems": len(est.multiclass_model.estimators_),
+                            "iterations": int(sum(e.n_iter_ for e in est.multiclass_model.estimators_)),
+                            "train_accuracy": float((est.predict(Xd) == yd).mean())}
+    if world > 1:
+        return out
+
+    def sweep_stats(e, l, d, nvars):
+        st = e.solve_stats_
+        it = max(1, st["n_iter"])
+        cold = st["cold_sweeps"]
+        b_cold = l * 4 * d + nvars * 18
+        return {"n_iter": st["n_iter"], "device_seconds": st["device_ms"] * 1e-3, "us_per_iteration": st["device_ms"] * 1e3 / it,
+                "cold_sweeps": cold, "warm_sweeps": st["cache_hits"] // 2,
+                "algorithmic_GBps": st["algorithmic_bytes"] / (st["device_ms"] * 1e-3) / 1e9,
+                "roofline_frac": st["algorithmic_bytes"] / (st["device_ms"] * 1e-3) / 1e9 / peak,
+                "cold_bytes_per_iteration": b_cold}
+
+    # C4: SVR l = 100k, d = 64 -> 200k variables (mirror).  Solver path capped; nu path capped (it never stops on tol)
+    Xr, z = gen.regression(n=100_000, d=64, seed=0)
+    quiet(lambda: P.KernelSVR(max_iter=2000).fit(Xr, z))
+    e, dt = timed(lambda: P.KernelSVR(max_iter=150_000).fit(Xr, z))
+    out["C4_kernel_svr"] = dict(fit_seconds=dt, max_iter=150_000, **sweep_stats(e, 100_000, 64, 200_000))
+    e, dt = timed(lambda: P.NuSVR(max_iter=50_000).fit(Xr, z))
+    out["C4_nu_svr"] = dict(fit_seconds=dt, max_iter=50_000, **sweep_stats(e, 100_000, 64, 200_000))
+    del e, Xr, z
+
+    # C5: one-class n = 1M, d = 32 (init gradient = 1M x 500k kernel evaluations, then the cold sweep), RFF, decision
+    Xo = gen.oneclass(n=1_000_000, d=32, seed=1)
+    e, dt = timed(lambda: P.OneClassSVM(max_iter=40_000).fit(Xo))
+    out["C5_one_class"] = dict(fit_seconds=dt, max_iter=40_000, **sweep_stats(e, 1_000_000, 32, 1_000_000))
+    Xq = np.random.default_rng(2).standard_normal((1_000_000, 32)).astype(np.float32)
+    e.decision_function(Xq[:4096])
+    _, dt = timed(lambda: e.decision_function(Xq))
+    nsv = int(len(e.support_))
+    out["C5_decision_exact"] = {"queries": len(Xq), "n_sv": nsv, "seconds": dt, "kernel_evals_per_s": len(Xq) * nsv / dt,
+                                "note": "host-resident float32 queries in, float64 decision values out (copies timed)"}
+    del e
+    from pysvm_b200.rff import NormalRFF
+    np.random.seed(0)
+    rff = NormalRFF(gamma=1 / 32, D=4096).fit(Xo[:1])
+    Xdev = torch.from_numpy(Xo[:262144]).to(dev)
+    rff.transform_device(Xdev[:4096])
+    Z, dt = timed(lambda: rff.transform_device(Xdev))
+    out["C5_rff_transform"] = {"rows": int(Xdev.shape[0]), "D": 4096, "seconds": dt, "rows_per_s": Xdev.shape[0] / dt,
+                               "output_GBps": Z.numel() * Z.element_size() / dt / 1e9, "out_dtype": str(Z.dtype).replace("torch.", ""),
+                               "roofline_frac_hbm_write": Z.numel() * Z.element_size() / dt / 1e9 / peak}
+    del Z, Xdev
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -180,11 +298,12 @@ def run_ours(args, rank, world, local_rank):
     p = -np.ones(N_ROWS)
 
     # ---- value: inputs resident in HBM, K fresh fits of ITERS iterations each -------------------------
+    shard = None
     if world == 1:
         func = S.QColumns(X, y, S.KernelSpec("rbf", gamma), device=dev, cache_bytes=0)   # cold path
         sol = S.SolverWithCache(p, y, 1.0, 1e-5, func=func)
     else:
-        # row-sharded over the GPUs of the box: one problem, every rank owns n/world rows (strong scaling)
+        # row-sharded over the GPUs of the box: ONE problem, every rank holds n/world rows (strong scaling)
         from pysvm_b200 import sharded
         sol, shard, _ = sharded.fit_csvc_sharded(X, y01, 1.0, S.KernelSpec("rbf", gamma), 1e-5, 8, cache_bytes=0)
         sharded.enable()
@@ -215,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
         total_ms = 0.0
         for _ in range(args.steps):
             flush.fill_(1)                      # flush L2 between steps (not timed)
-            torch.cuda.synchronize(dev)
+            barrier()
             ev0.record()
             st = step()
             ev1.record()
@@ -226,10 +345,21 @@ def run_ours(args, rank, world, local_rank):
             n_done += st.n_iter
         barrier()
     value_launches = launches
+    # what the value leg computed (the last timed fit): the same on every rank count when the sharded solve is bit-identical
     if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        from pysvm_b200 import sharded
+        alpha_all = sharded.gather_variables(sol.alpha.cpu().numpy(), shard, False)
+        t = torch.tensor([total_ms, kernel_ms, alg_bytes], device=dev, dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_ms, kernel_ms = float(tmax[0].item()), float(tmax[1].item())
+        alg_bytes = float(t[2].item())          # every rank sweeps its own rows: bytes add up over the box
+    else:
+        alpha_all = sol.alpha.cpu().numpy()
+    parity = {"n_iter": int(st.n_iter), "next_pair": [int(st.last_i), int(st.last_j)], "alpha_sha256": alpha_digest(alpha_all),
+              "n_nonzero_alpha": int(np.count_nonzero(alpha_all)),
+              "what": f"state after the last timed fit of {ITERS} iterations from alpha = 0 (value leg)"}
     n_total = float(n_done)        # iterations of the ONE (sharded) problem: not summed over ranks
     value = n_total / (total_ms * 1e-3)
 
@@ -254,29 +384,47 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e_value = e2e_iters / e2e_dt
-    h2d = (X.nbytes + 3 * 8 * N_ROWS) // world  # per rank: its rows of X, y, p (alpha/grad start on the device)
-    d2h = 8 * N_ROWS // world + 8               # per rank: its alpha slice + rho
+    e2e_cache = "off" if est.solve_stats_["cache_hits"] == 0 and est.solve_stats_["cold_sweeps"] == est.n_iter_ else "on"
+    e2e_sha = alpha_digest(est.alpha_)
+    rows_here = N_ROWS if world == 1 else shard.n_local
+    h2d = rows_here * N_FEATURES * 4 + 2 * 8 * rows_here     # per rank: ITS rows of X (float32) + y, p slices (float64)
+    d2h = 8 * rows_here + 8                                     # per rank: its alpha slice + rho
 
-    # ---- converged fit seconds (cold path), reported next to the throughput ---------------------------------
+    # ---- converged fit seconds (column cache on), reported next to the throughput ---------------------------
     fit_info = None
     del est
     import gc
-    gc.collect()                    # release the e2e fits' device memory (their Q-column caches) first
-    if world == 1 and not args.no_full_fit:
+    gc.collect()                    # release the e2e fits' device memory first
+    if not args.no_full_fit:
         with contextlib.redirect_stdout(io.StringIO()):
+            barrier()
             t0 = time.perf_counter()
             full = BiKernelSVC(max_iter=10 ** 7).fit(Xp, y01)
+            barrier()
             fit_s = time.perf_counter() - t0
         full.decision_function(Xp[:4096])       # warm
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         dec = full.decision_function(Xp)        # K7: n x n_sv kernel evaluations on the tensor cores (3xTF32), host in / host out
+        barrier()
         dec_s = time.perf_counter() - t0
         fit_info = {"fit_seconds": fit_s, "n_iter": full.n_iter_, "n_sv": int(len(full.support_)),
                     "device_seconds": full.solve_stats_["device_ms"] * 1e-3,
+                    "warm_sweeps": int(full.solve_stats_["cache_hits"] // 2), "cold_sweeps": int(full.solve_stats_["cold_sweeps"]),
                     "train_accuracy": float(((dec >= 0).astype(int) == y01).mean()),
+                    "alpha_sha256": alpha_digest(full.alpha_),
                     "decision_seconds_all_rows": dec_s,
                     "decision_kernel_evals_per_s": N_ROWS * float(len(full.support_)) / dec_s}
+        del full
+        gc.collect()
+
+    # ---- the other BASELINE configs, bounded (driver-visible secondary figures) ---------------------------------
+    secondary = None
+    if not args.no_secondary:
+        if world > 1:
+            from pysvm_b200 import sharded
+            sharded.enable()
+        secondary = secondary_configs(world, dev)
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ------------------------------
     cpu = None
@@ -294,30 +442,35 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_src = measured_peak()
+    # every rank sweeps its share concurrently: box-wide algorithmic bytes over the (max over ranks) kernel time
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+        "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 kernel values, f64 alpha/gradient", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "iterations_per_step": ITERS, "q_column_cache": "off (cold path)",
+        "config": {"workload": WORKLOAD, "iterations_per_step": ITERS, "q_column_cache": "off (cold path) in the value leg AND the e2e leg",
                    "parallelism": "single GPU" if world == 1 else
-                   f"rows sharded over {world} GPUs (n/{world} rows each), one NVLink candidate exchange per iteration",
-                   "l2": "flushed between steps (256 MB write); inside a step the SMO loop re-sweeps the same "
-                         "102.4 MB X (106 MB working set per iteration against 126 MB of L2) and the kernel asks L2 to "
-                         "keep the first 48 MB of it (evict_last hints on the bulk copies), so DRAM traffic is below "
-                         "the algorithmic bytes -- see roofline.traffic"},
+                   f"rows sharded over {world} GPUs ({N_ROWS // world} rows of X each, nothing replicated); per iteration one "
+                   f"level-2 exchange over NVLink: the GPU winners travel with alpha, norm and row",
+                   "l2": "flushed between steps (256 MB write); inside a step the SMO loop re-sweeps the same X (106 MB working "
+                         "set per iteration against 126 MB of L2 at N=1; the kernel asks L2 to keep the first 48 MB of it with "
+                         "evict_last hints), so DRAM traffic is below the algorithmic bytes -- see roofline.traffic"},
         "us_per_iteration": 1e3 * total_ms / n_total,
+        "parity": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "bytes_are": "per rank (every rank uploads only its own rows)", "q_column_cache": e2e_cache,
+                "alpha_sha256": e2e_sha,
                 "call": f"BiKernelSVC(max_iter={ITERS}).fit(X_host, y_host)", "steps": e2e_steps},
         "gpu_launches": value_launches,
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic_per_launch(ITERS) if world == 1 else None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                     "traffic": traffic_per_launch(ITERS) if world == 1 else None, "peak_source": peak_src + (f" x {world} GPUs" if world > 1 else ""),
                      "kernel": "b2svm::smo_persistent<float,32>", "algorithmic_bytes_per_iteration": algorithmic_bytes_per_iter(),
                      "kernel_ms_per_launch": kernel_ms / args.steps},
         "cpu_baseline": cpu,
         "fit": fit_info,
+        "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
 
@@ -330,6 +483,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-fit", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the bounded runs of the other BASELINE configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -260,12 +260,15 @@ struct b2svm_handle {
   long long ntiles = 0;
   size_t smem_bytes = 0;
   int launches = 0;
-  // ---- level-1 mailbox (MBOX_L1_BYTES) + level-2 box (MBOX_L2_BYTES, world > 1: shared over CUDA IPC)
+  // ---- exchange buffers (b2svm_smo.cuh): `l1` = private level-1 mailboxes of the CTAs (local); `block` = private
+  // level-2 mailboxes + bulk slots of the box (world > 1 only: a plain cudaMalloc, shared over CUDA IPC)
+  unsigned char* l1 = nullptr;
+  size_t l1_bytes = 0;
   unsigned char* block = nullptr;
   size_t block_bytes = 0;
   long long rows_per_rank = 0;
   std::vector<void*> peer_blocks;          // opened IPC mappings (nullptr for this rank)
-  void** peer_tables = nullptr;            // device: [world] level-2 box of every rank (own entry = block + MBOX_L1_BYTES)
+  void** peer_tables = nullptr;            // device: [world] exported block of every rank (own entry = block)
   bool attached = false, prepared = false;
   bool precomputed = false;       // kernel.kind == 4: X is the kernel matrix itself and doubles as a full cache
   void* cache = nullptr;          // Q-column cache [cache_slots][n_rows] in the input dtype
@@ -447,8 +450,8 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.row_offset = h->d.world > 1 ? h->d.row_offset : 0;
   P.l_global = h->d.world > 1 ? h->d.n_rows_global : h->d.n_rows;
   P.rows_per_rank = h->d.world > 1 ? h->rows_per_rank : h->d.n_rows;
-  P.mbox = reinterpret_cast<uint4*>(h->block);
-  P.box = reinterpret_cast<uint4*>(h->block + MBOX_L1_BYTES);
+  P.mbox = reinterpret_cast<uint4*>(h->l1);
+  P.box = reinterpret_cast<uint4*>(h->block);
   P.peer_box = reinterpret_cast<uint4* const*>(h->peer_tables);
   P.timeline = h->timeline;
   P.dbg_steps = h->dbg_steps;
@@ -464,7 +467,8 @@ int prepare_launch(b2svm_handle* h) {
   const int64_t nv = h->d.n_vars;
   refresh_flags_kernel<<<grid_for(nv), 256, 0, h->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, nv);
   B2_CUDA(cudaGetLastError());
-  B2_CUDA(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
+  B2_CUDA(cudaMemsetAsync(h->l1, 0, h->l1_bytes, h->stream));
+  if (h->block) B2_CUDA(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
   B2_CUDA(cudaMemsetAsync(h->abort_flag, 0, sizeof(int), h->stream));
   if (h->d.world > 1) B2_CUDA(cudaStreamSynchronize(h->stream));
   h->prepared = true;
@@ -586,10 +590,6 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     if (desc->row_offset != (long long)desc->rank * rpr || desc->n_rows != want)
       return cleanup_fail(B2SVM_E_INVALID, "shard must be rows [rank*rpr, min(n,(rank+1)*rpr)), rpr = roundup32(ceil(n/world))");
   }
-  h->block_bytes = MBOX_L1_BYTES + (desc->world > 1 ? MBOX_L2_BYTES : 0);
-  if (desc->world > 1) B2_TRY(cudaMalloc(&h->block, h->block_bytes));
-  else B2_TRY(pool_alloc(&h->block, h->block_bytes, h->stream));
-  B2_TRY(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
   // rows of X held by this GPU: its own slice only, also in a row-sharded solve (the winning rows of an iteration
   // travel with their candidate records)
   const int64_t lx = l;
@@ -660,12 +660,21 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     B2_TRY(cudaMalloc(&h->timeline, sizeof(long long) * TL_TOTAL));
     B2_TRY(cudaMemset(h->timeline, 0, sizeof(long long) * TL_TOTAL));
   }
-#undef B2_TRY
   int rc = plan(h);
   if (rc != B2SVM_OK) {
     b2svm_destroy(h);
     return rc;
   }
+  // exchange buffers, sized by the number of CTAs the plan chose (the same on every rank of a sharded solve)
+  h->l1_bytes = sizeof(uint4) * 2 * l1_units(h->ncta);
+  B2_TRY(pool_alloc(&h->l1, h->l1_bytes, h->stream));
+  B2_TRY(cudaMemsetAsync(h->l1, 0, h->l1_bytes, h->stream));
+  if (desc->world > 1) {
+    h->block_bytes = sizeof(uint4) * (l2_record_units(h->ncta) + BOX_BULK_UNITS);
+    B2_TRY(cudaMalloc(&h->block, h->block_bytes));
+    B2_TRY(cudaMemsetAsync(h->block, 0, h->block_bytes, h->stream));
+  }
+#undef B2_TRY
   *out = h;
   return B2SVM_OK;
 }
@@ -680,7 +689,8 @@ int b2svm_destroy(b2svm_handle* h) {
   for (void* pb : h->peer_blocks)
     if (pb) cudaIpcCloseMemHandle(pb);
   cudaFree(h->peer_tables);
-  if (h->d.world > 1) cudaFree(h->block); else pool_free(h->block, h->stream);
+  cudaFree(h->block);
+  pool_free(h->l1, h->stream);
   pool_free(h->flags, h->stream);
   if (!h->precomputed) pool_free(h->cache, h->stream);
   pool_free(h->slot_of, h->stream);
@@ -825,7 +835,7 @@ int b2svm_solve_ranks_on_one_gpu(b2svm_handle* const* handles, int32_t world, in
   if ((long long)world * h0->ncta > h0->num_sms)
     return fail(B2SVM_E_INVALID, "world * n_ctas exceeds the SM count: create the handles with max_ctas <= num_sms / world");
   std::vector<void*> tab((size_t)world);
-  for (int r = 0; r < world; ++r) tab[r] = handles[r]->block + MBOX_L1_BYTES;
+  for (int r = 0; r < world; ++r) tab[r] = handles[r]->block;
   std::vector<ProblemDev> P((size_t)world);
   ProblemDev* pd = nullptr;
   B2_CUDA(pool_alloc(&pd, sizeof(ProblemDev) * world, h0->stream));
@@ -953,7 +963,7 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
   for (int k = 0; k < count; ++k) {
     b2svm_handle* h = handles[k];
     refresh_flags_kernel<<<grid_for(h->d.n_vars), 256, 0, h0->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, h->d.n_vars);
-    cudaMemsetAsync(h->block, 0, h->block_bytes, h0->stream);
+    cudaMemsetAsync(h->l1, 0, h->l1_bytes, h0->stream);
     cudaMemsetAsync(h->abort_flag, 0, sizeof(int), h0->stream);
     memset(&P[k], 0, sizeof(ProblemDev));
     fill_problem(h, P[k], max_iter, -1, -1);
@@ -1049,7 +1059,7 @@ int b2svm_mailbox_attach(b2svm_handle* h, const void* ipc_handles) {
       h->peer_blocks[r] = p;
       base = reinterpret_cast<unsigned char*>(p);
     }
-    tab[r] = base + MBOX_L1_BYTES;   // the level-2 box sits behind the level-1 mailbox
+    tab[r] = base;
   }
   B2_CUDA(cudaMalloc(&h->peer_tables, sizeof(void*) * tab.size()));
   B2_CUDA(cudaMemcpy(h->peer_tables, tab.data(), sizeof(void*) * tab.size(), cudaMemcpyHostToDevice));

@@ -23,15 +23,19 @@
 // Candidate exchange, two levels, no atomics and no fences on the per-iteration critical path (MEMBAR.SC + CCTL.IVALL
 // cost 2-4 k cycles each on B200): every word that is polled carries the iteration ("epoch") it belongs to, so data
 // and flag travel together in single 16-byte relaxed stores, double-buffered by epoch parity.
-//   level 1 (inside a GPU): every CTA writes, per candidate type, one record {g, idx, epoch<<3 | flags} (+ a 16-byte
-//     alpha unit) into the GPU's mailbox; ONE warp per candidate type ("type warp": warp k handles type k, so the
-//     arg-max and the arg-min chains run side by side) polls the ncta records of its type -- that read IS the grid
-//     barrier -- and reduces them with REDUX.
-//   level 2 (row-sharded box, world > 1): the CTA that owns a GPU-level winner pushes it, TOGETHER WITH its alpha,
-//     norm and row x (candidates travel with their rows), into the box slot [rank][type] of every GPU
-//     over NVLink (CUDA-IPC peer mappings); the type warps of all CTAs then poll the `world` records of their type
-//     and read the winning row from local memory.  Row units are {8 payload bytes, epoch}: self-validating like the
-//     records.  Each GPU holds ONLY ITS OWN rows of X; nothing but these pushes crosses the link.
+//   level 1 (inside a GPU): every CTA pushes, per candidate type, one record {key, key, ~(idx<<3|flags), epoch}
+//     (+ a 16-byte alpha unit) into the PRIVATE mailbox of every CTA of the GPU (all-to-all: ncta stores per record,
+//     five per lane); ONE warp per candidate type ("type warp": warp k handles type k, so the arg-max and the
+//     arg-min chains run side by side) polls the ncta records of its own mailbox -- that read IS the grid barrier --
+//     and reduces them with REDUX.  No line is ever polled by two SMs: with one shared mailbox the 2 x 148 polling
+//     warps kept the L2 slices of those few lines so busy that the last record became visible only 3.6-4.9 us after
+//     its store (0.7-0.9 us with 12 CTAs), measured with the global timer.
+//   level 2 (row-sharded box, world > 1): the CTA that owns a GPU-level winner pushes its record into the private
+//     level-2 mailbox of EVERY CTA OF EVERY GPU over NVLink (CUDA-IPC peer mappings; 16 bytes each), and TOGETHER
+//     WITH IT alpha, norm, K(x,x) and the row x itself into the box slot [rank][type] of every GPU (SURVEY 8e:
+//     candidates travel with their rows); the type warps poll the `world` records of their private mailbox and then
+//     read the winning row from the local box.  Row units are {8 payload bytes, epoch, ~epoch}: self-validating like
+//     the records.  Each GPU holds ONLY ITS OWN rows of X; nothing but these pushes crosses the link.
 // A polled 16-byte unit is {payload, payload, epoch, ~epoch} (records: {g, g, idx, epoch<<3 | flags}) and the reader
 // consumes ALL FOUR words: ptxas narrows a vector load whose components are partly dead into separate scalar loads
 // (observed: ld.relaxed.sys.v4 with .y/.w unused became two LDG.32), and then payload and tag are no longer read by
@@ -83,9 +87,11 @@ struct ProblemDev {
   int pin_lo, pin_hi;   // macro tiles [pin_lo, pin_hi) of every CTA's slice are fetched with L2 evict_last, the rest evict_first
   int sub;              // 32-row tiles per ring stage (narrow rows: several tiles travel in one bulk copy)
   long long ntiles;
-  uint4* mbox;          // level-1 mailbox of this GPU [2][ncta][NCAND][2] {record, alpha unit} (zeroed before every launch)
-  uint4* box;           // level-2 box of this GPU [2][8 ranks][NCAND][BOX_UNITS] (world > 1; peers write into it over NVLink)
-  uint4* const* peer_box;    // [world] every rank's level-2 box (peer mapping; own entry = box)
+  uint4* mbox;          // level-1 private mailboxes [ncta targets][2][NCAND][nc8] records, then the alpha units in the same
+                        // layout (nc8 = ncta rounded up to 8; zeroed before every launch)
+  uint4* box;           // exported block of this GPU (world > 1; peers write into it over NVLink):
+                        // [ncta targets][2][NCAND][8 ranks] private level-2 records, then [2][8 ranks][NCAND][BOX_UNITS] bulk slots
+  uint4* const* peer_box;    // [world] every rank's exported block (peer mapping; own entry = box)
   int* abort_flag;
   SolveResult* result;
   long long max_iter;
@@ -107,8 +113,10 @@ struct ProblemDev {
 constexpr int BOX_UNITS = 4 + 2 * 128;
 constexpr int BOX_RANKS = 8;
 constexpr int MAX_CTAS = 160;              // level-1 poll: 5 records per lane
-constexpr size_t MBOX_L1_BYTES = sizeof(uint4) * 2 * MAX_CTAS * NCAND * 2;
-constexpr size_t MBOX_L2_BYTES = sizeof(uint4) * 2 * BOX_RANKS * NCAND * BOX_UNITS;
+// sizes of the exchange buffers for a launch with `ncta` CTAs per problem
+__host__ __device__ inline size_t l1_units(int ncta) { return (size_t)ncta * 2 * NCAND * ((ncta + 7) & ~7); }   // records (alpha units: the same again)
+__host__ __device__ inline size_t l2_record_units(int ncta) { return (size_t)ncta * 2 * NCAND * BOX_RANKS; }
+constexpr size_t BOX_BULK_UNITS = (size_t)2 * BOX_RANKS * NCAND * BOX_UNITS;
 constexpr size_t PROBLEM_SMEM_BYTES = (sizeof(ProblemDev) + 127) / 128 * 128;   // descriptor copy in front of the ring
 
 // Tile geometry.  A tile is one contiguous bulk copy of BR rows of CH 16-byte chunks.  LPR lanes share
@@ -139,10 +147,44 @@ struct Cfg {
 __device__ __forceinline__ bool unit_ok(const uint4& u, uint32_t epoch) { return u.z == epoch && u.w == ~epoch; }
 __device__ __forceinline__ uint4 make_unit(uint32_t lo, uint32_t hi, uint32_t epoch) { return make_uint4(lo, hi, epoch, ~epoch); }
 
-struct WCand {
-  double g, alpha;
-  int idx, flags;
+// A candidate as it travels through the exchange: an order-preserving 64-bit key of the gradient (bit-flipped for
+// the arg-min types, so every type is an arg-max over unsigned integers) and nik = ~((idx << 3) | flags), so that
+// the lexicographic maximum of (key, nik) is the reference's choice: best value, then the LOWER index
+// (np.argmax / np.argmin return the first extremum, solver.py:68-69).  nik == 0 marks an empty set.  Integer
+// compares keep the polling loops branch-free (double compares cost a divergent branch per record).
+struct KCand {
+  uint32_t kh, kl, nik;
 };
+__device__ __forceinline__ KCand kc_empty() { return KCand{0u, 0u, 0u}; }
+__device__ __forceinline__ KCand kc_make(bool is_max, const Cand& c) {
+  if (c.idx < 0) return kc_empty();
+  unsigned long long key = dkey(c.g);
+  if (!is_max) key = ~key;
+  return KCand{(uint32_t)(key >> 32), (uint32_t)key, ~(((uint32_t)c.idx << 3) | (uint32_t)(c.flags & 7))};
+}
+__device__ __forceinline__ bool kc_better(const KCand& a, const KCand& b) {   // a > b, branch-free
+  return (a.kh > b.kh) | ((a.kh == b.kh) & ((a.kl > b.kl) | ((a.kl == b.kl) & (a.nik > b.nik))));
+}
+__device__ __forceinline__ void kc_take(bool take, const KCand& a, KCand& b) {
+  b.kh = take ? a.kh : b.kh;
+  b.kl = take ? a.kl : b.kl;
+  b.nik = take ? a.nik : b.nik;
+}
+// warp-wide maximum (three REDUX.MAX); every lane receives the winner.  Full-warp collectives only.
+__device__ __forceinline__ KCand kc_redux(const KCand& c) {
+  KCand r;
+  r.kh = __reduce_max_sync(0xffffffffu, c.kh);
+  r.kl = __reduce_max_sync(0xffffffffu, c.kh == r.kh ? c.kl : 0u);
+  r.nik = __reduce_max_sync(0xffffffffu, (c.kh == r.kh && c.kl == r.kl) ? c.nik : 0u);
+  return r;
+}
+__device__ __forceinline__ int kc_idx(const KCand& c) { return c.nik ? (int)((~c.nik) >> 3) : -1; }
+__device__ __forceinline__ int kc_flags(const KCand& c) { return (int)((~c.nik) & 7u); }
+__device__ __forceinline__ double kc_g(bool is_max, const KCand& c) {
+  unsigned long long key = ((unsigned long long)c.kh << 32) | c.kl;
+  if (!is_max) key = ~key;
+  return c.nik ? dkey_inv(key) : 0.0;
+}
 
 // State only the leader warp needs between iterations.  It lives in shared memory and is loaded into
 // registers for the duration of the leader block only, so it costs the sweep loop no registers.
@@ -180,7 +222,7 @@ struct Shared {
   int ticket;           // next dynamically assigned tile of the current sweep
   uint4* peer[BOX_RANKS];   // level-2 box of every rank (copied once from global memory)
   volatile int status;  // a warp's watchdog tripped
-  WCand wc[NW][NCAND];  // per-warp candidates of the sweep
+  KCand wc[NW][NCAND];  // per-warp candidates of the sweep
   uint4 wa[NW][NCAND];  // ... their alpha, {lo, hi, epoch, 0}: written when the load lands, after the CTA join
   Selected<T> sel[NCAND];   // the box-wide winner of every type
 };
@@ -190,7 +232,12 @@ struct Shared {
 // miss sitting on the critical path between the sweep and the exchange: ~1600 cycles; a lane's best changes ~ln(rows
 // per lane) times per sweep, so this costs a handful of prefetches).
 __device__ __forceinline__ void touch_alpha(const double* pa) {
-  if (pa) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+  if (pa) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pa));   // alpha (8 B/row) is small: let it live in L2
+}
+__device__ __forceinline__ double ld_keep_f64(const double* p, uint64_t policy) {   // load that asks L2 to keep the line
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy) : "memory");
+  return v;
 }
 __device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (&b)[NCAND], const double* pa) {
   const bool second = nu && !(f & F_YPOS);
@@ -391,8 +438,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     if (P.timeline && cta == 0 && threadIdx.x == 0 && epoch >= 1 && epoch <= (uint32_t)TL_ITERS)
       P.timeline[(epoch - 1) * TL_SLOTS + slot] = clock64();
   };
+  auto stamp_val = [&](int slot, long long v) {
+    if (P.timeline && cta == 0 && threadIdx.x == 0 && epoch >= 1 && epoch <= (uint32_t)TL_ITERS)
+      P.timeline[(epoch - 1) * TL_SLOTS + slot] = v;
+  };
 #else
   auto stamp = [&](int) {};
+  auto stamp_val = [&](int, long long) {};
 #endif
   // local index of a variable this GPU owns
   auto local_var = [&](int idx) -> long long {
@@ -442,34 +494,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
 
   // every consumer warp owns at most one tile: its gradient-side state never leaves the registers
   const bool one_tile = SUB == 1 && NM <= NW;
-  const uint4* const l1_base = P.mbox;
-  const uint4* const box_base = P.box;
+  // exchange buffers (see ProblemDev): this CTA's private level-1 / level-2 mailboxes, the bulk slots of the box
+  const int nc8 = (ncta + 7) & ~7;
+  const size_t l1_total = l1_units(ncta);
+  const uint4* const box_base = P.box ? P.box + l2_record_units(ncta) : nullptr;
 
   for (;;) {
     // ---- (B) warp -> CTA candidate reduce, level-1 (GPU) and level-2 (box) exchange, step -------------------
     ++epoch;
     stamp(0);   // this warp's sweep done
     const uint32_t par = epoch & 1u;
+    // warp-level winners as integer keys (three REDUX.MAX per type)
+    KCand wk[NCAND];
 #pragma unroll
-    for (int k = 0; k < NCAND; ++k)
-      if (k < ntypes) redux_select(0xffffffffu, (k & 1) == 0, best[k]);
+    for (int k = 0; k < NCAND; ++k) {
+      wk[k] = kc_empty();
+      if (k < ntypes) wk[k] = kc_redux(kc_make((k & 1) == 0, best[k]));
+    }
     __syncwarp();
     // one lane per type also fetches the candidate's alpha (a row of this warp: same-SM coherent).  The load is
     // only issued here: its value is parked in shared memory after the CTA join, so neither the join nor the
     // candidate record waits for it (it is needed at step time only).
     double cand_alpha = 0.0;
     if (lane < ntypes) {
-      Cand m = best[0];
+      KCand m = wk[0];
 #pragma unroll
       for (int k = 1; k < NCAND; ++k)
-        if (lane == k) m = best[k];
-      if (m.idx >= 0) cand_alpha = alpha[local_var(m.idx)];
-      WCand wv;
-      wv.g = m.g;
-      wv.idx = m.idx;
-      wv.flags = m.flags;
-      wv.alpha = 0.0;
-      sh->wc[warp][lane] = wv;
+        if (lane == k) m = wk[k];
+      if (m.nik) cand_alpha = ld_keep_f64(alpha + local_var(kc_idx(m)), l2_policy_evict_last());
+      sh->wc[warp][lane] = m;
     }
     named_bar_sync(1, NW * 32);
     stamp(1);   // all warps of this CTA done
@@ -499,28 +552,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       if (!forced_now) {
         // ---- CTA-level winner (full-warp collectives only: two half-warp masks in one instruction compile to a
         // MATCH.ANY / WARPSYNC.EXCLUSIVE emulation that costs ~1000 cycles on this path)
-        WCand mw;
-        mw.g = 0.0; mw.alpha = 0.0; mw.idx = -1; mw.flags = 0;
-        if (lane < NW) mw = sh->wc[lane][k];
-        Cand m;
-        m.g = mw.g; m.idx = mw.idx; m.flags = mw.flags;
-        redux_select(0xffffffffu, is_max, m);
-        const unsigned holders = __ballot_sync(0xffffffffu, m.idx >= 0 && mw.idx == m.idx);
+        KCand mine_w = kc_empty();
+        if (lane < NW) mine_w = sh->wc[lane][k];
+        const KCand m = kc_redux(mine_w);
+        const unsigned holders = __ballot_sync(0xffffffffu, m.nik != 0u && mine_w.nik == m.nik);
         const int from_warp = holders ? __ffs(holders) - 1 : 0;
+        const int m_idx = kc_idx(m);
         stamp(7);   // CTA winner known
-        // ---- level 1: one tagged record into this GPU's mailbox
-        uint4* const l1 = const_cast<uint4*>(l1_base) + ((((size_t)par * ncta + cta) * NCAND + k) * 2);
-        if (lane == 0)
-          st_relaxed_v4(l1, make_uint4((uint32_t)__double2loint(m.g), (uint32_t)__double2hiint(m.g), (uint32_t)m.idx,
-                                       (epoch << 3) | (uint32_t)(m.flags & 7)));
+        // ---- level 1: the tagged record goes into the private mailbox of every CTA of this GPU (all-to-all push)
+        constexpr int MAXM = MAX_CTAS / 32;
+        auto l1_slot = [&](int target) -> uint4* {   // where CTA `cta` writes for CTA `target`
+          return P.mbox + (((size_t)target * 2 + par) * NCAND + k) * nc8 + cta;
+        };
+        const uint4* const l1_mine = P.mbox + (((size_t)cta * 2 + par) * NCAND + k) * nc8;   // what the others wrote for me
+        {
+          const uint4 rec = make_uint4(m.kl, m.kh, m.nik, epoch);
+#pragma unroll
+          for (int mm = 0; mm < MAXM; ++mm) {
+            const int t = lane + 32 * mm;
+            if (t < ncta && t != cta) st_relaxed_v4(l1_slot(t), rec);
+          }
+        }
+        // ---- poll loads of the first pass go out right away (they are looked at after the alpha hand-over below);
+        // this CTA's own record never leaves its registers
+        uint4 h[MAXM];
+        auto issue_poll = [&]() {
+#pragma unroll
+          for (int mm = 0; mm < MAXM; ++mm) {
+            const int c = lane + 32 * mm;
+            h[mm] = make_uint4(0u, 0u, 0u, 0u);
+            if (c < ncta && c != cta) h[mm] = ld_relaxed_v4(l1_mine + c);
+          }
+        };
+        issue_poll();
         // the candidate's row, requested now and used after the poll: real loads when it may have to travel to the
         // other GPUs (world > 1), an L2 prefetch otherwise (the leaders' fetch of the winning row then hits)
         V myrow[QL];
         T mynorm = 0, mykself = 0;
 #pragma unroll
         for (int q = 0; q < QL; ++q) myrow[q] = CK::zero();
-        if (m.idx >= 0 && P.kind != K_PRECOMPUTED) {
-          const long long lrow = ((mirror && m.idx >= lg) ? m.idx - lg : m.idx) - goff;
+        if (m_idx >= 0 && P.kind != K_PRECOMPUTED) {
+          const long long lrow = ((mirror && m_idx >= lg) ? m_idx - lg : m_idx) - goff;
           const V* src = reinterpret_cast<const V*>(P.X) + lrow * CH;
           if (world > 1) {
 #pragma unroll
@@ -537,49 +609,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         if (k == 0 && lane == 0) sh->ticket = NW;   // next sweep: tiles 0..NW-1 are static, the rest are drawn here
         stamp(2);   // published
 #ifdef B2SVM_TIMELINE
-        if (P.timeline && threadIdx.x == 0 && (epoch == 11u || epoch == 41u) && cta < 160)   // two sweeps: is a slow CTA always slow?
-          P.timeline[TL_CTA_BASE + 2 * cta + (epoch == 41u)] = clock64() - cta_sweep_start_prev;
+        if (P.timeline && threadIdx.x == 0 && epoch == 41u && cta < 160)   // when did every CTA publish (global ns timer)?
+          P.timeline[TL_CTA_BASE + 2 * cta] = (long long)globaltimer_ns();
 #endif
         // ---- the CTA winner's alpha, as soon as the warp that owns it has parked it
         park_alpha();
         __syncwarp();
         uint4 ua = ld_volatile_shared_v4(&sh->wa[from_warp][k]);
         while (!unit_ok(ua, epoch)) ua = ld_volatile_shared_v4(&sh->wa[from_warp][k]);
-        if (world == 1 && lane == 0) st_relaxed_v4(l1 + 1, make_unit(ua.x, ua.y, epoch));
+        if (world == 1) {   // ... pushed all-to-all like the record (world > 1: it travels with the level-2 push instead)
+          const uint4 au = make_unit(ua.x, ua.y, epoch);
+#pragma unroll
+          for (int mm = 0; mm < MAXM; ++mm) {
+            const int t = lane + 32 * mm;
+            if (t < ncta && t != cta) st_relaxed_v4(l1_slot(t) + l1_total, au);
+          }
+        }
 
         // ---- poll the ncta level-1 records of this type (this read is the grid barrier)
+        KCand gw;          // GPU-level winner
         {
-          constexpr int MAXM = MAX_CTAS / 32;
-          const uint4* rbase = l1_base + (size_t)par * ncta * NCAND * 2 + (size_t)k * 2;
           uint64_t t_start = 0;   // (the timer is only read once the poll has been spinning for a while)
           uint32_t rounds = 0;
+          stamp(12);   // poll entry
+          uint32_t passes = 0;
           for (;;) {
             bool all = true;
-            w.g = 0.0; w.idx = -1; w.flags = 0;
-            wsrc = 0;
-            uint4 h[MAXM];
-            // all loads of a pass are issued before any is looked at: one L2 round trip per pass
+            KCand bk = kc_empty();
+            int bsrc = 0;
 #pragma unroll
             for (int mm = 0; mm < MAXM; ++mm) {
               const int c = lane + 32 * mm;
-              if (c < ncta) h[mm] = ld_relaxed_v4(rbase + (size_t)c * NCAND * 2);
+              const bool own = c == cta;
+              KCand rc;
+              rc.kl = own ? m.kl : h[mm].x;
+              rc.kh = own ? m.kh : h[mm].y;
+              rc.nik = own ? m.nik : h[mm].z;
+              const bool valid = own | (h[mm].w == epoch);
+              all = all & (valid | (c >= ncta));
+              const bool take = (c < ncta) & valid & kc_better(rc, bk);
+              kc_take(take, rc, bk);
+              bsrc = take ? c : bsrc;
             }
-#pragma unroll
-            for (int mm = 0; mm < MAXM; ++mm) {
-              const int c = lane + 32 * mm;
-              if (c < ncta) {
-                const uint4 hh = h[mm];
-                if ((hh.w >> 3) != epoch) {
-                  all = false;
-                } else {
-                  const double g = __hiloint2double((int)hh.y, (int)hh.x);
-                  const int idx = (int)hh.z;
-                  const bool take = is_max ? better_max(g, idx, w.g, w.idx) : better_min(g, idx, w.g, w.idx);
-                  if (take) { w.g = g; w.idx = idx; w.flags = (int)(hh.w & 7u); wsrc = c; }
-                }
-              }
+            if (passes++ == 0) stamp(13);   // first pass back
+            if (__all_sync(0xffffffffu, all)) {
+              gw = kc_redux(bk);
+              const unsigned hold2 = __ballot_sync(0xffffffffu, gw.nik != 0u && bk.nik == gw.nik);
+              wsrc = __shfl_sync(0xffffffffu, bsrc, hold2 ? __ffs(hold2) - 1 : 0);
+              break;
             }
-            if (__all_sync(0xffffffffu, all)) break;
             if ((++rounds & 63u) == 0) {
               int bad = *(volatile int*)P.abort_flag | sh->status;
               const uint64_t now = globaltimer_ns();
@@ -588,22 +666,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
                 *(volatile int*)P.abort_flag = 1;
                 bad = 1;
               }
-              if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
+              if (__any_sync(0xffffffffu, bad)) { status = 1; gw = kc_empty(); break; }
             }
+            issue_poll();
           }
-          const int mine = w.idx;
-          redux_select(0xffffffffu, is_max, w);
-          const unsigned hold2 = __ballot_sync(0xffffffffu, w.idx >= 0 && mine == w.idx);
-          wsrc = __shfl_sync(0xffffffffu, wsrc, hold2 ? __ffs(hold2) - 1 : 0);
+          stamp(15);   // poll loop left
+          stamp_val(14, (long long)passes);
+#ifdef B2SVM_TIMELINE
+          if (P.timeline && threadIdx.x == 0 && epoch == 41u && cta < 160)   // ... and when did it see everybody's record?
+            P.timeline[TL_CTA_BASE + 2 * cta + 1] = (long long)globaltimer_ns();
+#endif
         }
         stamp(3);   // GPU-level winner known
 
         if (world > 1 && !status) {
           // ---- level 2: the owner of the GPU-level winner pushes it, with alpha, norm and row, to every GPU
-          const int owner = w.idx >= 0 ? wsrc : 0;
+          const int owner = gw.nik ? wsrc : 0;
           if (cta == owner) {
-            const uint4 rec = make_uint4((uint32_t)__double2loint(w.g), (uint32_t)__double2hiint(w.g), (uint32_t)w.idx,
-                                         (epoch << 3) | (uint32_t)(w.flags & 7));
+            const uint4 rec = make_uint4(gw.kl, gw.kh, gw.nik, epoch);
             // float: one unit {norm, K(x,x)}; double: one unit each
             uint4 un, uk;
             if (sizeof(T) == 8) {
@@ -615,8 +695,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             }
             for (int rr = 0; rr < world; ++rr) {
               const int r = (P.rank + 1 + rr) % world;   // peers first, the own box last
-              uint4* slot = sh->peer[r] + (((size_t)par * BOX_RANKS + P.rank) * NCAND + k) * BOX_UNITS;
-              if (w.idx >= 0) {
+              uint4* const bulk = sh->peer[r] + l2_record_units(ncta);
+              uint4* slot = bulk + (((size_t)par * BOX_RANKS + P.rank) * NCAND + k) * BOX_UNITS;
+              if (gw.nik) {
 #pragma unroll
                 for (int q = 0; q < QL; ++q) {
                   const int c = lane + 32 * q;
@@ -630,24 +711,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
                 if (lane == 2) st_relaxed_sys_v4(slot + 2, un);
                 if (sizeof(T) == 8 && lane == 3) st_relaxed_sys_v4(slot + 3, uk);
               }
-              if (lane == 0) st_relaxed_sys_v4(slot, rec);
+              // the record: into the private level-2 mailbox of every CTA of rank r
+#pragma unroll
+              for (int mm = 0; mm < MAXM; ++mm) {
+                const int t = lane + 32 * mm;
+                if (t < ncta) st_relaxed_sys_v4(sh->peer[r] + (((size_t)t * 2 + par) * NCAND + k) * BOX_RANKS + P.rank, rec);
+              }
             }
           }
-          // ---- poll the `world` level-2 records of this type in the local box (this read is the box barrier)
+          // ---- poll the `world` level-2 records of this type in this CTA's private mailbox (the box barrier)
           {
-            const uint4* rbase = box_base + ((size_t)par * BOX_RANKS * NCAND + k) * BOX_UNITS;
+            const uint4* rbase = P.box + (((size_t)cta * 2 + par) * NCAND + k) * BOX_RANKS;
             uint64_t t_start = 0;
             uint32_t rounds = 0;
             for (;;) {
+              KCand bk = kc_empty();
               bool ok = true;
-              w.g = 0.0; w.idx = -1; w.flags = 0;
-              wsrc = 0;
               if (lane < world) {
-                const uint4 hh = ld_relaxed_sys_v4(rbase + (size_t)lane * NCAND * BOX_UNITS);
-                if ((hh.w >> 3) != epoch) ok = false;
-                else { w.g = __hiloint2double((int)hh.y, (int)hh.x); w.idx = (int)hh.z; w.flags = (int)(hh.w & 7u); wsrc = lane; }
+                const uint4 hh = ld_relaxed_sys_v4(rbase + lane);
+                ok = hh.w == epoch;
+                bk.kl = hh.x; bk.kh = hh.y; bk.nik = ok ? hh.z : 0u;
               }
-              if (__all_sync(0xffffffffu, ok)) break;
+              if (__all_sync(0xffffffffu, ok)) {
+                gw = kc_redux(bk);
+                const unsigned hold2 = __ballot_sync(0xffffffffu, gw.nik != 0u && bk.nik == gw.nik);
+                wsrc = hold2 ? __ffs(hold2) - 1 : 0;     // lane = rank
+                break;
+              }
               if ((++rounds & 63u) == 0) {
                 int bad = *(volatile int*)P.abort_flag | sh->status;
                 const uint64_t now = globaltimer_ns();
@@ -656,15 +746,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
                   *(volatile int*)P.abort_flag = 1;
                   bad = 1;
                 }
-                if (__any_sync(0xffffffffu, bad)) { status = 1; break; }
+                if (__any_sync(0xffffffffu, bad)) { status = 1; gw = kc_empty(); break; }
               }
             }
-            const int mine = w.idx;
-            redux_select(0xffffffffu, is_max, w);
-            const unsigned hold2 = __ballot_sync(0xffffffffu, w.idx >= 0 && mine == w.idx);
-            wsrc = __shfl_sync(0xffffffffu, wsrc, hold2 ? __ffs(hold2) - 1 : 0);
           }
         }
+        w.idx = kc_idx(gw);
+        w.flags = kc_flags(gw);
+        w.g = kc_g(is_max, gw);
         stamp(4);   // box-wide winner known
 
         // ---- the winner's alpha, norm and row
@@ -709,8 +798,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             have_row = have_alpha = true;
           } else {
             // single GPU: the alpha unit its CTA published next to the record, the row straight from X
-            const uint4* unit = l1_base + ((((size_t)par * ncta + wsrc) * NCAND + k) * 2) + 1;
-            uint4 u = ld_relaxed_v4(unit);
+            const uint4* unit = P.mbox + l1_total + (((size_t)cta * 2 + par) * NCAND + k) * nc8 + wsrc;
+            uint4 u = wsrc == cta ? make_unit(0u, 0u, epoch) : ld_relaxed_v4(unit);
             if (P.kind != K_PRECOMPUTED) {
               const long long lrow = (mirror && w.idx >= lg) ? w.idx - lg : w.idx;
               const V* src = reinterpret_cast<const V*>(P.X) + lrow * CH;
@@ -728,6 +817,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
               u = ld_relaxed_v4(unit);
               if ((++spins & 4095u) == 0 && *(volatile int*)P.abort_flag) { status = 1; break; }
             }
+            if (wsrc == cta) u = ua;      // my own candidate won: its alpha never left this CTA
             w_alpha = __hiloint2double((int)u.y, (int)u.x);
             have_alpha = true;
           }

@@ -28,14 +28,11 @@ def run(n, d, iters, dtype=np.float32):
     t = allb[:1024].reshape(64, 16)
     wt = allb[1024:1088].reshape(16, 4)
     ct = allb[1088:].reshape(160, 2)[:st.n_ctas]
-    for e in (0, 1):
-        c = ct[:, e]
-        print('   per-CTA sweep cycles (epoch %d): min %d median %d p90 %d max %d' % (10 + 30 * e, c.min(), np.median(c), np.percentile(c, 90), c.max()))
-    order = np.argsort(ct[:, 0])
-    print('   slowest CTAs at epoch 10:', [(int(c), int(ct[c, 0]), int(ct[c, 1])) for c in order[-10:]])
-    print('   fastest CTAs at epoch 10:', [(int(c), int(ct[c, 0]), int(ct[c, 1])) for c in order[:6]])
-    print('   correlation of per-CTA sweep time between the two epochs: %.3f' % np.corrcoef(ct[:, 0], ct[:, 1])[0, 1])
-    print('   sweep time by CTA index block of 16 (epoch 10 / 40):', [(int(ct[b:b+16, 0].mean()), int(ct[b:b+16, 1].mean())) for b in range(0, st.n_ctas, 16)])
+    pub, seen = ct[:, 0].astype(np.int64), ct[:, 1].astype(np.int64)
+    t0 = pub.min()
+    print(f"   epoch 41, global ns timer: publish times spread {pub.max() - t0} ns (sorted, first/last 4: {np.sort(pub - t0)[:4].tolist()} .. {np.sort(pub - t0)[-4:].tolist()})")
+    print(f"   all records seen: {np.sort(seen - t0)[:4].tolist()} .. {np.sort(seen - t0)[-4:].tolist()} ns after the first publish;"
+          f" last publish -> first 'all seen' {seen.min() - pub.max()} ns, -> last 'all seen' {seen.max() - pub.max()} ns; CTA 0 published at {pub[0] - t0}, saw all at {seen[0] - t0}")
     k = min(iters, 60)
     seg = t[2:k]      # skip first epochs
     chain = [("join (0->1)", 0, 1), ("CTA winner (1->7)", 1, 7), ("publish L1 (7->2)", 7, 2), ("alpha park + L1 poll (2->3)", 2, 3),
@@ -49,6 +46,8 @@ def run(n, d, iters, dtype=np.float32):
         v = np.median(seg[:, b] - seg[:, a])
         print(f"   {nm:34s} {v:9.0f}")
         tot += v
+    print(f"      poll detail: publish->poll entry {np.median(seg[:, 12] - seg[:, 2]):.0f}, first pass {np.median(seg[:, 13] - seg[:, 12]):.0f}, "
+          f"loop total {np.median(seg[:, 15] - seg[:, 12]):.0f}, passes median {np.median(seg[:, 14]):.0f} max {seg[:, 14].max()}, reduce after {np.median(seg[:, 3] - seg[:, 15]):.0f}")
     sw = np.median(seg[1:, 0] - seg[:-1, 6])
     print(f"   {'sweep (6->next 0)':34s} {sw:9.0f}")
     print(f"   chain {tot:.0f} + sweep {sw:.0f} = {tot + sw:.0f} cycles -> {(tot + sw)/us:.0f} cycles/us")

@@ -12,7 +12,7 @@ from pysvm_b200 import solver as S, sharded as SH, _native as N
 n = int(os.environ.get("N", 200000))
 X, y01 = G.classification(n=n, d=128, seed=0)
 spec = S.KernelSpec("rbf", 1 / (128 * X.std()))
-solver, shard, st = SH.fit_csvc_sharded(X, y01, 1.0, spec, 1e-5, 200)
+solver, shard, st = SH.fit_csvc_sharded(X, y01, 1.0, spec, 1e-5, 200, cache_bytes=0)
 solver._engine.init_state(solver.p)
 st = solver.solve(300)
 lib = N.load()
@@ -22,17 +22,20 @@ lib.b2svm_debug_timeline.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 N.check(lib.b2svm_debug_timeline(solver._engine.h, buf, NT_ALL))
 t = np.array(buf[:1024], dtype=np.int64).reshape(64, 16)
 seg = t[2:60]
-names = ["join(0->1)", "publish(1->2)", "box poll(2->3)", "final reduce(3->4)", "step(4->5)", "bar(5->6)", "sweep(6->next0)"]
-d01 = [seg[:, 1] - seg[:, 0], seg[:, 2] - seg[:, 1], seg[:, 3] - seg[:, 2], seg[:, 4] - seg[:, 3], seg[:, 5] - seg[:, 4], seg[:, 6] - seg[:, 5], np.r_[seg[1:, 0] - seg[:-1, 6], 0]]
+chain = [("join (0->1)", 0, 1), ("CTA winner (1->7)", 1, 7), ("publish L1 (7->2)", 7, 2), ("alpha park + L1 poll (2->3)", 2, 3),
+         ("level 2: push + poll (3->4)", 3, 4), ("row / alpha fetch (4->8)", 4, 8), ("type barrier (8->9)", 8, 9),
+         ("select + K_ij (9->10)", 9, 10), ("smo_step (10->11)", 10, 11), ("cache plan + hand-over (11->5)", 11, 5), ("bar (5->6)", 5, 6)]
 for r in range(world):
     if r == rank:
         print(f"rank {rank}: n={n} world={world}: {st.device_ms*1e3/st.n_iter:.2f} us/it, ctas {st.n_ctas}", flush=True)
-        for nm, v in zip(names, d01):
-            print(f"   {nm:30s} {np.median(v):9.0f}", flush=True)
-        fine = [("join->CTA winners (1->7)", seg[:, 7] - seg[:, 1]), ("push record (7->2)", seg[:, 2] - seg[:, 7]), ("decide + issue loads (4->8)", seg[:, 8] - seg[:, 4]),
-                ("rows + pair kernels (8->9)", seg[:, 9] - seg[:, 8]), ("alpha settled (9->10)", seg[:, 10] - seg[:, 9]), ("smo_step (10->11)", seg[:, 11] - seg[:, 10]),
-                ("cache plan + publish (11->5)", seg[:, 5] - seg[:, 11])]
-        for nm, v in fine:
-            print(f"      {nm:30s} {np.median(v):9.0f}", flush=True)
+        tot = 0
+        for nm, a, b in chain:
+            v = np.median(seg[:, b] - seg[:, a])
+            tot += v
+            print(f"   {nm:34s} {v:9.0f}", flush=True)
+        print(f"      poll detail: publish->poll entry {np.median(seg[:, 12] - seg[:, 2]):.0f}, first pass {np.median(seg[:, 13] - seg[:, 12]):.0f}, "
+              f"loop total {np.median(seg[:, 15] - seg[:, 12]):.0f}, passes median {np.median(seg[:, 14]):.0f} max {seg[:, 14].max()}, reduce after {np.median(seg[:, 3] - seg[:, 15]):.0f}", flush=True)
+        sw = np.median(seg[1:, 0] - seg[:-1, 6])
+        print(f"   {'sweep (6->next 0)':34s} {sw:9.0f}   chain {tot:.0f} + sweep {sw:.0f} = {tot + sw:.0f} cycles", flush=True)
     dist.barrier()
 dist.destroy_process_group()
