@@ -680,10 +680,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         stamp(3);   // GPU-level winner known
 
         if (world > 1 && !status) {
-          // ---- level 2: the owner of the GPU-level winner pushes it, with alpha, norm and row, to every GPU
+          // ---- level 2.  Records: every CTA forwards its GPU's winner to its counterpart (the CTA with the same
+          // index) on every GPU -- one store instruction, lane = destination rank -- so the records of a GPU travel
+          // from ncta SMs in parallel instead of queueing behind each other in one SM's NVLink store path (measured:
+          // ~85 cycles per peer store instruction; the owner alone needed 64 of them for 8 GPUs).
+          if (lane < world)
+            st_relaxed_sys_v4(sh->peer[lane] + (((size_t)cta * 2 + par) * NCAND + k) * BOX_RANKS + P.rank,
+                              make_uint4(gw.kl, gw.kh, gw.nik, epoch));
+          // Bulk: the owner of the GPU-level winner pushes alpha, norm, K(x,x) and the row into the box of every GPU
           const int owner = gw.nik ? wsrc : 0;
-          if (cta == owner) {
-            const uint4 rec = make_uint4(gw.kl, gw.kh, gw.nik, epoch);
+          if (cta == owner && gw.nik) {
             // float: one unit {norm, K(x,x)}; double: one unit each
             uint4 un, uk;
             if (sizeof(T) == 8) {
@@ -693,29 +699,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
               un = make_unit(__float_as_uint((float)mynorm), __float_as_uint((float)mykself), epoch);
               uk = un;
             }
+            const size_t slot_off = l2_record_units(ncta) + (((size_t)par * BOX_RANKS + P.rank) * NCAND + k) * BOX_UNITS;
+            // the three small units of all destinations in one instruction: lane = 4 * destination + unit
+            {
+              const int r = lane >> 2, which = lane & 3;
+              if (r < world && which >= 1 && (which < 3 || sizeof(T) == 8)) {
+                const uint4 u = which == 1 ? make_unit(ua.x, ua.y, epoch) : (which == 2 ? un : uk);
+                st_relaxed_sys_v4(sh->peer[r] + slot_off + which, u);
+              }
+            }
             for (int rr = 0; rr < world; ++rr) {
               const int r = (P.rank + 1 + rr) % world;   // peers first, the own box last
-              uint4* const bulk = sh->peer[r] + l2_record_units(ncta);
-              uint4* slot = bulk + (((size_t)par * BOX_RANKS + P.rank) * NCAND + k) * BOX_UNITS;
-              if (gw.nik) {
+              uint4* slot = sh->peer[r] + slot_off;
 #pragma unroll
-                for (int q = 0; q < QL; ++q) {
-                  const int c = lane + 32 * q;
-                  if (c < CH) {
-                    const uint4 bits = *reinterpret_cast<const uint4*>(&myrow[q]);
-                    st_relaxed_sys_v4(slot + 4 + 2 * c, make_unit(bits.x, bits.y, epoch));
-                    st_relaxed_sys_v4(slot + 4 + 2 * c + 1, make_unit(bits.z, bits.w, epoch));
-                  }
+              for (int q = 0; q < QL; ++q) {
+                const int c = lane + 32 * q;
+                if (c < CH) {
+                  const uint4 bits = *reinterpret_cast<const uint4*>(&myrow[q]);
+                  st_relaxed_sys_v4(slot + 4 + 2 * c, make_unit(bits.x, bits.y, epoch));
+                  st_relaxed_sys_v4(slot + 4 + 2 * c + 1, make_unit(bits.z, bits.w, epoch));
                 }
-                if (lane == 1) st_relaxed_sys_v4(slot + 1, make_unit(ua.x, ua.y, epoch));
-                if (lane == 2) st_relaxed_sys_v4(slot + 2, un);
-                if (sizeof(T) == 8 && lane == 3) st_relaxed_sys_v4(slot + 3, uk);
-              }
-              // the record: into the private level-2 mailbox of every CTA of rank r
-#pragma unroll
-              for (int mm = 0; mm < MAXM; ++mm) {
-                const int t = lane + 32 * mm;
-                if (t < ncta) st_relaxed_sys_v4(sh->peer[r] + (((size_t)t * 2 + par) * NCAND + k) * BOX_RANKS + P.rank, rec);
               }
             }
           }
