@@ -159,9 +159,31 @@ int b2svm_kernel_matvec(int32_t device, void* stream, const b2svm_kernel_desc* k
                         const void* Xb, int64_t nb, int64_t ldb, const double* coef, double* out);
 
 /* NormalRFF.transform (rff.py:19-20): out[n][D] = sqrt(2/D) * cos(X W^T + b), float64 like the
- * reference (W, b float64 [D][d], [D]; X in x_dtype). */
+ * reference (W, b float64 [D][d], [D]; X in x_dtype).  float64 X (the sklearn datasets): float64 arithmetic, exact to
+ * 1e-13.  float32 X with n_features <= 96, n >= 1024, D >= 128: tcgen05 GEMM (3xTF32) + cos epilogue + TMA stores; the
+ * cos ARGUMENT is then accurate to ~1e-6 (float32 X against float64 W: the reference promotes X), the values to ~2e-6
+ * of sqrt(2/D) -- enough for the kernel approximation the features serve, not bit parity. */
 int b2svm_rff_transform(int32_t device, void* stream, int32_t x_dtype, const void* X, int64_t n,
                         int64_t ldx, int32_t d, const double* W, const double* b, int32_t D, double* out);
+
+/* The same features as float32 (prediction-only pipelines, and half the bytes of the HBM-write-bound transform).
+ * Tensor-core path only: float32 X with n_features <= 96; out: dev [n][ldo] float32, ldo*4 a multiple of 16. */
+int b2svm_rff_transform_f32(int32_t device, void* stream, const float* X, int64_t n, int64_t ldx, int32_t d,
+                            const double* W, const double* b, int32_t D, float* out, int64_t ldo);
+
+/* Dense kernel matrix out[i][j] = K(Xa[i], Xb[j]) in the dtype of X (dev [na][ldo]): what the reference's dense-Q
+ * mode (cache_size == 0: svc.py:251-253, :419-421; oc_svm.py:85-89) and its rff=True kernel z(a).z(b) (svc.py:225-228)
+ * build on the host with kernel_func(X, X).  float32 with n_features <= 96 and >= 1024 rows on both sides: tcgen05 GEMM
+ * (3xTF32) + kernel epilogue + TMA stores; float64 and everything else: a tiled FMA kernel (products accumulated in
+ * feature order).  kind: linear / poly / rbf / sigmoid.  Synchronises the stream. */
+int b2svm_kernel_matrix(int32_t device, void* stream, const b2svm_kernel_desc* k, int32_t x_dtype, int32_t n_features,
+                        const void* Xa, int64_t na, int64_t lda, const void* Xb, int64_t nb, int64_t ldb,
+                        void* out, int64_t ldo);
+
+/* out[c] = sum_r w[r] * X[r][c] as float64 (dev [d]): the primal weights w = X^T (alpha*y) of the Linear* estimators
+ * (svc.py:76, svr.py:89-90, telescoped) and Z^T coef of the RFF decision.  Deterministic summation order. */
+int b2svm_weighted_rows(int32_t device, void* stream, int32_t x_dtype, const void* X, int64_t n, int64_t ldx, int32_t d,
+                        const double* w, double* out);
 
 /* z(q) . wz  without materialising z(q):  out[q] = sum_k sqrt(2/D) cos(x_q . W_k + b_k) * wz[k].
  * float32 queries (n_features <= 128, nq >= 1024, D >= 256) run as a tcgen05 GEMM with a cos epilogue, argument error

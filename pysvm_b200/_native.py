@@ -19,7 +19,7 @@ EXPORTS = [
     "b2svm_init_gradient", "b2svm_select", "b2svm_update", "b2svm_kernel_column", "b2svm_solve",
     "b2svm_rho", "b2svm_rho_b", "b2svm_kernel_matvec", "b2svm_rff_transform", "b2svm_rff_decision",
     "b2svm_solve_batched", "b2svm_mailbox_export", "b2svm_mailbox_attach", "b2svm_prepare", "b2svm_bias_partials",
-    "b2svm_host_std", "b2svm_solve_ranks_on_one_gpu",
+    "b2svm_host_std", "b2svm_solve_ranks_on_one_gpu", "b2svm_rff_transform_f32", "b2svm_kernel_matrix", "b2svm_weighted_rows",
 ]
 
 
@@ -89,6 +89,9 @@ def load():
     lib.b2svm_rho_b.argtypes = [vp, P(dbl), P(dbl)]
     lib.b2svm_kernel_matvec.argtypes = [i32, vp, P(KernelDesc), i32, i32, vp, i64, i64, vp, i64, i64, vp, vp]
     lib.b2svm_rff_transform.argtypes = [i32, vp, i32, vp, i64, i64, i32, vp, vp, i32, vp]
+    lib.b2svm_rff_transform_f32.argtypes = [i32, vp, vp, i64, i64, i32, vp, vp, i32, vp, i64]
+    lib.b2svm_kernel_matrix.argtypes = [i32, vp, P(KernelDesc), i32, i32, vp, i64, i64, vp, i64, i64, vp, i64]
+    lib.b2svm_weighted_rows.argtypes = [i32, vp, i32, vp, i64, i64, i32, vp, vp]
     lib.b2svm_rff_decision.argtypes = [i32, vp, i32, vp, i64, i64, i32, vp, vp, i32, vp, vp]
     lib.b2svm_solve_batched.argtypes = [P(vp), i32, i64, P(SolveStats)]
     lib.b2svm_solve_ranks_on_one_gpu.argtypes = [P(vp), i32, i64, P(SolveStats)]

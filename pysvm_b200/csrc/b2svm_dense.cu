@@ -322,6 +322,124 @@ static int rff_launch(int device, void* stream_, int x_dtype, const void* X, int
   return B2SVM_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// dense kernel matrix out[i][j] = K(a_i, b_j) in the input dtype (the reference's dense-Q mode builds
+// y y^T * kernel_func(X, X) on the host: svc.py:251-253, oc_svm.py:85-89; with rff=True the kernel is z(a).z(b),
+// svc.py:225-228).  CUDA-core version: float64 (exact like the reference's BLAS product up to summation order) and
+// every shape the tensor-core path (tile_tc, float32, d <= 96) does not take.  64 x 64 tile per block, 4 x 4 per
+// thread, K in chunks of 16 through shared memory; products are accumulated in increasing feature order.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void sq_norms_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n; r += nwarps) {
+    T s = 0;
+    for (int c = lane; c < d; c += 32) {
+      const T v = X[r * ld + c];
+      s += v * v;
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[r] = s;
+  }
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256) kernel_matrix_kernel(const T* __restrict__ A, int64_t lda, int64_t na, const T* __restrict__ B,
+                                                            int64_t ldb, int64_t nb, int d, const T* __restrict__ an,
+                                                            const T* __restrict__ bn, KernelParams<T> kp, T* __restrict__ out,
+                                                            int64_t ldo) {
+  __shared__ T As[16][65], Bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t i0 = (int64_t)blockIdx.y * 64, j0 = (int64_t)blockIdx.x * 64;
+  T acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+  for (int k0 = 0; k0 < d; k0 += 16) {
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      const int r = e >> 4, k = e & 15;
+      As[k][r] = (i0 + r < na && k0 + k < d) ? A[(i0 + r) * lda + k0 + k] : T(0);
+      Bs[k][r] = (j0 + r < nb && k0 + k < d) ? B[(j0 + r) * ldb + k0 + k] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      T av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = As[k][ty * 4 + a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[k][tx * 4 + b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int64_t i = i0 + ty * 4 + a;
+    if (i >= na) continue;
+    const T ni = KIND == K_RBF ? an[i] : T(0);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t j = j0 + tx * 4 + b;
+      if (j < nb) out[i * ldo + j] = kernel_value_k<KIND>(kp, acc[a][b], ni, KIND == K_RBF ? bn[j] : T(0));
+    }
+  }
+}
+
+template <typename T>
+static int kernel_matrix_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const T* A, int64_t na, int64_t lda, const T* B,
+                           int64_t nb, int64_t ldb, T* out, int64_t ldo) {
+  keep_pool_memory();
+  T *an = nullptr, *bn = nullptr;
+  if (k.kind == K_RBF) {
+    B2_CUDA(cudaMallocAsync(&an, sizeof(T) * (size_t)na, stream));
+    B2_CUDA(cudaMallocAsync(&bn, sizeof(T) * (size_t)nb, stream));
+    sq_norms_kernel<T><<<(int)std::max<int64_t>(1, std::min<int64_t>(1184, (na * 32 + 255) / 256)), 256, 0, stream>>>(A, lda, na, d, an);
+    sq_norms_kernel<T><<<(int)std::max<int64_t>(1, std::min<int64_t>(1184, (nb * 32 + 255) / 256)), 256, 0, stream>>>(B, ldb, nb, d, bn);
+  }
+  KernelParams<T> kp{k.kind, (T)k.gamma, (T)k.coef0, (T)k.degree};
+  dim3 grid((unsigned)((nb + 63) / 64), (unsigned)((na + 63) / 64));
+  switch (k.kind) {
+    case K_RBF: kernel_matrix_kernel<T, K_RBF><<<grid, 256, 0, stream>>>(A, lda, na, B, ldb, nb, d, an, bn, kp, out, ldo); break;
+    case K_POLY: kernel_matrix_kernel<T, K_POLY><<<grid, 256, 0, stream>>>(A, lda, na, B, ldb, nb, d, an, bn, kp, out, ldo); break;
+    case K_SIGMOID: kernel_matrix_kernel<T, K_SIGMOID><<<grid, 256, 0, stream>>>(A, lda, na, B, ldb, nb, d, an, bn, kp, out, ldo); break;
+    default: kernel_matrix_kernel<T, K_LINEAR><<<grid, 256, 0, stream>>>(A, lda, na, B, ldb, nb, d, an, bn, kp, out, ldo); break;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (an) cudaFreeAsync(an, stream);
+  if (bn) cudaFreeAsync(bn, stream);
+  if (e != cudaSuccess) return fail(B2SVM_E_CUDA, cudaGetErrorString(e));
+  return B2SVM_OK;
+}
+
+// out[c] = sum_r w[r] X[r][c] in float64 (primal weights of the linear estimators, svc.py:76 / svr.py:89-90 telescoped;
+// z(x).(Z^T coef) of the RFF decision).  Deterministic: fixed row slices, partial sums reduced in slice order.
+template <typename T>
+__global__ void __launch_bounds__(256) weighted_rows_kernel(const T* __restrict__ X, int64_t ld, int64_t n, int d,
+                                                            const double* __restrict__ w, int64_t rows_per_slice,
+                                                            double* __restrict__ partial) {
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice, r1 = min(n, r0 + rows_per_slice);
+  double acc = 0.0;
+  if (c < d)
+    for (int64_t r = r0 + ty; r < r1; r += 8) acc = fma(w[r], (double)X[r * ld + c], acc);
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < d) {
+    double s = 0.0;
+    for (int y = 0; y < 8; ++y) s += red[y][tx];
+    partial[(size_t)blockIdx.y * d + c] = s;
+  }
+}
+
 }  // namespace b2svm
 
 using namespace b2svm;
@@ -338,10 +456,82 @@ int b2svm_kernel_matvec(int32_t device, void* stream, const b2svm_kernel_desc* k
   return kernel_matvec_impl((cudaStream_t)stream, *k, x_dtype, n_features, Xa, na, lda, Xb, nb, ldb, coef, out);
 }
 
+// does the tensor-core tile kernel take this RFF transform?  B2SVM_RFF_TC=0 keeps the float64 kernel, =2 forces it
+static bool rff_transform_on_tc(int32_t x_dtype, int64_t n, int32_t d, int32_t D, int64_t ldo, bool out_f64, const void* out) {
+  int mode = x_dtype == B2SVM_F32 ? 1 : 0;
+  if (const char* e = getenv("B2SVM_RFF_TC")) mode = std::min(mode ? 2 : 0, atoi(e));
+  if (!tile_tc_ok(d, ldo, out_f64, out)) return false;
+  return mode == 2 || (mode == 1 && n >= 1024 && D >= 128);
+}
+
 int b2svm_rff_transform(int32_t device, void* stream, int32_t x_dtype, const void* X, int64_t n, int64_t ldx, int32_t d,
                         const double* W, const double* b, int32_t D, double* out) {
   if (!X || !W || !b || !out) return fail(B2SVM_E_INVALID, "null argument");
+  if (n <= 0 || D <= 0 || d <= 0) return fail(B2SVM_E_INVALID, "empty RFF problem");
+  if (rff_transform_on_tc(x_dtype, n, d, D, D, true, out)) {
+    B2_CUDA(cudaSetDevice(device));
+    b2svm_kernel_desc k{};
+    return tile_tc((cudaStream_t)stream, k, d, (const float*)X, ldx, n, nullptr, 0, W, b, D, std::sqrt(2.0 / (double)D), out, D, true);
+  }
   return rff_launch<false>(device, stream, x_dtype, X, n, ldx, d, W, b, D, nullptr, out);
+}
+
+int b2svm_rff_transform_f32(int32_t device, void* stream, const float* X, int64_t n, int64_t ldx, int32_t d, const double* W,
+                            const double* b, int32_t D, float* out, int64_t ldo) {
+  if (!X || !W || !b || !out) return fail(B2SVM_E_INVALID, "null argument");
+  if (n <= 0 || D <= 0 || d <= 0 || ldo < D) return fail(B2SVM_E_INVALID, "empty RFF problem / bad output pitch");
+  if (!tile_tc_ok(d, ldo, false, out))
+    return fail(B2SVM_E_UNSUPPORTED, "rff_transform_f32 needs n_features <= 96 and a 16-byte aligned output pitch (tensor-core path only)");
+  B2_CUDA(cudaSetDevice(device));
+  b2svm_kernel_desc k{};
+  return tile_tc((cudaStream_t)stream, k, d, X, ldx, n, nullptr, 0, W, b, D, std::sqrt(2.0 / (double)D), out, ldo, false);
+}
+
+int b2svm_kernel_matrix(int32_t device, void* stream, const b2svm_kernel_desc* k, int32_t x_dtype, int32_t n_features,
+                        const void* Xa, int64_t na, int64_t lda, const void* Xb, int64_t nb, int64_t ldb, void* out, int64_t ldo) {
+  if (!k || !Xa || !Xb || !out) return fail(B2SVM_E_INVALID, "null argument");
+  if (x_dtype != B2SVM_F32 && x_dtype != B2SVM_F64) return fail(B2SVM_E_INVALID, "bad x_dtype");
+  if (k->kind < 0 || k->kind > 3) return fail(B2SVM_E_INVALID, "bad kernel kind");
+  if (n_features <= 0 || na <= 0 || nb <= 0 || lda < n_features || ldb < n_features || ldo < nb) return fail(B2SVM_E_INVALID, "bad shape");
+  B2_CUDA(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (x_dtype == B2SVM_F32) {
+    int mode = 1;
+    if (const char* e = getenv("B2SVM_GRAM_TC")) mode = atoi(e);
+    if (mode > 0 && tile_tc_ok(n_features, ldo, false, out) && (mode == 2 || (na >= 1024 && nb >= 1024)))
+      return tile_tc(s, *k, n_features, (const float*)Xa, lda, na, (const float*)Xb, ldb, nullptr, nullptr, nb, 1.0, out, ldo, false);
+    int rc = kernel_matrix_T<float>(s, *k, n_features, (const float*)Xa, na, lda, (const float*)Xb, nb, ldb, (float*)out, ldo);
+    if (rc) return rc;
+  } else {
+    int rc = kernel_matrix_T<double>(s, *k, n_features, (const double*)Xa, na, lda, (const double*)Xb, nb, ldb, (double*)out, ldo);
+    if (rc) return rc;
+  }
+  B2_CUDA(cudaStreamSynchronize(s));
+  return B2SVM_OK;
+}
+
+int b2svm_weighted_rows(int32_t device, void* stream, int32_t x_dtype, const void* X, int64_t n, int64_t ldx, int32_t d,
+                        const double* w, double* out) {
+  if (!X || !w || !out) return fail(B2SVM_E_INVALID, "null argument");
+  if (x_dtype != B2SVM_F32 && x_dtype != B2SVM_F64) return fail(B2SVM_E_INVALID, "bad x_dtype");
+  if (n <= 0 || d <= 0 || ldx < d) return fail(B2SVM_E_INVALID, "bad shape");
+  B2_CUDA(cudaSetDevice(device));
+  cudaStream_t s = (cudaStream_t)stream;
+  keep_pool_memory();
+  const int gx = (d + 31) / 32;
+  int ny = (int)std::max<int64_t>(1, std::min<int64_t>(n / 256 + 1, (4 * 148 + gx - 1) / gx));
+  const int64_t rps = (n + ny - 1) / ny;
+  ny = (int)((n + rps - 1) / rps);
+  double* partial = nullptr;
+  B2_CUDA(cudaMallocAsync(&partial, sizeof(double) * (size_t)ny * d, s));
+  if (x_dtype == B2SVM_F64) weighted_rows_kernel<double><<<dim3(gx, ny), 256, 0, s>>>((const double*)X, ldx, n, d, w, rps, partial);
+  else weighted_rows_kernel<float><<<dim3(gx, ny), 256, 0, s>>>((const float*)X, ldx, n, d, w, rps, partial);
+  reduce_partials_kernel<<<std::max(1, (d + 255) / 256), 256, 0, s>>>(partial, ny, d, out);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(partial, s);
+  if (e != cudaSuccess) return fail(B2SVM_E_CUDA, cudaGetErrorString(e));
+  B2_CUDA(cudaStreamSynchronize(s));
+  return B2SVM_OK;
 }
 
 int b2svm_rff_decision(int32_t device, void* stream, int32_t x_dtype, const void* Xq, int64_t nq, int64_t ldx, int32_t d,

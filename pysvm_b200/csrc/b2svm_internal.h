@@ -37,6 +37,11 @@ int matvec_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const floa
 int rff_decision_tc(cudaStream_t stream, int d, const double* W, const double* b, int D, const double* wz, const float* Xq,
                     int64_t nq, int64_t ldq, double* out);
 
+// tile-output tensor-core kernel: out[m][n] = scale * f(a_m . b_n) written with TMA stores (b2svm_matvec_tc.cu)
+bool tile_tc_ok(int d, int64_t ldo, bool out_f64, const void* out);
+int tile_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const float* A, int64_t lda, int64_t m, const float* Bf,
+            int64_t ldb, const double* Wd, const double* phase_d, int64_t n, double scale, void* out, int64_t ldo, bool out_f64);
+
 void keep_pool_memory();   // stream-ordered allocator: keep up to 4 GB of work buffers between calls
 
 struct ProblemDev;

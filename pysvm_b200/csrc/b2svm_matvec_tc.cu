@@ -152,11 +152,11 @@ struct TcParams {
 // (split_rows_kernel) and c2 = 2 gamma log2(e): one add, one fma, one MUFU.EX2.  The rounding of the exponent
 // is |x| 2^-24 relative -- the same order as the float32 rounding of -gamma * dist in the reference (svc.py:230-232).
 template <int KIND>
-__device__ __forceinline__ float epi_value(const TcParams& p, uint32_t dot_bits, float norm_s, float norm_q) {
+__device__ __forceinline__ float epi_value(float c2, const KernelParams<float>& kp, uint32_t dot_bits, float norm_s, float norm_q) {
   const float dot = __uint_as_float(dot_bits);
   if constexpr (KIND == K_RBF) {
     float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(p.c2, dot, norm_s + norm_q)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(c2, dot, norm_s + norm_q)));
     return r;
   } else if constexpr (KIND == K_RFFCOS) {
     // cos(w_s . x_q + b_s): reduce to [-pi, pi] with a two-term 2 pi, then MUFU.COS (abs error ~5e-7)
@@ -168,7 +168,7 @@ __device__ __forceinline__ float epi_value(const TcParams& p, uint32_t dot_bits,
     asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(u));
     return r;
   } else {
-    return kernel_value_k<KIND>(p.kp, dot, norm_s, norm_q);
+    return kernel_value_k<KIND>(kp, dot, norm_s, norm_q);
   }
 }
 
@@ -187,10 +187,10 @@ __device__ __forceinline__ double accum32(const TcParams& p, const uint32_t (&v)
   for (int j = 0; j < 8; ++j) {
     const float4 n = n4[j];                                      // shared-memory broadcast reads
     const float4 c = c4[j];
-    s0 = fmaf(c.x, epi_value<KIND>(p, v[4 * j + 0], n.x, nq), s0);
-    s1 = fmaf(c.y, epi_value<KIND>(p, v[4 * j + 1], n.y, nq), s1);
-    s2 = fmaf(c.z, epi_value<KIND>(p, v[4 * j + 2], n.z, nq), s2);
-    s3 = fmaf(c.w, epi_value<KIND>(p, v[4 * j + 3], n.w, nq), s3);
+    s0 = fmaf(c.x, epi_value<KIND>(p.c2, p.kp, v[4 * j + 0], n.x, nq), s0);
+    s1 = fmaf(c.y, epi_value<KIND>(p.c2, p.kp, v[4 * j + 1], n.y, nq), s1);
+    s2 = fmaf(c.z, epi_value<KIND>(p.c2, p.kp, v[4 * j + 2], n.z, nq), s2);
+    s3 = fmaf(c.w, epi_value<KIND>(p.c2, p.kp, v[4 * j + 3], n.w, nq), s3);
   }
   return (double)((s0 + s1) + (s2 + s3));
 }
@@ -336,7 +336,7 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
       } else {   // last, ragged tile: padding rows carry coefficient 0, but their kernel value need not be finite
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (s0 + j < p.nsv) sum = fma(__ldg(p.svc + s0 + j), (double)epi_value<KIND>(p, v[j], __ldg(p.svn + s0 + j), nq), sum);
+          if (s0 + j < p.nsv) sum = fma(__ldg(p.svc + s0 + j), (double)epi_value<KIND>(p.c2, p.kp, v[j], __ldg(p.svn + s0 + j), nq), sum);
       }
       __syncwarp();   // every lane is done with the staged metadata before the next tile overwrites it
     }
@@ -347,6 +347,190 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
     asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
     if (part == 0 && q0 + qrow < p.nq)
       p.partial[(size_t)blockIdx.y * p.nq + q0 + qrow] = ((sum + red[qrow]) + red[TC_M + qrow]) + red[2 * TC_M + qrow];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ tile-output variant
+// The same GEMM pipeline (TMA -> tcgen05.mma 3xTF32 -> TMEM), but the epilogue WRITES the tile: out[m][n] =
+// f(a_m . b_n, row scalar, column scalar) -- random Fourier features sqrt(2/D) cos(x w^T + b) (rff.py:19-20) and the
+// dense kernel matrix K(X, X) of the reference's dense-Q mode (svc.py:251-253).  Each epilogue warp owns 32 rows x 32
+// columns of the accumulator; every thread converts its row's values, writes them into a 128-byte-swizzled staging
+// tile in shared memory (conflict-free 16-byte stores) and one lane hands the tile to the TMA store engine
+// (cp.async.bulk.tensor.2d.global.shared::cta, SASS UTMASTG): full-line writes, no LSU traffic, clipped to the
+// tensor bounds by the hardware (ragged last tiles need no masks).  The kernel is bound by the HBM write stream.
+struct TileParams {
+  const float* coln;     // [n_pad] per-column scalar: phase b (rff) / squared norm pre-scaled (rbf)
+  const float* rown;     // [m_pad] per-row scalar
+  int tiles_total;       // column tiles of 128
+  int tiles_per_slice;
+  int kb, stages;
+  float c2, scale;       // rbf exponent factor; output scale (rff: sqrt(2/D))
+  int nbuf;              // staging buffers per epilogue warp (1 or 2)
+  KernelParams<float> kp;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c_inner), "r"(c_outer), "r"(smem_u32(smem_src))
+               : "memory");
+}
+
+template <int KIND, typename OUT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tile_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+               const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+               const __grid_constant__ CUtensorMap tm_out, TileParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_tc[];
+  const int KB = p.kb, ST = p.stages;
+  constexpr int BOXC = 128 / (int)sizeof(OUT);        // columns per 128-byte staging row: 16 doubles / 32 floats
+  constexpr int NBOX = 32 / BOXC;                      // TMA stores per 32-column part: 2 / 1
+  unsigned char* a_hi = smem_tc;
+  unsigned char* a_lo = a_hi + (size_t)KB * TC_TILE_BYTES;
+  unsigned char* b_base = a_lo + (size_t)KB * TC_TILE_BYTES;
+  const size_t b_stage_bytes = (size_t)2 * TC_TILE_BYTES;
+  unsigned char* stage_base = b_base + (size_t)ST * b_stage_bytes;                 // [epilogue warp][nbuf][32 rows][128 B], 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + (size_t)TC_EPI_WARPS * p.nbuf * 4096);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;
+  uint64_t* b_empty = b_full + ST;
+  uint64_t* t_full = b_empty + ST;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  unsigned char* meta = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_M;
+  const int tile_begin = blockIdx.y * p.tiles_per_slice;
+  const int tile_end = min(p.tiles_total, tile_begin + p.tiles_per_slice);
+  const int ntile = max(0, tile_end - tile_begin);
+
+  if (threadIdx.x == 0) {
+    mbar_init(a_full, 1);
+    for (int s = 0; s < ST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], TC_EPI_WARPS); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer (as in matvec_tc_kernel)
+      mbar_arrive_expect_tx(a_full, (uint32_t)(2 * KB * TC_TILE_BYTES));
+      for (int kb = 0; kb < KB; ++kb) {
+        tma_load_2d(a_hi + (size_t)kb * TC_TILE_BYTES, &tm_a_hi, kb * TC_KBLK, m0, a_full);
+        tma_load_2d(a_lo + (size_t)kb * TC_TILE_BYTES, &tm_a_lo, kb * TC_KBLK, m0, a_full);
+      }
+      for (int step = 0; step < ntile * KB; ++step) {
+        const int s = step % ST, it = step / KB, kb = step - it * KB;
+        mbar_wait(&b_empty[s], (uint32_t)(((step / ST) & 1) ^ 1));
+        unsigned char* bh = b_base + (size_t)s * b_stage_bytes;
+        mbar_arrive_expect_tx(&b_full[s], (uint32_t)b_stage_bytes);
+        const int row = (tile_begin + it) * TC_N;
+        tma_load_2d(bh, &tm_b_hi, kb * TC_KBLK, row, &b_full[s]);
+        tma_load_2d(bh + TC_TILE_BYTES, &tm_b_lo, kb * TC_KBLK, row, &b_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer
+      mbar_wait(a_full, 0);
+      int step = 0;
+      for (int it = 0; it < ntile; ++it) {
+        const int acc = it & 1;
+        mbar_wait(&t_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_N);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < KB; ++kb, ++step) {
+          const int s = step % ST;
+          mbar_wait(&b_full[s], (uint32_t)((step / ST) & 1));
+          tc_fence_after();
+          const unsigned char* bh = b_base + (size_t)s * b_stage_bytes;
+          const unsigned char* bl = bh + TC_TILE_BYTES;
+          for (int pass = 0; pass < 3; ++pass) {   // lo.hi + hi.lo + hi.hi, small terms first
+            const uint64_t da = umma_desc_sw128((pass == 0 ? a_lo : a_hi) + (size_t)kb * TC_TILE_BYTES);
+            const uint64_t db = umma_desc_sw128(pass == 1 ? bl : bh);
+#pragma unroll
+            for (int k = 0; k < TC_KBLK / 8; ++k) {
+              tc_mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), TC_IDESC, accumulate);
+              accumulate = 1;
+            }
+          }
+          tc_commit(&b_empty[s]);
+        }
+        tc_commit(&t_full[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue warps: TMEM lane = output row; warp (quarter, part) owns rows quarter*32.. and columns part*32..
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int part = ew >> 2;
+    const int mrow = quarter * 32 + lane;
+    const float rs = p.rown ? p.rown[m0 + mrow] : 0.f;
+    float* wn = reinterpret_cast<float*>(meta + (size_t)ew * 128);
+    unsigned char* stg = stage_base + (size_t)ew * p.nbuf * 4096;
+    float mn = 0.f;
+    if (ntile > 0) mn = __ldg(p.coln + tile_begin * TC_N + part * 32 + lane);
+    int buf = 0;
+    for (int it = 0; it < ntile; ++it) {
+      const int acc = it & 1;
+      mbar_wait(&t_full[acc], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const int n0 = (tile_begin + it) * TC_N + part * 32;
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + part * 32);
+      B2_TMEM_LD32(taddr, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);     // accumulator slice is in registers: hand the TMEM buffer back
+      wn[lane] = mn;
+      __syncwarp();
+      if (it + 1 < ntile) mn = __ldg(p.coln + n0 + TC_N + lane);
+#pragma unroll
+      for (int b = 0; b < NBOX; ++b) {
+        unsigned char* tile = stg + (size_t)buf * 4096;
+        // the staging tile may still be read by the TMA store issued nbuf boxes ago
+        if (lane == 0) {
+          if (p.nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncwarp();
+        // my row: BOXC values = 8 chunks of 16 bytes, chunk position XORed with (row & 7) (the 128-byte TMA swizzle)
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          constexpr int EPC = 16 / (int)sizeof(OUT);     // values per 16-byte chunk: 2 doubles / 4 floats
+          OUT o[EPC];
+#pragma unroll
+          for (int e = 0; e < EPC; ++e) {
+            const int j = b * BOXC + ch * EPC + e;
+            o[e] = (OUT)(p.scale * epi_value<KIND>(p.c2, p.kp, v[j], wn[j], rs));
+          }
+          *reinterpret_cast<uint4*>(tile + lane * 128 + ((ch ^ (lane & 7)) << 4)) = *reinterpret_cast<const uint4*>(o);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm_out, tile, n0 + b * BOXC, m0 + quarter * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        buf = (buf + 1 == p.nbuf) ? 0 : buf + 1;
+      }
+      __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
   }
 
   tc_fence_before();
@@ -510,6 +694,115 @@ static int matvec_tc_core(cudaStream_t stream, const b2svm_kernel_desc& k, int d
   TC_TRY(cudaGetLastError());
   TC_TRY(cudaStreamSynchronize(stream));
 #undef TC_TRY
+  return done(B2SVM_OK);
+}
+
+__global__ void phase_kernel(const double* __restrict__ b, int D, int D_pad, float* __restrict__ phase) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < D_pad; k += gridDim.x * blockDim.x) phase[k] = k < D ? (float)b[k] : 0.f;
+}
+
+static bool make_out_map(CUtensorMap* m, void* base, int64_t rows, int64_t cols, int64_t ld, bool f64) {
+  const size_t esz = f64 ? 8 : 4;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / esz), 32u};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode_fn()(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// can the tile-output tensor path take this shape?  (float32 operands, K blocks that leave room for the staging tiles,
+// a 16-byte friendly output pitch)
+bool tile_tc_ok(int d, int64_t ldo, bool out_f64, const void* out) {
+  if (encode_fn() == nullptr || d > 96) return false;
+  const size_t esz = out_f64 ? 8 : 4;
+  return (ldo * esz) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+}
+
+// out[m][n] = scale * f(a_m . b_n): f = cos(. + phase_n) (W / b given as float64: NormalRFF.transform) or the kernel
+// function of `k` (Bf rows float32: the dense kernel matrix).  out is float64 or float32 with row pitch ldo (elements).
+int tile_tc(cudaStream_t stream, const b2svm_kernel_desc& k, int d, const float* A, int64_t lda, int64_t m, const float* Bf,
+            int64_t ldb, const double* Wd, const double* phase_d, int64_t n, double scale, void* out, int64_t ldo, bool out_f64) {
+  keep_pool_memory();
+  const bool rff = Wd != nullptr;
+  const int dp = (d + TC_KBLK - 1) / TC_KBLK * TC_KBLK;
+  const int KB = dp / TC_KBLK;
+  const int64_t m_pad = (m + TC_M - 1) / TC_M * TC_M, n_pad = (n + TC_N - 1) / TC_N * TC_N;
+  float *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr, *rown = nullptr, *coln = nullptr;
+  auto done = [&](int code) {
+    for (void* ptr : {(void*)a_hi, (void*)a_lo, (void*)b_hi, (void*)b_lo, (void*)rown, (void*)coln})
+      if (ptr) cudaFreeAsync(ptr, stream);
+    return code;
+  };
+#define TT_TRY(expr)                                                                                             \
+  do {                                                                                                           \
+    cudaError_t _e = (expr);                                                                                     \
+    if (_e != cudaSuccess) return done(fail(B2SVM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)));  \
+  } while (0)
+  TT_TRY(cudaMallocAsync(&a_hi, sizeof(float) * m_pad * dp, stream));
+  TT_TRY(cudaMallocAsync(&a_lo, sizeof(float) * m_pad * dp, stream));
+  TT_TRY(cudaMallocAsync(&b_hi, sizeof(float) * n_pad * dp, stream));
+  TT_TRY(cudaMallocAsync(&b_lo, sizeof(float) * n_pad * dp, stream));
+  TT_TRY(cudaMallocAsync(&rown, sizeof(float) * m_pad, stream));
+  TT_TRY(cudaMallocAsync(&coln, sizeof(float) * n_pad, stream));
+  const float norm_scale = (!rff && k.kind == K_RBF) ? (float)(-(double)(float)k.gamma * 1.4426950408889634) : 1.0f;
+  auto grid_rows = [](int64_t rows) { return (int)std::max<int64_t>(1, std::min<int64_t>(148 * 8, (rows * 32 + 255) / 256)); };
+  split_rows_kernel<<<grid_rows(m_pad), 256, 0, stream>>>(A, lda, d, dp, nullptr, m, m_pad, a_hi, a_lo, rown, norm_scale);
+  if (rff) {
+    split_rows_f64_kernel<<<grid_rows(n_pad), 256, 0, stream>>>(Wd, d, dp, n, n_pad, b_hi, b_lo);
+    phase_kernel<<<std::max(1, (int)((n_pad + 255) / 256)), 256, 0, stream>>>(phase_d, (int)n, (int)n_pad, coln);
+  } else {
+    split_rows_kernel<<<grid_rows(n_pad), 256, 0, stream>>>(Bf, ldb, d, dp, nullptr, n, n_pad, b_hi, b_lo, coln, norm_scale);
+  }
+  TT_TRY(cudaGetLastError());
+  CUtensorMap m_ah, m_al, m_bh, m_bl, m_out;
+  if (!make_map(&m_ah, a_hi, m_pad, dp) || !make_map(&m_al, a_lo, m_pad, dp) || !make_map(&m_bh, b_hi, n_pad, dp) ||
+      !make_map(&m_bl, b_lo, n_pad, dp) || !make_out_map(&m_out, out, m, n, ldo, out_f64))
+    return done(fail(B2SVM_E_CUDA, "cuTensorMapEncodeTiled failed"));
+  TileParams p;
+  p.coln = coln;
+  p.rown = rown;
+  p.tiles_total = (int)(n_pad / TC_N);
+  const int gx = (int)(m_pad / TC_M);
+  int ny = std::max(1, std::min(p.tiles_total, (2 * 148 + gx - 1) / gx));
+  ny = std::min(ny, 65535);
+  p.tiles_per_slice = (p.tiles_total + ny - 1) / ny;
+  ny = (p.tiles_total + p.tiles_per_slice - 1) / p.tiles_per_slice;
+  p.kb = KB;
+  p.c2 = (float)(2.0 * (double)(float)k.gamma * 1.4426950408889634);
+  p.scale = (float)scale;
+  p.kp = KernelParams<float>{k.kind, (float)k.gamma, (float)k.coef0, (float)k.degree};
+  const size_t a_bytes = (size_t)2 * KB * TC_TILE_BYTES, b_stage = (size_t)2 * TC_TILE_BYTES;
+  const size_t fixed = (size_t)(2 * 6 + 8) * sizeof(uint64_t) + 32 + TC_EPI_WARPS * 128 + 1024;
+  const size_t budget = 227 * 1024;
+  p.nbuf = (a_bytes + 2 * b_stage + (size_t)TC_EPI_WARPS * 2 * 4096 + fixed <= budget) ? 2 : 1;
+  const size_t stage_bytes = (size_t)TC_EPI_WARPS * p.nbuf * 4096;
+  if (a_bytes + 2 * b_stage + stage_bytes + fixed > budget) return done(fail(B2SVM_E_UNSUPPORTED, "tile_tc: n_features too large"));
+  p.stages = (int)std::min<size_t>(6, (budget - a_bytes - stage_bytes - fixed) / b_stage);
+  const size_t smem = a_bytes + p.stages * b_stage + stage_bytes + fixed;
+#define TT_LAUNCH(KIND, OUT)                                                                                         \
+  do {                                                                                                               \
+    TT_TRY(cudaFuncSetAttribute(tile_tc_kernel<KIND, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    tile_tc_kernel<KIND, OUT><<<dim3(gx, ny), TC_THREADS, smem, stream>>>(m_ah, m_al, m_bh, m_bl, m_out, p);          \
+  } while (0)
+#define TT_KIND(KIND)                                \
+  do {                                               \
+    if (out_f64) TT_LAUNCH(KIND, double);            \
+    else TT_LAUNCH(KIND, float);                     \
+  } while (0)
+  switch (rff ? K_RFFCOS : k.kind) {
+    case K_RFFCOS: TT_KIND(K_RFFCOS); break;
+    case K_RBF: TT_KIND(K_RBF); break;
+    case K_POLY: TT_KIND(K_POLY); break;
+    case K_SIGMOID: TT_KIND(K_SIGMOID); break;
+    default: TT_KIND(K_LINEAR); break;
+  }
+#undef TT_KIND
+#undef TT_LAUNCH
+  TT_TRY(cudaGetLastError());
+  TT_TRY(cudaStreamSynchronize(stream));
+#undef TT_TRY
   return done(B2SVM_OK);
 }
 

@@ -11,14 +11,23 @@ from . import _native as N
 from .solver import default_device, to_device_matrix
 
 
-def rff_transform_device(X: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """sqrt(2/D) * cos(X w^T + b) as a float64 CUDA matrix (b2svm_rff_transform; rff.py:19-20)."""
+def rff_transform_device(X: torch.Tensor, w: torch.Tensor, b: torch.Tensor, dtype=torch.float64) -> torch.Tensor:
+    """sqrt(2/D) * cos(X w^T + b) as a CUDA matrix (rff.py:19-20): float64 like the reference (b2svm_rff_transform), or
+    float32 for prediction-only pipelines (b2svm_rff_transform_f32: tensor cores, float32 X with at most 96 features)."""
     lib = N.load()
     X = X.contiguous()
     D, d = w.shape
     assert X.shape[1] == d
-    out = torch.empty((X.shape[0], D), dtype=torch.float64, device=X.device)
     torch.cuda.synchronize(X.device)
+    if dtype == torch.float32:
+        if X.dtype != torch.float32:
+            raise TypeError("float32 features need a float32 X")
+        ldo = (D + 3) // 4 * 4
+        out = torch.empty((X.shape[0], ldo), dtype=torch.float32, device=X.device)
+        N.check(lib.b2svm_rff_transform_f32(X.device.index or 0, None, X.data_ptr(), X.shape[0], X.stride(0), d, w.data_ptr(),
+                                            b.data_ptr(), D, out.data_ptr(), ldo))
+        return out if ldo == D else out[:, :D]
+    out = torch.empty((X.shape[0], D), dtype=torch.float64, device=X.device)
     N.check(lib.b2svm_rff_transform(X.device.index or 0, None, N.F64 if X.dtype == torch.float64 else N.F32,
                                     X.data_ptr(), X.shape[0], X.stride(0), d, w.data_ptr(), b.data_ptr(), D,
                                     out.data_ptr()))
@@ -61,11 +70,11 @@ class NormalRFF(TransformerMixin):
             self._b_dev = torch.from_numpy(np.ascontiguousarray(self.b)).to(device)
         return self._w_dev, self._b_dev
 
-    def transform_device(self, X) -> torch.Tensor:
+    def transform_device(self, X, dtype=torch.float64) -> torch.Tensor:
         device = X.device if isinstance(X, torch.Tensor) else default_device()
         Xd = to_device_matrix(X, device)
         w, b = self._device_params(device)
-        return rff_transform_device(Xd, w, b)
+        return rff_transform_device(Xd, w, b, dtype=dtype)
 
     def transform(self, X):
         return self.transform_device(X).cpu().numpy()

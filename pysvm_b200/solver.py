@@ -456,6 +456,36 @@ def kernel_matvec(kernel: KernelSpec, Xa: torch.Tensor, coef: torch.Tensor, Xb: 
     return out
 
 
+def kernel_matrix(kernel: KernelSpec, Xa: torch.Tensor, Xb: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K[i][j] = K(Xa[i], Xb[j]) as a dense device matrix in X's dtype (``b2svm_kernel_matrix``): what the reference's
+    dense-Q mode and its rff=True kernel build with ``kernel_func(X, X)`` on the host (svc.py:251-253, 225-228)."""
+    lib = N.load()
+    Xb = Xa if Xb is None else Xb
+    assert Xa.dtype == Xb.dtype and Xa.shape[1] == Xb.shape[1]
+    Xa, Xb = Xa.contiguous(), Xb.contiguous()
+    nb = Xb.shape[0]
+    ldo = (nb + 3) // 4 * 4 if Xa.dtype == torch.float32 else (nb + 1) // 2 * 2        # 16-byte row pitch
+    out = torch.empty((Xa.shape[0], ldo), dtype=Xa.dtype, device=Xa.device)
+    kd = kernel.desc()
+    torch.cuda.synchronize(Xa.device)
+    N.check(lib.b2svm_kernel_matrix(Xa.device.index or 0, None, C.byref(kd), N.F64 if Xa.dtype == torch.float64 else N.F32,
+                                    Xa.shape[1], Xa.data_ptr(), Xa.shape[0], Xa.stride(0), Xb.data_ptr(), nb, Xb.stride(0),
+                                    out.data_ptr(), ldo))
+    return out if ldo == nb else out[:, :nb].contiguous()
+
+
+def weighted_rows(X: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """sum_r w[r] X[r] as float64 (``b2svm_weighted_rows``): X^T (alpha*y) of the linear estimators, Z^T coef of RFF."""
+    lib = N.load()
+    X = X.contiguous()
+    w = w.to(dtype=torch.float64).contiguous()
+    out = torch.empty(X.shape[1], dtype=torch.float64, device=X.device)
+    torch.cuda.synchronize(X.device)
+    N.check(lib.b2svm_weighted_rows(X.device.index or 0, None, N.F64 if X.dtype == torch.float64 else N.F32, X.data_ptr(),
+                                    X.shape[0], X.stride(0), X.shape[1], w.data_ptr(), out.data_ptr()))
+    return out
+
+
 def solve_batched(solvers, max_iter: int):
     """Solve several independent problems concurrently, one CTA group each, in ONE persistent launch
     (``b2svm_solve_batched``): the one-vs-one / one-vs-rest sub-problems of the multiclass wrappers

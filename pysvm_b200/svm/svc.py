@@ -12,8 +12,8 @@ from sklearn.multiclass import OneVsOneClassifier, OneVsRestClassifier
 
 from .._native import B2SVMError
 from ..rff import NormalRFF, rff_decision_device
-from ..solver import (KernelSpec, host_std, NuSolverWithCache, QColumns, SolverWithCache, default_device, kernel_matvec,
-                      solve_batched, to_device_matrix)
+from ..solver import (KernelSpec, host_std, NuSolverWithCache, QColumns, SolverWithCache, default_device, kernel_matrix,
+                      kernel_matvec, solve_batched, to_device_matrix, weighted_rows)
 
 
 # ---- batching of small independent sub-problems (one-vs-one / one-vs-rest) --------------------------------
@@ -79,9 +79,10 @@ class deferred_solves:
 class _Fitted:
     """What the reference keeps alive inside the ``decision_function`` closure."""
 
-    def __init__(self, solver, func, spec, coef, rff=None, X_raw=None, Z=None):
+    def __init__(self, solver, func, spec, coef, rff=None, X_raw=None, Z=None, X_train=None):
         self.solver, self.func, self.spec, self.coef, self.rff, self.X_raw = solver, func, spec, coef, rff, X_raw
         self.Z = Z            # random Fourier features of the training rows (rff=True)
+        self.X_train = X_train if X_train is not None else func.X     # (dense-Q mode: func.X is the kernel matrix)
         self._wz = None
 
     def kernel_sum(self, x) -> np.ndarray:
@@ -91,11 +92,11 @@ class _Fitted:
             # K(a, b) = z(a).z(b)  =>  coef.K(X, x) = z(x).(Z^T coef)
             Xq = to_device_matrix(x if isinstance(x, torch.Tensor) else np.asarray(x), dev).to(self.X_raw.dtype)
             if self._wz is None:
-                self._wz = self.Z.t().contiguous() @ self.coef
+                self._wz = weighted_rows(self.Z, self.coef)           # Z^T coef (b2svm_weighted_rows)
             w, b = self.rff._device_params(dev)
             return rff_decision_device(Xq, w, b, self._wz).cpu().numpy()
-        Xq = to_device_matrix(x if isinstance(x, torch.Tensor) else np.asarray(x), dev).to(self.func.X.dtype)
-        return kernel_matvec(self.spec, self.func.X, self.coef, Xq).cpu().numpy()
+        Xq = to_device_matrix(x if isinstance(x, torch.Tensor) else np.asarray(x), dev).to(self.X_train.dtype)
+        return kernel_matvec(self.spec, self.X_train, self.coef, Xq).cpu().numpy()
 
 
 class BiLinearSVC(BaseEstimator):
@@ -128,7 +129,7 @@ class BiLinearSVC(BaseEstimator):
         def finish(stats):
             self._report(stats)
             # svc.py:76 accumulates w += delta_i y_i x_i + delta_j y_j x_j; the sum telescopes to X^T (alpha*y)
-            w = (func.X.to(torch.float64).t() @ (solver.alpha * func.y)).cpu().numpy()
+            w = weighted_rows(func.X, solver.alpha * func.y).cpu().numpy()
             self.coef_ = (w, solver.calculate_rho())
             self._fitted = _Fitted(solver, func, func.kernel, solver.alpha * func.y)
 
@@ -213,21 +214,34 @@ class BiKernelSVC(BiLinearSVC):
         """Device Q-column source for this estimator's kernel (the reference's ``func``)."""
         spec, rff = self.register_kernel(host_std(X))
         self._Z = None
+        self._X_dense = None
         if rff is not None:
             Z = rff.transform_device(to_device_matrix(X, default_device()))       # n x D float64, like rff.py:20
             self._Z = Z
             if Z.shape[1] <= 256:
                 return QColumns(Z, y, KernelSpec("linear"), mirror=mirror), spec, rff
             # wider feature maps (default D = 1000): the kernel z(a).z(b) is handed over as a precomputed
-            # n x n matrix (one library GEMM), which the solver reads like a completely filled column cache
+            # n x n matrix (b2svm_kernel_matrix), which the solver reads like a completely filled column cache
             n = Z.shape[0]
-            free, _ = torch.cuda.mem_get_info(Z.device)
-            if n * n * 8 > 0.6 * free:
-                raise NotImplementedError(f"rff=True with D={Z.shape[1]} > 256 needs the n x n kernel matrix "
-                                          f"({n * n * 8 / 2**30:.1f} GiB); use D <= 256 for this many rows")
-            K = torch.matmul(Z, Z.t()).contiguous()
+            self._check_dense(n, 8)
+            K = kernel_matrix(KernelSpec("linear"), Z)
             return QColumns(K, y, KernelSpec("precomputed"), mirror=mirror, cache_bytes=0), spec, rff
+        if self.cache_size == 0:
+            # the reference's dense-Q mode (svc.py:251-253, 419-421; oc_svm.py:85-89): the whole kernel matrix is built
+            # once -- on the device (b2svm_kernel_matrix) -- and every SMO iteration reads two of its columns
+            Xd = to_device_matrix(X, default_device())
+            self._check_dense(Xd.shape[0], Xd.element_size())
+            K = kernel_matrix(spec, Xd)
+            self._X_dense = Xd
+            return QColumns(K, y, KernelSpec("precomputed"), mirror=mirror, cache_bytes=0), spec, None
         return QColumns(X, y, spec, mirror=mirror), spec, None
+
+    @staticmethod
+    def _check_dense(n, esz):
+        free, _ = torch.cuda.mem_get_info(default_device())
+        if n * n * esz > 0.6 * free:
+            raise MemoryError(f"the dense {n} x {n} kernel matrix needs {n * n * esz / 2**30:.1f} GiB of device memory; "
+                              f"use the column cache (cache_size > 0) for this many rows")
 
     def fit(self, X, y):
         X, y = np.asarray(X), np.array(y, dtype=float)     # X is never written: no host copy needed
@@ -251,9 +265,10 @@ class BiKernelSVC(BiLinearSVC):
         return self
 
     def _finish(self, solver, func, spec, rff, X, coef):
-        self._fitted = _Fitted(solver, func, func.kernel, coef, rff=rff,
+        dense = getattr(self, "_X_dense", None)
+        self._fitted = _Fitted(solver, func, spec if dense is not None else func.kernel, coef, rff=rff,
                                X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None,
-                               Z=getattr(self, "_Z", None))
+                               Z=getattr(self, "_Z", None), X_train=dense)
         try:
             self.rho_ = solver.calculate_rho()
         except B2SVMError:
@@ -367,9 +382,10 @@ class BiNuSVC(BiKernelSVC):
         return self._fitted.kernel_sum(x) / rho + b / rho
 
     def _finish(self, solver, func, spec, rff, X, coef):
-        self._fitted = _Fitted(solver, func, func.kernel, coef, rff=rff,
+        dense = getattr(self, "_X_dense", None)
+        self._fitted = _Fitted(solver, func, spec if dense is not None else func.kernel, coef, rff=rff,
                                X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None,
-                               Z=getattr(self, "_Z", None))
+                               Z=getattr(self, "_Z", None), X_train=dense)
         a = solver.alpha.cpu().numpy()
         self.alpha_ = a
         self.support_ = np.flatnonzero(a > 0)

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 from sklearn.metrics import r2_score
 
-from ..solver import KernelSpec, NuSolverWithCache, QColumns, SolverWithCache
+from ..solver import KernelSpec, NuSolverWithCache, QColumns, SolverWithCache, weighted_rows
 from .svc import BiKernelSVC, BiLinearSVC, _Fitted
 
 
@@ -36,7 +36,7 @@ class LinearSVR(BiLinearSVC):
         solver = SolverWithCache(p, y, self.C, self.tol, self.cache_size, func=func, max_iter_hint=self.max_iter)
         self._report(solver.solve(self.max_iter))
         coef = solver.alpha[:l] - solver.alpha[l:]
-        w = (func.X.to(torch.float64).t() @ coef).cpu().numpy()      # svr.py:89-90, telescoped
+        w = weighted_rows(func.X, coef).cpu().numpy()      # svr.py:89-90, telescoped (b2svm_weighted_rows)
         self.coef_ = (w, solver.calculate_rho())
         self._fitted = _Fitted(solver, func, func.kernel, coef)
         return self
@@ -125,9 +125,10 @@ class NuSVR(KernelSVR):
 
     def _finish(self, solver, func, spec, rff, X, coef):
         from ..solver import to_device_matrix
-        self._fitted = _Fitted(solver, func, func.kernel, coef, rff=rff,
+        dense = getattr(self, "_X_dense", None)
+        self._fitted = _Fitted(solver, func, spec if dense is not None else func.kernel, coef, rff=rff,
                                X_raw=to_device_matrix(X[:1], func.device) if rff is not None else None,
-                               Z=getattr(self, "_Z", None))
+                               Z=getattr(self, "_Z", None), X_train=dense)
         self.alpha_ = solver.alpha.cpu().numpy()
 
     def decision_function(self, x):

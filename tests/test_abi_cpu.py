@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol():
     build()
     lib = N.load()
     header = open(os.path.join(ROOT, "include", "b2svm.h")).read()
-    declared = set(re.findall(r"\b(b2svm_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(b2svm_[a-z0-9_]+)\s*\(", header))
     assert declared == set(N.EXPORTS), declared ^ set(N.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name

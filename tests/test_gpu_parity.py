@@ -770,3 +770,81 @@ def test_macro_tiles_generic_kernel(monkeypatch, variant):
         assert st.n_iter == 300
         out.append((sol.alpha.cpu().numpy().copy(), sol.neg_y_grad.cpu().numpy().copy()))
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+# ------------------------------------------------------------------------------ dense kernel matrix / dense-Q mode / K8 on tensor cores
+@pytest.mark.parametrize("kind", ["rbf", "linear", "poly", "sigmoid"])
+@pytest.mark.parametrize("na,nb,d,dtype", [(70, 130, 30, np.float64), (1500, 1100, 64, np.float32), (2000, 2000, 33, np.float32),
+                                           (300, 40, 100, np.float32)])
+def test_kernel_matrix_matches_oracle(kind, na, nb, d, dtype):
+    """b2svm_kernel_matrix against the oracle's kernel_func (svc.py:230-241): float64 to 1e-12; float32 on the FMA
+    kernel to float32 rounding, on the tensor cores (>= 1024 rows, d <= 96: 3xTF32) to ~1e-6 of the value scale."""
+    torch, _, S, *_ = _mods()
+    rng = np.random.default_rng(na + d)
+    A = rng.standard_normal((na, d)).astype(dtype)
+    B = rng.standard_normal((nb, d)).astype(dtype)
+    spec = O.KernelSpec(kind=kind, gamma=0.5 / d, coef0=0.3, degree=3)
+    want = O.make_kernel(spec)(A.astype(np.float64), B.astype(np.float64))
+    dev = torch.device("cuda")
+    got = S.kernel_matrix(S.KernelSpec(kind, spec.gamma, spec.coef0, spec.degree), torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev))
+    assert got.shape == (na, nb) and got.dtype == (torch.float64 if dtype == np.float64 else torch.float32)
+    tol = 1e-12 if dtype == np.float64 else 3e-6
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=tol, atol=tol * max(1.0, np.abs(want).max()))
+
+
+def test_dense_q_mode_of_the_estimators(breast_cancer, golden):
+    """cache_size=0 is the reference's dense-Q mode (svc.py:251-253): the kernel matrix is built once, on the device,
+    and the solve reads its columns; the fit must equal the column-mode fit and the reference's golden vectors."""
+    *_, svc, svr, oc = _mods()
+    X, y = breast_cancer
+    g = golden("g1_breast_cancer_csvc")
+    dense = svc.BiKernelSVC(max_iter=10 ** 6, cache_size=0).fit(X, y)
+    cols = svc.BiKernelSVC(max_iter=10 ** 6).fit(X, y)
+    iters_close(dense.n_iter_, int(g["n_iter"]))
+    np.testing.assert_array_equal(dense.support_, np.flatnonzero(g["alpha"] > 0))
+    rel_close(dense.alpha_, g["alpha"])
+    rel_close(dense.decision_function(X), g["dec"])
+    rel_close(dense.alpha_, cols.alpha_, atol=1e-9)
+    # float32 rows large enough for the tensor-core Gram kernel (3xTF32: kernel values to ~1e-6)
+    Xs, ys = O.synth_classification(n=3000, d=64, seed=5)
+    ref = O.fit_csvc(Xs, ys, max_iter=10 ** 6)
+    est = svc.BiKernelSVC(max_iter=10 ** 6, cache_size=0).fit(Xs, ys)
+    iters_close(est.n_iter_, ref.n_iter, frac=0.02)
+    np.testing.assert_array_equal(est.support_, np.flatnonzero(ref.alpha > 0))
+    rel_close(est.alpha_, ref.alpha, atol=2e-4)
+    np.testing.assert_array_equal(est.predict(Xs), ref.predict(Xs))
+
+
+@pytest.mark.parametrize("n,d,D,out", [(5000, 32, 512, "f64"), (3000, 20, 1000, "f64"), (4096, 32, 4096, "f32"), (1100, 64, 130, "f64")])
+def test_rff_transform_on_tensor_cores(n, d, D, out):
+    """NormalRFF.transform for float32 X (configs[4]: d = 32, D = 4096) as a tcgen05 GEMM + cos epilogue + TMA stores.
+    Against rff.py:19-20 evaluated in float64: the cosine argument carries the 3xTF32 error (~1e-6), so the features
+    agree to 8e-6 of their scale sqrt(2/D) -- stated, not bit parity; float64 X stays on the exact kernel (test_rff_vectors)."""
+    torch, *_ = _mods()
+    from pysvm_b200.rff import NormalRFF
+    rng = np.random.default_rng(n + D)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    np.random.seed(1)
+    r = NormalRFF(gamma=1.0 / d, D=D).fit(X[:1])
+    want = np.sqrt(2 / D) * np.cos(X.astype(np.float64) @ r.w.T + r.b)
+    Z = r.transform_device(torch.from_numpy(X).cuda(), dtype=torch.float32 if out == "f32" else torch.float64)
+    assert Z.shape == (n, D) and Z.dtype == (torch.float32 if out == "f32" else torch.float64)
+    np.testing.assert_allclose(Z.cpu().numpy().astype(np.float64), want, rtol=0, atol=8e-6 * np.sqrt(2 / D) + (1e-7 if out == "f32" else 0))
+    # and the float64 CUDA-core kernel on the same float32 input is exact
+    import os
+    os.environ["B2SVM_RFF_TC"] = "0"
+    try:
+        Ze = r.transform_device(torch.from_numpy(X).cuda())
+    finally:
+        del os.environ["B2SVM_RFF_TC"]
+    np.testing.assert_allclose(Ze.cpu().numpy(), want, rtol=0, atol=1e-13)
+
+
+def test_weighted_rows_is_x_transposed_times_w():
+    torch, _, S, *_ = _mods()
+    rng = np.random.default_rng(9)
+    for n, d, dtype in ((1000, 7, np.float64), (50000, 130, np.float32), (3, 1000, np.float64)):
+        X = rng.standard_normal((n, d)).astype(dtype)
+        w = rng.standard_normal(n)
+        got = S.weighted_rows(torch.from_numpy(X).cuda(), torch.from_numpy(w).cuda()).cpu().numpy()
+        np.testing.assert_allclose(got, X.astype(np.float64).T @ w, rtol=1e-12, atol=1e-10)
