@@ -129,6 +129,12 @@ int b2svm_init_gradient(b2svm_handle* h, const double* p);
  * according to the handle's variant.  (-1,-1) = stop. */
 int b2svm_select(b2svm_handle* h, int64_t* i, int64_t* j);
 
+/* OPT-IN, not the reference's rule: second-order working-set selection (LIBSVM WSS 3, Fan / Chen / Lin 2005):
+ * i = argmax_{I_up} g, j = argmin_{t in I_low, g_t < g_i} -(g_i - g_t)^2 / (K_ii + K_tt - 2 K_it); the stopping test is
+ * the reference's (g_i - min_{I_low} g < tol -> (-1,-1)).  C variant, single GPU; one extra sweep of X per call.
+ * Pair it with b2svm_update; iteration counts differ from the reference's (typically 2-3x fewer). */
+int b2svm_select_wss3(b2svm_handle* h, int64_t* i, int64_t* j);
+
 /* Solver.update (solver.py:77-147) / NuSolver.update (solver.py:341-376): analytic two-variable
  * step with box clipping + rank-2 gradient update.  Returns (delta_i, delta_j). */
 int b2svm_update(b2svm_handle* h, int64_t i, int64_t j, double* delta_i, double* delta_j);

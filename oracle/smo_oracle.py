@@ -214,6 +214,30 @@ def select_pair(st: DualState) -> Tuple[int, int]:
     return i, j
 
 
+def select_pair_wss3(st: DualState, columns, kdiag: np.ndarray) -> Tuple[int, int]:
+    """OPT-IN rule, NOT in the reference (its Solver takes the maximal violating pair, solver.py:47-75): LIBSVM's
+    second-order working-set selection WSS 3 (Fan, Chen, Lin, JMLR 6, 2005, Algorithm 2; libsvm svm.cpp
+    Solver::select_working_set), restated on the reference's quantities: g = neg_y_grad, I_up / I_low as in
+    solver.py:55-64.  i = argmax_{I_up} g; j = argmin_{t in I_low, g_t < g_i} -(g_i - g_t)^2 / a_it with
+    a_it = K_ii + K_tt - 2 K_it (<= 0 -> 1e-12); stop like solver.py:72-75.  Ties: the lower index.
+    ``columns(i)`` is the Q column (y_t y_i K_ti); ``kdiag`` the kernel diagonal per variable."""
+    up, low, _, _ = _masks(st)
+    if not up.any() or not low.any():
+        return -1, -1
+    i = _first_argmax(st.g, up)
+    j0 = _first_argmin(st.g, low)
+    if st.g[i] - st.g[j0] < st.tol:
+        return -1, -1
+    K_i = columns(i) * st.y * st.y[i]                     # K(x_t, x_i) for every variable t
+    a = (kdiag[i] + kdiag) - 2.0 * K_i
+    a = np.where(a <= 0, 1e-12, a)
+    b = st.g[i] - st.g
+    cand = low & (st.g < st.g[i])
+    gain = np.where(cand, -(b * b) / a, np.inf)
+    j = int(np.argmin(gain))                              # first minimum = lower index
+    return (int(i), j) if cand.any() else (-1, -1)
+
+
 def _clip_equal_sign(st: DualState, i: int, j: int, delta: float):
     """The y_i*y_j == +1 box clipping, in the reference's order (solver.py:120-142, 349-371)."""
     a, C = st.alpha, st.C

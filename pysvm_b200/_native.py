@@ -19,7 +19,7 @@ EXPORTS = [
     "b2svm_init_gradient", "b2svm_select", "b2svm_update", "b2svm_kernel_column", "b2svm_solve",
     "b2svm_rho", "b2svm_rho_b", "b2svm_kernel_matvec", "b2svm_rff_transform", "b2svm_rff_decision",
     "b2svm_solve_batched", "b2svm_mailbox_export", "b2svm_mailbox_attach", "b2svm_prepare", "b2svm_bias_partials",
-    "b2svm_host_std", "b2svm_solve_ranks_on_one_gpu", "b2svm_rff_transform_f32", "b2svm_kernel_matrix", "b2svm_weighted_rows",
+    "b2svm_host_std", "b2svm_solve_ranks_on_one_gpu", "b2svm_rff_transform_f32", "b2svm_kernel_matrix", "b2svm_weighted_rows", "b2svm_select_wss3",
 ]
 
 
@@ -82,6 +82,7 @@ def load():
     lib.b2svm_init_state.argtypes = [vp, vp]
     lib.b2svm_init_gradient.argtypes = [vp, vp]
     lib.b2svm_select.argtypes = [vp, P(i64), P(i64)]
+    lib.b2svm_select_wss3.argtypes = [vp, P(i64), P(i64)]
     lib.b2svm_update.argtypes = [vp, i64, i64, P(dbl), P(dbl)]
     lib.b2svm_kernel_column.argtypes = [vp, i64, vp]
     lib.b2svm_solve.argtypes = [vp, i64, P(SolveStats)]

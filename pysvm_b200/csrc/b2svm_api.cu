@@ -138,6 +138,133 @@ __global__ void dense_matvec_kernel(const T* __restrict__ K, const double* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Opt-in second-order working-set selection (LIBSVM's WSS 3; Fan, Chen, Lin, JMLR 2005, Algorithm 2).  NOT what the
+// reference's Solver does (it takes the maximal violating pair, solver.py:47-75); BASELINE.json's north_star names it,
+// so it is offered as an opt-in with its own iteration count:
+//   i = argmax_{t in I_up} g_t;  j = argmin_{t in I_low, g_t < g_i} -(g_i - g_t)^2 / a_it,
+//   a_it = K_ii + K_tt - 2 K_it (<= 0 -> 1e-12); stop when g_i - min_{I_low} g < tol.  Ties go to the lower index.
+// Two block-parallel passes per iteration (the second evaluates K(x_i, .), i.e. one extra sweep of X).
+// ------------------------------------------------------------------------------------------
+struct WssRec {
+  double v;
+  long long idx;
+};
+__device__ __forceinline__ bool wss_less(const WssRec& a, const WssRec& b) {   // a strictly better for a MIN search
+  return a.idx >= 0 && (b.idx < 0 || a.v < b.v || (a.v == b.v && a.idx < b.idx));
+}
+__device__ __forceinline__ WssRec wss_block_min(WssRec r, WssRec* sh) {
+  for (int m = 16; m >= 1; m >>= 1) {
+    WssRec o;
+    o.v = __shfl_down_sync(0xffffffffu, r.v, m);
+    o.idx = __shfl_down_sync(0xffffffffu, r.idx, m);
+    if (wss_less(o, r)) r = o;
+  }
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = r;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : WssRec{0.0, -1};
+    for (int m = 16; m >= 1; m >>= 1) {
+      WssRec o;
+      o.v = __shfl_down_sync(0xffffffffu, r.v, m);
+      o.idx = __shfl_down_sync(0xffffffffu, r.idx, m);
+      if (wss_less(o, r)) r = o;
+    }
+  }
+  return r;   // valid in thread 0
+}
+
+// pass 1: per block, arg-max of g over I_up (as a min of -g) and min of g over I_low
+__global__ void __launch_bounds__(256) wss3_first_kernel(const double* __restrict__ G, const uint8_t* __restrict__ flags, int64_t nv,
+                                                         WssRec* __restrict__ pmax, WssRec* __restrict__ pmin) {
+  __shared__ WssRec sh[8];
+  WssRec up{0.0, -1}, low{0.0, -1};
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nv; v += (int64_t)gridDim.x * blockDim.x) {
+    const int f = flags[v];
+    const double g = G[v];
+    if (in_up(f)) { WssRec c{-g, v}; if (wss_less(c, up)) up = c; }
+    if (in_low(f)) { WssRec c{g, v}; if (wss_less(c, low)) low = c; }
+  }
+  up = wss_block_min(up, sh);
+  if (threadIdx.x == 0) pmax[blockIdx.x] = up;
+  __syncthreads();
+  low = wss_block_min(low, sh);
+  if (threadIdx.x == 0) pmin[blockIdx.x] = low;
+}
+
+// out[0] = i (or -1), out[1] = g_i, out[2] = min over I_low of g (as doubles), from the per-block partials
+__global__ void wss3_reduce_first_kernel(const WssRec* __restrict__ pmax, const WssRec* __restrict__ pmin, int nb, double* __restrict__ out) {
+  __shared__ WssRec sh[8];
+  WssRec a{0.0, -1}, b{0.0, -1};
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    if (wss_less(pmax[k], a)) a = pmax[k];
+    if (wss_less(pmin[k], b)) b = pmin[k];
+  }
+  a = wss_block_min(a, sh);
+  __syncthreads();
+  WssRec a0 = a;
+  b = wss_block_min(b, sh);
+  if (threadIdx.x == 0) {
+    out[0] = (double)a0.idx;
+    out[1] = -a0.v;
+    out[2] = b.idx >= 0 ? b.v : 0.0;
+    out[3] = (double)b.idx;
+  }
+}
+
+// pass 2: one warp per row r: K(x_r, x_i), then the second-order gain of the row's variables; per-block arg-min
+template <typename T>
+__global__ void __launch_bounds__(256) wss3_second_kernel(const T* __restrict__ X, const T* __restrict__ norms, const T* __restrict__ kdiag,
+                                                          const T* __restrict__ Kpre, const double* __restrict__ G,
+                                                          const uint8_t* __restrict__ flags, int64_t l, int64_t nv, int dp,
+                                                          KernelParams<T> kp, const double* __restrict__ first, WssRec* __restrict__ pgain) {
+  __shared__ WssRec sh[8];
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t i = (int64_t)first[0];
+  const double gi = first[1];
+  WssRec best{0.0, -1};
+  if (i >= 0) {
+    const int64_t ri = i >= l ? i - l : i;
+    const double kii = (double)kdiag[ri];
+    for (int64_t r = warp; r < l; r += nwarps) {
+      T k;
+      if (Kpre) {
+        k = Kpre[r * l + ri];
+      } else {
+        T s = 0;
+        for (int c = lane; c < dp; c += 32) s = fma(X[r * dp + c], X[ri * dp + c], s);
+        s = warp_sum(s);
+        k = kernel_value(kp, s, norms[r], norms[ri]);
+      }
+      if (lane == 0) {
+        double a = (kii + (double)kdiag[r]) - 2.0 * (double)k;
+        if (a <= 0) a = 1e-12;
+        for (int64_t v = r; v < nv; v += l) {
+          const double g = G[v];
+          if (in_low((int)flags[v]) && g < gi) {
+            const double b = gi - g;
+            WssRec c{-(b * b) / a, v};
+            if (wss_less(c, best)) best = c;
+          }
+        }
+      }
+    }
+  }
+  best = wss_block_min(best, sh);
+  if (threadIdx.x == 0) pgain[blockIdx.x] = best;
+}
+
+__global__ void wss3_reduce_second_kernel(const WssRec* __restrict__ pgain, int nb, double* __restrict__ out) {
+  __shared__ WssRec sh[8];
+  WssRec a{0.0, -1};
+  for (int k = threadIdx.x; k < nb; k += blockDim.x)
+    if (wss_less(pgain[k], a)) a = pgain[k];
+  a = wss_block_min(a, sh);
+  if (threadIdx.x == 0) out[4] = (double)a.idx;
+}
+
 __global__ void iota_kernel(int* __restrict__ a, int64_t n) {
   for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) a[v] = (int)v;
 }
@@ -253,6 +380,7 @@ struct b2svm_handle {
   BiasStats* bias_dev = nullptr;
   double* scratch = nullptr;    // [2 * n_rows] row weights + mat-vec result
   double* p_dev = nullptr;      // staging for host-side p
+  unsigned char* wss_buf = nullptr;   // scratch of b2svm_select_wss3
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int num_sms = 0;
   int ncta = 1, tiles_per_cta = 1, stages = 2, sub = 1, stages1 = 2, tile_bytes = 0;
@@ -700,6 +828,7 @@ int b2svm_destroy(b2svm_handle* h) {
   pool_free(h->bias_dev, h->stream);
   pool_free(h->scratch, h->stream);
   pool_free(h->p_dev, h->stream);
+  pool_free(h->wss_buf, h->stream);
   cudaFree(h->timeline);
   cudaFree(h->dbg_steps);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -772,6 +901,47 @@ int b2svm_update(b2svm_handle* h, int64_t i, int64_t j, double* delta_i, double*
   if (rc) return rc;
   if (delta_i) *delta_i = r.di;
   if (delta_j) *delta_j = r.dj;
+  return B2SVM_OK;
+}
+
+int b2svm_select_wss3(b2svm_handle* h, int64_t* i, int64_t* j) {
+  if (!h || !i || !j) return fail(B2SVM_E_INVALID, "null argument");
+  if (h->d.world > 1) return fail(B2SVM_E_UNSUPPORTED, "second-order selection is single-GPU only");
+  if (h->d.variant != B2SVM_SOLVER_C) return fail(B2SVM_E_UNSUPPORTED, "second-order selection is offered for the C variant (Solver) only");
+  B2_CUDA(cudaSetDevice(h->d.device));
+  const int64_t l = h->d.n_rows, nv = h->d.n_vars;
+  const int nb = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 4, (l * 32 + 255) / 256));
+  // scratch: [nb] max partials, [nb] min partials, [nb] gain partials, 8 doubles of results
+  const size_t need = sizeof(WssRec) * 3 * (size_t)nb + 64;
+  if (!h->wss_buf) B2_CUDA(pool_alloc(&h->wss_buf, sizeof(WssRec) * 3 * 148 * 4 + 64, h->stream));
+  (void)need;
+  WssRec* pmax = reinterpret_cast<WssRec*>(h->wss_buf);
+  WssRec* pmin = pmax + nb;
+  WssRec* pgain = pmin + nb;
+  double* res = reinterpret_cast<double*>(pgain + nb);
+  refresh_flags_kernel<<<grid_for(nv), 256, 0, h->stream>>>(h->d.y, h->d.alpha, h->d.C, h->flags, nv);
+  wss3_first_kernel<<<nb, 256, 0, h->stream>>>(h->d.neg_y_grad, h->flags, nv, pmax, pmin);
+  wss3_reduce_first_kernel<<<1, 256, 0, h->stream>>>(pmax, pmin, nb, res);
+  if (h->f64) {
+    KernelParams<double> kp{h->d.kernel.kind, h->d.kernel.gamma, h->d.kernel.coef0, h->d.kernel.degree};
+    wss3_second_kernel<double><<<nb, 256, 0, h->stream>>>((const double*)h->Xuse, (const double*)h->norms, (const double*)h->kdiag,
+                                                         h->precomputed ? (const double*)h->Xuse : nullptr, h->d.neg_y_grad, h->flags, l, nv,
+                                                         h->dp, kp, res, pgain);
+  } else {
+    KernelParams<float> kp{h->d.kernel.kind, (float)h->d.kernel.gamma, (float)h->d.kernel.coef0, (float)h->d.kernel.degree};
+    wss3_second_kernel<float><<<nb, 256, 0, h->stream>>>((const float*)h->Xuse, (const float*)h->norms, (const float*)h->kdiag,
+                                                        h->precomputed ? (const float*)h->Xuse : nullptr, h->d.neg_y_grad, h->flags, l, nv,
+                                                        h->dp, kp, res, pgain);
+  }
+  wss3_reduce_second_kernel<<<1, 256, 0, h->stream>>>(pgain, nb, res);
+  B2_CUDA(cudaGetLastError());
+  double host[5];
+  B2_CUDA(cudaMemcpyAsync(host, res, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+  B2_CUDA(cudaStreamSynchronize(h->stream));
+  const int64_t si = (int64_t)host[0], low_any = (int64_t)host[3], sj = (int64_t)host[4];
+  // stopping rule of the reference (solver.py:72-75) with the same two extremes: m(alpha) - M(alpha) < tol
+  if (si < 0 || low_any < 0 || host[1] - host[2] < h->d.tol || sj < 0) { *i = -1; *j = -1; }
+  else { *i = si; *j = sj; }
   return B2SVM_OK;
 }
 

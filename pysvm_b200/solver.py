@@ -188,6 +188,11 @@ class _Engine:
         N.check(self.lib.b2svm_select(self.h, C.byref(i), C.byref(j)))
         return int(i.value), int(j.value)
 
+    def select_wss3(self):
+        i, j = C.c_int64(), C.c_int64()
+        N.check(self.lib.b2svm_select_wss3(self.h, C.byref(i), C.byref(j)))
+        return int(i.value), int(j.value)
+
     def update(self, i: int, j: int):
         di, dj = C.c_double(), C.c_double()
         N.check(self.lib.b2svm_update(self.h, int(i), int(j), C.byref(di), C.byref(dj)))
@@ -338,6 +343,10 @@ class Solver:
         """solver.py:47-75."""
         return self._need().select()
 
+    def working_set_select_wss3(self):
+        """OPT-IN, not in the reference: LIBSVM's second-order rule (WSS 3).  Same stopping test as ``working_set_select``."""
+        return self._need().select_wss3()
+
     def update(self, i: int, j: int, func=None):
         """solver.py:77-147."""
         return self._need(func).update(i, j)
@@ -351,10 +360,33 @@ class Solver:
         return self._need(func).column(i)
 
     # -- fused driver loop ----------------------------------------------------------------------------
-    def solve(self, max_iter: int, func=None) -> N.SolveStats:
+    def solve(self, max_iter: int, func=None, wss: str = "mvp") -> N.SolveStats:
         """The estimator loop ``for n_iter in range(max_iter): select; break if i < 0; update``
-        (svc.py:260-267) on the device.  ``stats.n_iter`` = number of updates made."""
-        st = self._need(func).solve(max_iter)
+        (svc.py:260-267) on the device.  ``stats.n_iter`` = number of updates made.
+
+        ``wss="mvp"`` (default) is the reference's maximal-violating-pair rule, fused into one persistent kernel.
+        ``wss="wss3"`` opts into LIBSVM's second-order selection: a host-driven loop of ``b2svm_select_wss3`` +
+        ``b2svm_update`` (several launches per iteration) that reaches the same optimum in fewer, differently counted
+        iterations -- parity with the reference's iteration counts does not apply to it."""
+        eng = self._need(func)
+        if wss == "mvp":
+            st = eng.solve(max_iter)
+        elif wss == "wss3":
+            st = N.SolveStats()
+            n = 0
+            nxt = (-1, -1)
+            while n < int(max_iter):
+                nxt = eng.select_wss3()
+                if nxt[0] < 0:
+                    st.converged = 1
+                    break
+                st.last_delta_i, st.last_delta_j = eng.update(*nxt)
+                n += 1
+            st.n_iter, st.n_ctas = n, 0
+            st.last_i, st.last_j = nxt if n >= int(max_iter) else (-1, -1)
+            st.cold_sweeps, st.launches = 2 * n, 8 * n
+        else:
+            raise ValueError("wss must be 'mvp' (the reference's rule) or 'wss3'")
         self.last_stats = st
         return st
 

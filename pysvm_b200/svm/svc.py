@@ -184,8 +184,11 @@ class BiKernelSVC(BiLinearSVC):
 
     def __init__(self, C: float = 1., kernel: str = 'rbf', degree: float = 3, gamma: str = 'scale', coef0: float = 0,
                  max_iter: int = 1000, rff: bool = False, D: int = 1000, tol: float = 1e-5,
-                 cache_size: int = 256) -> None:
+                 cache_size: int = 256, wss: str = "mvp") -> None:
+        """``wss`` is an additive, opt-in keyword (not in the reference): "mvp" = the reference's maximal violating
+        pair (default, parity path); "wss3" = LIBSVM's second-order working-set selection."""
         super().__init__(C, max_iter, tol, cache_size)
+        self.wss = wss
         self.kernel = kernel
         self.gamma = gamma
         self.degree = degree
@@ -258,10 +261,11 @@ class BiKernelSVC(BiLinearSVC):
             self._report(stats)
             self._finish(solver, func, spec, rff, X, solver.alpha * func.y)
 
-        if _PENDING is not None and l <= BATCH_MAX_ROWS:
+        wss = getattr(self, "wss", "mvp")
+        if _PENDING is not None and l <= BATCH_MAX_ROWS and wss == "mvp":
             _PENDING.append((self, solver, finish))       # solved together with its sibling sub-problems
         else:
-            finish(solver.solve(self.max_iter))
+            finish(solver.solve(self.max_iter, wss=wss))
         return self
 
     def _finish(self, solver, func, spec, rff, X, coef):

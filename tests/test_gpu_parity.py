@@ -848,3 +848,33 @@ def test_weighted_rows_is_x_transposed_times_w():
         w = rng.standard_normal(n)
         got = S.weighted_rows(torch.from_numpy(X).cuda(), torch.from_numpy(w).cuda()).cpu().numpy()
         np.testing.assert_allclose(got, X.astype(np.float64).T @ w, rtol=1e-12, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------ opt-in second-order selection (WSS 3)
+def test_wss3_opt_in_pairs_and_optimum(breast_cancer):
+    """wss="wss3" is an opt-in (north_star names LIBSVM's second-order rule; the reference itself uses the maximal
+    violating pair).  The device selection must pick the oracle's WSS-3 pair step for step, reach the same optimum as
+    the default rule, and need fewer iterations -- which it reports as its own count."""
+    torch, _, S, svc, _, _ = _mods()
+    X, y01 = breast_cancer
+    y = np.where(y01 == 1, 1.0, -1.0)
+    n = len(y)
+    gamma = 1 / (30 * X.std())
+    spec = O.KernelSpec(kind="rbf", gamma=gamma)
+    cols = O.ColumnSource(X, y, O.make_kernel(spec), mirror=False)
+    kdiag = np.array([cols(t)[t] for t in range(n)])
+    st = O.fresh_state(-np.ones(n), y, 1.0, 1e-5)
+    solver = S.SolverWithCache(-np.ones(n), y, 1.0, func=S.QColumns(X, y, S.KernelSpec("rbf", gamma)))
+    for k in range(60):
+        i, j = O.select_pair_wss3(st, cols, kdiag)
+        assert solver.working_set_select_wss3() == (i, j), k
+        want = O.take_step(st, i, j, cols(i), cols(j))
+        np.testing.assert_allclose(solver.update(i, j), want, rtol=1e-9, atol=1e-12)
+    mvp = svc.BiKernelSVC(max_iter=10 ** 6).fit(X, y01)
+    w3 = svc.BiKernelSVC(max_iter=10 ** 6, wss="wss3").fit(X, y01)
+    assert w3.n_iter_ < mvp.n_iter_                           # 487 for the reference's rule
+    np.testing.assert_array_equal(w3.support_, mvp.support_)
+    rel_close(w3.alpha_, mvp.alpha_, atol=2e-4)
+    rel_close(w3.rho_, mvp.rho_, atol=1e-4)
+    np.testing.assert_array_equal(w3.predict(X), mvp.predict(X))
+    print("WSS3 iterations", w3.n_iter_, "vs maximal violating pair", mvp.n_iter_)
