@@ -105,6 +105,8 @@ typedef struct b2svm_solve_stats {
   double algorithmic_bytes;  /* sum over iterations of B_iter          */
   float device_ms;           /* CUDA-event time of the persistent kernel(s) of this call    */
   int32_t launches;          /* kernels launched by this call                               */
+  int64_t cache_stores;      /* Q columns written into the HBM column cache                 */
+  int64_t cache_evictions;   /* ... of which replaced an older column (FIFO, cache full)    */
 } b2svm_solve_stats;
 
 typedef struct b2svm_handle b2svm_handle;

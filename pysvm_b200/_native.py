@@ -54,6 +54,7 @@ class SolveStats(C.Structure):
         ("last_delta_i", C.c_double), ("last_delta_j", C.c_double),
         ("cold_sweeps", C.c_int64), ("cache_hits", C.c_int64), ("cache_misses", C.c_int64),
         ("algorithmic_bytes", C.c_double), ("device_ms", C.c_float), ("launches", C.c_int32),
+        ("cache_stores", C.c_int64), ("cache_evictions", C.c_int64),
     ]
 
     def as_dict(self):

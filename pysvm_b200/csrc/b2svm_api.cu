@@ -401,7 +401,8 @@ struct b2svm_handle {
   bool precomputed = false;       // kernel.kind == 4: X is the kernel matrix itself and doubles as a full cache
   void* cache = nullptr;          // Q-column cache [cache_slots][n_rows] in the input dtype
   int* slot_of = nullptr;
-  long long cache_slots = 0, cache_used = 0;
+  int* row_of_slot = nullptr;
+  long long cache_slots = 0, cache_used = 0, cache_hand = 0;
   long long* timeline = nullptr;   // debug: set by B2SVM_TIMELINE=1
   double* dbg_steps = nullptr;     // debug: set by B2SVM_DEBUG_STEPS=1
 };
@@ -573,6 +574,8 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.slot_of = h->slot_of;
   P.cache_slots = h->cache_slots;
   P.cache_used = h->cache_used;
+  P.cache_hand = h->cache_hand;
+  P.row_of_slot = h->row_of_slot;
   P.world = h->d.world > 1 ? h->d.world : 1;
   P.rank = h->d.world > 1 ? h->d.rank : 0;
   P.row_offset = h->d.world > 1 ? h->d.row_offset : 0;
@@ -628,6 +631,7 @@ int run_solver(b2svm_handle* h, long long max_iter, long long fi, long long fj, 
   h->launches = 2;
   *res = *h->result_host;
   h->cache_used = res->cache_used;
+  h->cache_hand = res->cache_hand;
   if (ms) B2_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   if (res->status != 0) return fail(B2SVM_E_TIMEOUT, "device watchdog: a grid barrier did not complete");
   return B2SVM_OK;
@@ -656,6 +660,8 @@ static void fill_stats(const b2svm_handle* h, const SolveResult& r, int n_ctas, 
       (double)r.warm_sweeps * ((double)h->d.n_vars * 18.0 + 2.0 * (double)h->d.n_rows * esz);
   stats->device_ms = ms;
   stats->launches = launches;
+  stats->cache_stores = r.cols_stored;
+  stats->cache_evictions = r.cols_evicted;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -762,13 +768,18 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
   } else if (desc->cache_bytes > 0) {
     // device-resident Q-column cache: as many whole columns (this GPU's rows) as the budget holds
     const size_t col_bytes = (size_t)l * esz;
-    long long slots = (long long)(desc->cache_bytes / col_bytes);
+    // the same number of slots on every rank of a sharded solve (slices may differ by a few rows): the replicated
+    // slot tables then take the same store / evict decisions everywhere
+    const size_t plan_col_bytes = (size_t)(desc->world > 1 ? h->rows_per_rank : l) * esz;
+    long long slots = (long long)(desc->cache_bytes / plan_col_bytes);
     const long long lglob = desc->world > 1 ? desc->n_rows_global : l;
     slots = std::min<long long>(slots, lglob);
     if (slots > 0) {
       B2_TRY(pool_alloc(&h->cache, (size_t)slots * col_bytes, h->stream));
       B2_TRY(pool_alloc(&h->slot_of, sizeof(int) * (size_t)lglob, h->stream));
       B2_TRY(cudaMemsetAsync(h->slot_of, 0xff, sizeof(int) * (size_t)lglob, h->stream));
+      B2_TRY(pool_alloc(&h->row_of_slot, sizeof(int) * (size_t)slots, h->stream));
+      B2_TRY(cudaMemsetAsync(h->row_of_slot, 0xff, sizeof(int) * (size_t)slots, h->stream));
       h->cache_slots = slots;
     }
   }
@@ -822,6 +833,7 @@ int b2svm_destroy(b2svm_handle* h) {
   pool_free(h->flags, h->stream);
   if (!h->precomputed) pool_free(h->cache, h->stream);
   pool_free(h->slot_of, h->stream);
+  pool_free(h->row_of_slot, h->stream);
   pool_free(h->abort_flag, h->stream);
   pool_free(h->result, h->stream);
   pool_free(h->prob_dev, h->stream);
@@ -1042,6 +1054,7 @@ int b2svm_solve_ranks_on_one_gpu(b2svm_handle* const* handles, int32_t world, in
     for (int r = 0; r < world; ++r) {
       const SolveResult& R = pinned_result()[r];
       handles[r]->cache_used = R.cache_used;
+      handles[r]->cache_hand = R.cache_hand;
       if (R.status != 0) rc = fail(B2SVM_E_TIMEOUT, "device watchdog tripped in an emulated sharded solve");
       if (stats) fill_stats(handles[r], R, h0->ncta, ms, 1, &stats[r]);
     }
@@ -1160,6 +1173,7 @@ int b2svm_solve_batched(b2svm_handle* const* handles, int32_t count, int64_t max
     cudaEventElapsedTime(&ms, h0->ev0, h0->ev1);
     for (int k = 0; rc == B2SVM_OK && k < count; ++k) {
       handles[k]->cache_used = R[k].cache_used;   // the device slot table persists across launches (as in run_solver)
+      handles[k]->cache_hand = R[k].cache_hand;
       if (R[k].status != 0) rc = fail(B2SVM_E_TIMEOUT, "device watchdog tripped in a batched solve");
       if (stats) {
         memset(&stats[k], 0, sizeof(stats[k]));

@@ -63,7 +63,7 @@ struct SolveResult {
   long long n_iter;
   long long last_i, last_j;
   long long cold_sweeps;
-  long long warm_sweeps, cols_stored, cache_used;
+  long long warm_sweeps, cols_stored, cache_used, cache_hand, cols_evicted;
   double di, dj;
   int converged;
   int status;   // 0 ok, 1 watchdog
@@ -100,8 +100,10 @@ struct ProblemDev {
   // ---- device-resident Q-column cache (replaces the LRU of solver.py:207,227-229) -------------------
   void* cache;                    // T [cache_slots][l]: K(x_t, x_r) for this GPU's rows t, one slot per cached row r
   int* slot_of;                   // [l_global] slot of global row r, -1 = not cached (replicated per GPU)
+  int* row_of_slot;               // [cache_slots] the row a slot holds (victim bookkeeping; replicated per GPU)
   long long cache_slots;          // 0 = cache off
   long long cache_used;           // slots already filled by earlier solves on this handle
+  long long cache_hand;           // FIFO victim pointer carried over from earlier solves
   // ---- row-sharded multi-GPU (world > 1): this GPU holds and sweeps global rows [row_offset, row_offset + l) ONLY
   // (X, norms, alpha, G, flags and cached columns are all indexed by local row)
   int world, rank;
@@ -192,8 +194,10 @@ struct LeaderState {
   double di, dj;          // last step
   int ri, rj, si, sj;     // ... its rows / cache slots (same deferral)
   int n_cached;           // cache slots handed out so far (identical in every leader)
+  int hand;               // next FIFO victim once every slot is taken
+  int ei, ej;             // rows evicted by the last step (their slot-table entries are cleared one sweep late)
   int converged;
-  long long warm_cnt, stored_cnt;
+  long long warm_cnt, stored_cnt, evict_cnt;
 };
 
 // What a type warp found for its candidate type after the exchange (read by the leader = warp 0).
@@ -215,6 +219,7 @@ struct Shared {
   int slot_i, slot_j;   // cache slots of rows i, j (-1 = none); store_* = fill the slot during this sweep
   int store_i, store_j, warm;
   int p_ri, p_rj, p_si, p_sj;   // previous pair's rows / slots: slot_of[] is updated one sweep late, like alpha
+  int p_ei, p_ej;               // ... and the rows that step evicted
   int stop;
   volatile int producer_stop;
   volatile long long consumed;
@@ -339,8 +344,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     L0.di = L0.dj = 0.0;
     L0.ri = L0.rj = L0.si = L0.sj = -1;
     L0.n_cached = (int)P.cache_used;
+    L0.hand = (int)P.cache_hand;
+    L0.ei = L0.ej = -1;
     L0.converged = 0;
-    L0.warm_cnt = L0.stored_cnt = 0;
+    L0.warm_cnt = L0.stored_cnt = L0.evict_cnt = 0;
     sh->leader = L0;
   }
   __syncthreads();
@@ -952,9 +959,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
               r.warm_sweeps = L.warm_cnt;
               r.cols_stored = L.stored_cnt;
               r.cache_used = L.n_cached;
+              r.cache_hand = L.hand;
+              r.cols_evicted = L.evict_cnt;
               if (CACHE && P.cache_slots > 0 && L.ri >= 0) {   // pending slot-table entries of the last step
-                if (L.si >= 0) P.slot_of[L.ri] = L.si;
-                if (L.sj >= 0) P.slot_of[L.rj] = L.sj;
+                if (L.ei >= 0) P.slot_of[L.ei] = -1;
+                if (L.ej >= 0) P.slot_of[L.ej] = -1;
+                if (L.si >= 0) { P.slot_of[L.ri] = L.si; if (P.row_of_slot) P.row_of_slot[L.si] = L.ri; }
+                if (L.sj >= 0) { P.slot_of[L.rj] = L.sj; if (P.row_of_slot) P.row_of_slot[L.sj] = L.rj; }
               }
               r.di = L.di;
               r.dj = L.dj;
@@ -975,20 +986,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           stamp(11);
           // ---- Q-column cache: which of the two columns are already resident, which get stored now --------
           const int gri = (int)((mirror && si >= lg) ? si - lg : si), grj = (int)((mirror && sj >= lg) ? sj - lg : sj);
-          int slot_i = -1, slot_j = -1, store_i = 0, store_j = 0;
+          int slot_i = -1, slot_j = -1, store_i = 0, store_j = 0, ev_i = -1, ev_j = -1;
           if (CACHE && P.cache_slots > 0) {
-            slot_i = gri == L.ri ? L.si : (gri == L.rj ? L.sj : SI.raw_slot);
-            slot_j = grj == L.ri ? L.si : (grj == L.rj ? L.sj : SJ.raw_slot);
-            if (slot_i < 0 && L.n_cached < P.cache_slots) { slot_i = L.n_cached++; store_i = 1; }
+            // a row evicted by the previous step still shows its old slot in the (one sweep late) table
+            const int raw_i = (gri == L.ei || gri == L.ej) ? -1 : SI.raw_slot;
+            const int raw_j = (grj == L.ei || grj == L.ej) ? -1 : SJ.raw_slot;
+            slot_i = gri == L.ri ? L.si : (gri == L.rj ? L.sj : raw_i);
+            slot_j = grj == L.ri ? L.si : (grj == L.rj ? L.sj : raw_j);
+            // a free slot while there are any; afterwards the oldest column that neither this nor the previous pair
+            // uses is replaced (FIFO: the reference's LRU, solver.py:207,227-229, evicts too -- a cache that only ever
+            // filled would stop adapting once full).  Every leader of every GPU takes the same decision.
+            auto take_slot = [&](int avoid, int& evicted_row) -> int {
+              if (L.n_cached < P.cache_slots) return L.n_cached++;
+              if (P.cache_slots < 256 || P.kind == K_PRECOMPUTED) return -1;   // (a handful of slots would only thrash: they stay fill-only)
+              for (int t = 0; t < 6; ++t) {
+                const int v = L.hand;
+                L.hand = (v + 1 == (int)P.cache_slots) ? 0 : v + 1;
+                if (v == avoid || v == L.si || v == L.sj) continue;
+                evicted_row = __ldcg(P.row_of_slot + v);
+                ++L.evict_cnt;
+                return v;
+              }
+              return -1;
+            };
+            if (slot_i < 0) { slot_i = take_slot(slot_j, ev_i); store_i = slot_i >= 0 ? 1 : 0; }
             if (grj == gri) { slot_j = slot_i; }
-            else if (slot_j < 0 && L.n_cached < P.cache_slots) { slot_j = L.n_cached++; store_j = 1; }
+            else if (slot_j < 0) { slot_j = take_slot(slot_i, ev_j); store_j = slot_j >= 0 ? 1 : 0; }
           }
           const int warm = (CACHE && P.cache_slots > 0 && slot_i >= 0 && slot_j >= 0 && !store_i && !store_j) ? 1 : 0;
           if (lane == 0) {
             sh->slot_i = slot_i; sh->slot_j = slot_j; sh->store_i = store_i; sh->store_j = store_j; sh->warm = warm;
             sh->p_ri = L.ri; sh->p_rj = L.rj; sh->p_si = L.si; sh->p_sj = L.sj;
+            sh->p_ei = L.ei; sh->p_ej = L.ej;
           }
           L.ri = gri; L.rj = grj; L.si = slot_i; L.sj = slot_j;
+          L.ei = ev_i; L.ej = ev_j;
           if (warm) ++L.warm_cnt;
           L.stored_cnt += store_i + store_j;
           L.di = so.di; L.dj = so.dj;
@@ -1086,8 +1118,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     cache_j = col_j;
     if (CACHE && P.cache_slots > 0 && cta == 0 && warp == NW - 1 && lane == 0 && sh->p_ri >= 0) {
       // the previous step's slot-table entries, one sweep late (a slow leader may still have been reading them)
-      if (sh->p_si >= 0) P.slot_of[sh->p_ri] = sh->p_si;
-      if (sh->p_sj >= 0) P.slot_of[sh->p_rj] = sh->p_sj;
+      if (sh->p_ei >= 0) P.slot_of[sh->p_ei] = -1;
+      if (sh->p_ej >= 0) P.slot_of[sh->p_ej] = -1;
+      if (sh->p_si >= 0) { P.slot_of[sh->p_ri] = sh->p_si; if (P.row_of_slot) P.row_of_slot[sh->p_si] = sh->p_ri; }
+      if (sh->p_sj >= 0) { P.slot_of[sh->p_rj] = sh->p_sj; if (P.row_of_slot) P.row_of_slot[sh->p_sj] = sh->p_rj; }
       __threadfence();
     }
     if (warm) {   // the first tile's state was prefetched before this sweep's plan was known

@@ -28,7 +28,7 @@ def test_struct_layouts_match_header_sizes():
     from pysvm_b200 import _native as N
     assert ctypes.sizeof(N.KernelDesc) == 32
     assert ctypes.sizeof(N.ProblemDesc) == 176
-    assert ctypes.sizeof(N.SolveStats) == 88
+    assert ctypes.sizeof(N.SolveStats) == 104
 
 
 def test_errors_are_reported_not_swallowed():

@@ -878,3 +878,33 @@ def test_wss3_opt_in_pairs_and_optimum(breast_cancer):
     rel_close(w3.rho_, mvp.rho_, atol=1e-4)
     np.testing.assert_array_equal(w3.predict(X), mvp.predict(X))
     print("WSS3 iterations", w3.n_iter_, "vs maximal violating pair", mvp.n_iter_)
+
+
+def test_column_cache_evicts_and_stays_transparent():
+    """A cache far smaller than the set of columns the solve touches: once full, the oldest column is replaced (the
+    reference's LRU evicts too, solver.py:207,227-229).  Results stay bit-identical to the cache-less solve, later hits
+    exist that a fill-only cache could not have (columns first seen after the cache was full), and a second fit on the
+    same handle starts from the adapted cache."""
+    torch, _, S, *_ = _mods()
+    X, y01 = O.synth_classification(n=6000, d=128, seed=2)
+    y = np.where(y01 == 1, 1.0, -1.0)
+    spec = S.KernelSpec("rbf", 1 / (128 * X.std()))
+    off = S.SolverWithCache(-np.ones(len(y)), y, 1.0, func=S.QColumns(X, y, spec, cache_bytes=0))
+    s0 = off.solve(10 ** 6)
+    slots = 600
+    small = S.SolverWithCache(-np.ones(len(y)), y, 1.0, func=S.QColumns(X, y, spec, cache_bytes=slots * 6000 * 4))
+    s1 = small.solve(10 ** 6)
+    assert s1.n_iter == s0.n_iter
+    assert torch.equal(off.alpha, small.alpha) and torch.equal(off.neg_y_grad, small.neg_y_grad)
+    assert s1.cache_stores > slots and s1.cache_evictions == s1.cache_stores - slots     # the full cache kept replacing
+    assert s1.cache_hits > 0
+    small._engine.init_state(small.p)
+    s2 = small.solve(10 ** 6)
+    assert s2.n_iter == s0.n_iter and torch.equal(off.alpha, small.alpha)
+    # two emulated ranks keep their replicated slot tables in step while evicting
+    from pysvm_b200 import sharded as SH
+    ranks = SH.EmulatedRanks(X, y, -np.ones(len(y)), 1.0, 1e-5, spec, 2, cache_bytes=slots * 3008 * 4)
+    st = ranks.solve(10 ** 6)
+    assert all(t.n_iter == s0.n_iter for t in st) and st[0].cache_hits == st[1].cache_hits > 0
+    assert st[0].cache_evictions == st[1].cache_evictions > 0
+    np.testing.assert_array_equal(ranks.gather("alpha"), off.alpha.cpu().numpy())
