@@ -402,6 +402,7 @@ struct b2svm_handle {
   void* cache = nullptr;          // Q-column cache [cache_slots][n_rows] in the input dtype
   int* slot_of = nullptr;
   int* row_of_slot = nullptr;
+  bool cache_pooled = true;
   long long cache_slots = 0, cache_used = 0, cache_hand = 0;
   long long* timeline = nullptr;   // debug: set by B2SVM_TIMELINE=1
   double* dbg_steps = nullptr;     // debug: set by B2SVM_DEBUG_STEPS=1
@@ -775,7 +776,11 @@ int b2svm_create(const b2svm_problem_desc* desc, b2svm_handle** out) {
     const long long lglob = desc->world > 1 ? desc->n_rows_global : l;
     slots = std::min<long long>(slots, lglob);
     if (slots > 0) {
-      B2_TRY(pool_alloc(&h->cache, (size_t)slots * col_bytes, h->stream));
+      // (a multi-GB cache stays out of the pool: freed into it, the pool would trim back to its release threshold at the
+      // next synchronisation -- hundreds of ms of unmapping inside somebody else's timed region)
+      h->cache_pooled = (size_t)slots * col_bytes <= ((size_t)1 << 30);
+      if (h->cache_pooled) B2_TRY(pool_alloc(&h->cache, (size_t)slots * col_bytes, h->stream));
+      else B2_TRY(cudaMalloc(&h->cache, (size_t)slots * col_bytes));
       B2_TRY(pool_alloc(&h->slot_of, sizeof(int) * (size_t)lglob, h->stream));
       B2_TRY(cudaMemsetAsync(h->slot_of, 0xff, sizeof(int) * (size_t)lglob, h->stream));
       B2_TRY(pool_alloc(&h->row_of_slot, sizeof(int) * (size_t)slots, h->stream));
@@ -831,7 +836,7 @@ int b2svm_destroy(b2svm_handle* h) {
   cudaFree(h->block);
   pool_free(h->l1, h->stream);
   pool_free(h->flags, h->stream);
-  if (!h->precomputed) pool_free(h->cache, h->stream);
+  if (!h->precomputed) { if (h->cache_pooled) pool_free(h->cache, h->stream); else cudaFree(h->cache); }
   pool_free(h->slot_of, h->stream);
   pool_free(h->row_of_slot, h->stream);
   pool_free(h->abort_flag, h->stream);

@@ -195,16 +195,20 @@ __device__ __forceinline__ double accum32(const TcParams& p, const uint32_t (&v)
   return (double)((s0 + s1) + (s2 + s3));
 }
 
-template <int KIND>
+// MT = query tiles (of 128 rows) per CTA.  Every support tile that TMA brings in is multiplied against MT query
+// tiles, so the L2 -> shared-memory traffic per kernel evaluation drops by MT: at d = 32 one CTA with MT = 1 needs
+// 32 KB of support data per 16 384 evaluations (~1000 MUFU cycles), i.e. ~9 TB/s over 148 SMs -- more than the L2
+// delivers; MT = 2 halves that.  TMEM: MT x 2 accumulators of 128 columns (512 columns = all of it at MT = 2).
+template <int KIND, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                  const __grid_constant__ CUtensorMap tm_s_hi, const __grid_constant__ CUtensorMap tm_s_lo, TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_tc[];
   const int KB = p.kb, ST = p.stages;
-  // [A_hi KB blocks][A_lo KB blocks][stage: one K block of B_hi, B_lo] ...
+  // [A_hi MT*KB blocks][A_lo MT*KB blocks][stage: one K block of B_hi, B_lo] ...
   unsigned char* a_hi = smem_tc;
-  unsigned char* a_lo = a_hi + (size_t)KB * TC_TILE_BYTES;
-  unsigned char* b_base = a_lo + (size_t)KB * TC_TILE_BYTES;
+  unsigned char* a_lo = a_hi + (size_t)MT * KB * TC_TILE_BYTES;
+  unsigned char* b_base = a_lo + (size_t)MT * KB * TC_TILE_BYTES;
   const size_t b_stage_bytes = (size_t)2 * TC_TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)ST * b_stage_bytes);
   uint64_t* a_full = bars;            // 1
@@ -216,10 +220,11 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
   unsigned char* meta = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [epilogue warp][32 norms | 32 coefficients] float32, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * TC_M;
+  const int q0 = blockIdx.x * TC_M * MT;
   const int tile_begin = blockIdx.y * p.tiles_per_slice;
   const int tile_end = min(p.tiles_total, tile_begin + p.tiles_per_slice);
   const int ntile = max(0, tile_end - tile_begin);
+  constexpr uint32_t TMEM_COLS = MT == 1 ? 256 : 512;
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1);
@@ -227,8 +232,8 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
     for (int a = 0; a < 2; ++a) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], TC_EPI_WARPS); }
     mbar_fence_init();
   }
-  if (warp == 1) {   // TMEM: two accumulators of 128 fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256)
+  if (warp == 1) {   // TMEM: MT x two accumulators of 128 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -240,11 +245,12 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(a_full, (uint32_t)(2 * KB * TC_TILE_BYTES));
-      for (int kb = 0; kb < KB; ++kb) {
-        tma_load_2d(a_hi + (size_t)kb * TC_TILE_BYTES, &tm_q_hi, kb * TC_KBLK, q0, a_full);
-        tma_load_2d(a_lo + (size_t)kb * TC_TILE_BYTES, &tm_q_lo, kb * TC_KBLK, q0, a_full);
-      }
+      mbar_arrive_expect_tx(a_full, (uint32_t)(2 * MT * KB * TC_TILE_BYTES));
+      for (int mt = 0; mt < MT; ++mt)
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_2d(a_hi + (size_t)(mt * KB + kb) * TC_TILE_BYTES, &tm_q_hi, kb * TC_KBLK, q0 + mt * TC_M, a_full);
+          tma_load_2d(a_lo + (size_t)(mt * KB + kb) * TC_TILE_BYTES, &tm_q_lo, kb * TC_KBLK, q0 + mt * TC_M, a_full);
+        }
       // one pipeline stage = one K block (32 floats) of a support tile, hi and lo copies
       for (int step = 0; step < ntile * KB; ++step) {
         const int s = step % ST, it = step / KB, kb = step - it * KB;
@@ -265,8 +271,7 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
       int step = 0;
       for (int it = 0; it < ntile; ++it) {
         const int acc = it & 1;
-        mbar_wait(&t_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained this accumulator
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_N);
+        mbar_wait(&t_empty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained this accumulator set
         uint32_t accumulate = 0;
         for (int kb = 0; kb < KB; ++kb, ++step) {
           const int s = step % ST;
@@ -274,19 +279,25 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
           tc_fence_after();
           const unsigned char* bh = b_base + (size_t)s * b_stage_bytes;
           const unsigned char* bl = bh + TC_TILE_BYTES;
-          // lo.hi + hi.lo + hi.hi per K block, small terms first
-          for (int pass = (p.debug & 2) ? 3 : 0; pass < 3; ++pass) {
-            const uint64_t da = umma_desc_sw128((pass == 0 ? a_lo : a_hi) + (size_t)kb * TC_TILE_BYTES);
-            const uint64_t db = umma_desc_sw128(pass == 1 ? bl : bh);
 #pragma unroll
-            for (int k = 0; k < TC_KBLK / 8; ++k) {   // UMMA_K = 8 tf32 = 32 bytes: advance the start address
-              tc_mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), TC_IDESC, accumulate);
-              accumulate = 1;
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((mt * 2 + acc) * TC_N);
+            uint32_t accm = accumulate;
+            // lo.hi + hi.lo + hi.hi per K block, small terms first
+            for (int pass = (p.debug & 2) ? 3 : 0; pass < 3; ++pass) {
+              const uint64_t da = umma_desc_sw128((pass == 0 ? a_lo : a_hi) + (size_t)(mt * KB + kb) * TC_TILE_BYTES);
+              const uint64_t db = umma_desc_sw128(pass == 1 ? bl : bh);
+#pragma unroll
+              for (int k = 0; k < TC_KBLK / 8; ++k) {   // UMMA_K = 8 tf32 = 32 bytes: advance the start address
+                tc_mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), TC_IDESC, accm);
+                accm = 1;
+              }
             }
           }
+          accumulate = 1;
           tc_commit(&b_empty[s]);   // the smem stage may be refilled once these MMAs have read it
         }
-        tc_commit(&t_full[acc]);    // the accumulator is complete
+        tc_commit(&t_full[acc]);    // the accumulators are complete
       }
     }
   } else {
@@ -294,7 +305,9 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
     const int quarter = warp & 3;                       // a warp may only touch TMEM lanes 32*(warp%4) ..
     const int part = (warp - 2) >> 2;                   // columns part*32 .. +32 of the tile
     const int qrow = quarter * 32 + lane;
-    const float nq = p.qn[q0 + qrow];
+    float nq[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) nq[mt] = p.qn[q0 + mt * TC_M + qrow];
     // the metadata of this warp's 32 support rows is fetched one tile ahead (coalesced, one value per lane) and
     // staged in shared memory: the per-pair reads are then short-latency broadcasts instead of L1/L2 round trips
     float* wn = reinterpret_cast<float*>(meta + (size_t)(warp - 2) * 256);
@@ -304,20 +317,14 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
       mn = __ldg(p.svn + tile_begin * TC_N + part * 32 + lane);
       mc = (float)__ldg(p.svc + tile_begin * TC_N + part * 32 + lane);
     }
-    double sum = 0.0;
+    double sum[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) sum[mt] = 0.0;
     for (int it = 0; it < ntile; ++it) {
       const int acc = it & 1;
       mbar_wait(&t_full[acc], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const int s0 = (tile_begin + it) * TC_N + part * 32;
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_N + part * 32);
-      B2_TMEM_LD32(taddr, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      // the accumulator slice is in registers: hand the TMEM buffer back before the math
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[acc]);
       wn[lane] = mn;
       wc[lane] = mc;
       __syncwarp();
@@ -325,35 +332,60 @@ matvec_tc_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_const
         mn = __ldg(p.svn + s0 + TC_N + lane);
         mc = (float)__ldg(p.svc + s0 + TC_N + lane);
       }
-      if (p.debug & 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += (double)__uint_as_float(v[j]);
-        __syncwarp();
-        continue;
-      }
-      if (s0 + 32 <= p.nsv) {
-        sum += accum32<KIND>(p, v, reinterpret_cast<const float4*>(wn), reinterpret_cast<const float4*>(wc), nq);
-      } else {   // last, ragged tile: padding rows carry coefficient 0, but their kernel value need not be finite
+      for (int mt = 0; mt < MT; ++mt) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((mt * 2 + acc) * TC_N + part * 32);
+        B2_TMEM_LD32(taddr, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (mt == MT - 1) {
+          // the last accumulator slice is in registers: hand the TMEM buffers back before the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[acc]);
+        }
+        if (p.debug & 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (s0 + j < p.nsv) sum = fma(__ldg(p.svc + s0 + j), (double)epi_value<KIND>(p.c2, p.kp, v[j], __ldg(p.svn + s0 + j), nq), sum);
+          for (int j = 0; j < 32; ++j) sum[mt] += (double)__uint_as_float(v[j]);
+          continue;
+        }
+        if (s0 + 32 <= p.nsv) {
+          sum[mt] += accum32<KIND>(p, v, reinterpret_cast<const float4*>(wn), reinterpret_cast<const float4*>(wc), nq[mt]);
+        } else {   // last, ragged tile: padding rows carry coefficient 0, but their kernel value need not be finite
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (s0 + j < p.nsv) sum[mt] = fma(__ldg(p.svc + s0 + j), (double)epi_value<KIND>(p.c2, p.kp, v[j], __ldg(p.svn + s0 + j), nq[mt]), sum[mt]);
+        }
       }
       __syncwarp();   // every lane is done with the staged metadata before the next tile overwrites it
     }
     // the column parts of a query row meet in shared memory (the A tiles are dead by now: every MMA that read
     // them completed before the last t_full flipped)
-    double* red = reinterpret_cast<double*>(a_hi);      // [3][128]
-    if (part > 0) red[(part - 1) * TC_M + qrow] = sum;
+    double* red = reinterpret_cast<double*>(a_hi);      // [MT][3][128]
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+      if (part > 0) red[(mt * 3 + part - 1) * TC_M + qrow] = sum[mt];
     asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
-    if (part == 0 && q0 + qrow < p.nq)
-      p.partial[(size_t)blockIdx.y * p.nq + q0 + qrow] = ((sum + red[qrow]) + red[TC_M + qrow]) + red[2 * TC_M + qrow];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+      if (part == 0 && q0 + mt * TC_M + qrow < p.nq)
+        p.partial[(size_t)blockIdx.y * p.nq + q0 + mt * TC_M + qrow] =
+            ((sum[mt] + red[(mt * 3) * TC_M + qrow]) + red[(mt * 3 + 1) * TC_M + qrow]) + red[(mt * 3 + 2) * TC_M + qrow];
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+__global__ void reduce_partials_tc_kernel(const double* __restrict__ partial, int ny, int64_t nb, double* __restrict__ out) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nb; q += (int64_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int y = 0; y < ny; ++y) s += partial[(size_t)y * nb + q];
+    out[q] = s;
   }
 }
 
@@ -541,14 +573,6 @@ tile_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
   }
 }
 
-__global__ void reduce_partials_tc_kernel(const double* __restrict__ partial, int ny, int64_t nb, double* __restrict__ out) {
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nb; q += (int64_t)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int y = 0; y < ny; ++y) s += partial[(size_t)y * nb + q];
-    out[q] = s;
-  }
-}
-
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -617,7 +641,11 @@ static int matvec_tc_core(cudaStream_t stream, const b2svm_kernel_desc& k, int d
   const int dp = (d + TC_KBLK - 1) / TC_KBLK * TC_KBLK;
   const int KB = dp / TC_KBLK;
   const int64_t nsv_pad = ((int64_t)nsv + TC_N - 1) / TC_N * TC_N;
-  const int64_t nq_pad = (nb + TC_M - 1) / TC_M * TC_M;
+  // two query tiles per CTA when their operands fit beside a useful B pipeline (K blocks <= 2, i.e. d <= 64) and there
+  // are enough queries to fill the GPU twice over: halves the support-tile traffic per kernel evaluation
+  int MT = (KB <= 2 && nb >= 2 * 148 * 2 * TC_M) ? 2 : 1;
+  if (const char* e = getenv("B2SVM_TC_MT")) MT = std::max(1, std::min(KB <= 2 ? 2 : 1, atoi(e)));
+  const int64_t nq_pad = (nb + TC_M * MT - 1) / (TC_M * MT) * (TC_M * MT);
   float *s_hi = nullptr, *s_lo = nullptr, *q_hi = nullptr, *q_lo = nullptr, *svn = nullptr, *qn = nullptr;
   double *svc = nullptr, *partial = nullptr;
   auto done = [&](int code) {
@@ -658,7 +686,7 @@ static int matvec_tc_core(cudaStream_t stream, const b2svm_kernel_desc& k, int d
   TcParams p;
   p.svn = svn; p.svc = svc; p.qn = qn; p.nq = nb; p.nsv = nsv;
   p.tiles_total = (int)(nsv_pad / TC_N);
-  const int gx = (int)(nq_pad / TC_M);
+  const int gx = (int)(nq_pad / (TC_M * MT));
   int ny = std::max(1, std::min(p.tiles_total, (2 * 148 + gx - 1) / gx));
   // one slice of support rows (hi + lo copies) should sit in L2 while the query tiles sweep over it
   const int l2_tiles = std::max(1, (int)((32u << 20) / (2u * KB * TC_TILE_BYTES)));
@@ -669,17 +697,22 @@ static int matvec_tc_core(cudaStream_t stream, const b2svm_kernel_desc& k, int d
   p.kb = KB;
   p.c2 = (float)(2.0 * (double)(float)k.gamma * 1.4426950408889634);
   p.debug = getenv("B2SVM_TC_DEBUG") ? atoi(getenv("B2SVM_TC_DEBUG")) : 0;
-  const size_t a_bytes = (size_t)2 * KB * TC_TILE_BYTES, b_stage = (size_t)2 * TC_TILE_BYTES;
+  const size_t a_bytes = (size_t)2 * MT * KB * TC_TILE_BYTES, b_stage = (size_t)2 * TC_TILE_BYTES;
   p.stages = (int)std::min<size_t>(6, (200 * 1024 - a_bytes) / b_stage);
   if (p.stages < 2) return done(fail(B2SVM_E_UNSUPPORTED, "kernel_matvec (tensor path): n_features too large"));
   p.kp = KernelParams<float>{k.kind, (float)k.gamma, (float)k.coef0, (float)k.degree};
   TC_TRY(cudaMallocAsync(&partial, sizeof(double) * (size_t)ny * nb, stream));
   p.partial = partial;
   const size_t smem = a_bytes + p.stages * b_stage + (size_t)(2 * p.stages + 8) * sizeof(uint64_t) + 32 + TC_EPI_WARPS * 256 + 1024;
-#define TC_LAUNCH(KIND)                                                                                             \
-  do {                                                                                                              \
-    TC_TRY(cudaFuncSetAttribute(matvec_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    matvec_tc_kernel<KIND><<<dim3(gx, ny), TC_THREADS, smem, stream>>>(m_qh, m_ql, m_sh, m_sl, p);                  \
+#define TC_LAUNCH2(KIND, MTV)                                                                                             \
+  do {                                                                                                                    \
+    TC_TRY(cudaFuncSetAttribute(matvec_tc_kernel<KIND, MTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    matvec_tc_kernel<KIND, MTV><<<dim3(gx, ny), TC_THREADS, smem, stream>>>(m_qh, m_ql, m_sh, m_sl, p);                   \
+  } while (0)
+#define TC_LAUNCH(KIND)              \
+  do {                               \
+    if (MT == 2) TC_LAUNCH2(KIND, 2); \
+    else TC_LAUNCH2(KIND, 1);         \
   } while (0)
   switch (rff ? K_RFFCOS : k.kind) {
     case K_RFFCOS: TC_LAUNCH(K_RFFCOS); break;
@@ -689,6 +722,7 @@ static int matvec_tc_core(cudaStream_t stream, const b2svm_kernel_desc& k, int d
     default: TC_LAUNCH(K_LINEAR); break;
   }
 #undef TC_LAUNCH
+#undef TC_LAUNCH2
   TC_TRY(cudaGetLastError());
   reduce_partials_tc_kernel<<<std::max(1, (int)std::min<int64_t>(1184, (nb + 255) / 256)), 256, 0, stream>>>(partial, ny, nb, out);
   TC_TRY(cudaGetLastError());

@@ -1,4 +1,4 @@
-"""Turn the ncu outputs of scripts/final_n1.sh (gpurun_out/) into the tracked summaries under profiles/.
+"""Turn the ncu outputs of scripts/final_r2.sh (gpurun_out/) into the tracked summaries under profiles/.
 
     python scripts/summarize_profiles.py r1
 """
@@ -28,9 +28,9 @@ def launch_list():
     with open(os.path.join(G, "launches.csv")) as f, open(os.path.join(P, f"{tag}_launches.csv"), "w") as o:
         o.write(f.read())
     out = [f"# Round {tag[1:]} -- launch list of `bench.py` (ncu, per-launch device time)", "",
-           "Command (run on a B200 through gpurun, directly after the same command had exited 0 without ncu; scripts/final_n1.sh):", "",
+           "Command (run on a B200 through gpurun, directly after the same command had exited 0 without ncu; scripts/final_r2.sh):", "",
            "    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \\",
-           "        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-full-fit", "",
+           "        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-full-fit --no-secondary", "",
            f"Raw list: `profiles/{tag}_launches.csv`.  Times under ncu are serialised and cold-cache; compare shares.", "",
            "| kernel | launches | total ms | share |", "|---|---|---|---|"]
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -82,25 +82,25 @@ if __name__ == "__main__":
              "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
              "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
              "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "sm__warps_active.avg.pct_of_peak_sustained_active"]
-    m = full_capture(os.path.join(G, "prof_r1_smo.ncu-rep"),
+    m = full_capture(os.path.join(G, f"prof_{tag}_smo.ncu-rep"),
                      f"# Round {tag[1:]} -- `ncu --set full` of the persistent SMO kernel (C3: n=200 000, d=128, float32, RBF, cache off)", f"{tag}_smo_persistent_ncu_full.md",
-                     ["Command (gpurun, one B200; the plain run of the same command exited 0 directly before; scripts/final_n1.sh):", "",
+                     ["Command (gpurun, one B200; the plain run of the same command exited 0 directly before; scripts/final_r2.sh):", "",
                       "    ncu --set full --clock-control none --import-source on -k regex:smo_persistent -s 1 -c 1 \\",
-                      "        -o gpurun_out/prof_r1_smo python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-full-fit", "",
+                      f"        -o gpurun_out/prof_{tag}_smo python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-full-fit --no-secondary", "",
                       "One captured launch = 20 000 SMO iterations (148 CTAs x 384 threads: 11 consumer warps + 1 TMA producer warp)."], names)
     rd, wr = float(m["dram__bytes_read.sum"]), float(m["dram__bytes_write.sum"])
     unit = {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "byte": 1.0}
-    _, u = raw_metrics(os.path.join(G, "prof_r1_smo.ncu-rep"))
+    _, u = raw_metrics(os.path.join(G, f"prof_{tag}_smo.ncu-rep"))
     rd *= unit[u["dram__bytes_read.sum"]]
     wr *= unit[u["dram__bytes_write.sum"]]
     json.dump({"source": f"profiles/{tag}_smo_persistent_ncu_full.md (ncu --set full, one launch of 20000 iterations, n=200000 d=128)",
                "iterations_in_capture": 20000, "dram_bytes_read": rd, "dram_bytes_write": wr,
                "dram_bytes_per_iteration": (rd + wr) / 20000}, open(os.path.join(P, "traffic.json"), "w"), indent=1)
-    if os.path.exists(os.path.join(G, "prof_r1_matvec.ncu-rep")):
-        full_capture(os.path.join(G, "prof_r1_matvec.ncu-rep"),
+    if os.path.exists(os.path.join(G, f"prof_{tag}_matvec.ncu-rep")):
+        full_capture(os.path.join(G, f"prof_{tag}_matvec.ncu-rep"),
                      f"# Round {tag[1:]} -- `ncu --set full` of the tensor-core kernel mat-vec (K7: 400 000 queries x 200 000 support rows, d=32, RBF)", f"{tag}_matvec_tc_ncu_full.md",
-                     ["Command (gpurun, one B200, after the plain run exited 0; scripts/final_n1.sh):", "",
+                     ["Command (gpurun, one B200, after the plain run exited 0; scripts/final_r2.sh):", "",
                       "    ncu --set full --clock-control none --import-source on -k regex:matvec_tc_kernel -s 1 -c 1 \\",
-                      "        -o gpurun_out/prof_r1_matvec python scripts/ncu_matvec_target.py", "",
+                      f"        -o gpurun_out/prof_{tag}_matvec python scripts/ncu_matvec_target.py", "",
                       "One launch = 8e10 kernel evaluations: 3125 query tiles x 2 support slices, 576 threads (TMA warp, MMA warp, 16 epilogue warps)."], names)
     print("profiles written")
