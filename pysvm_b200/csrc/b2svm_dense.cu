@@ -14,15 +14,59 @@ namespace b2svm {
 // ------------------------------------------------------------------------------------------
 // ordered compaction of the rows with a non-zero coefficient (support vectors)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) compact_nonzero_kernel(const double* __restrict__ coef, int64_t n,
-                                                               int* __restrict__ idx, int* __restrict__ count) {
-  __shared__ int warp_tot[32];
+// Ordered, multi-block: (1) every block counts the non-zeros of its contiguous chunk, (2) one block turns the counts
+// into exclusive offsets (and the total), (3) every block writes its indices at its offset, in index order.
+constexpr int CMP_THREADS = 256, CMP_ITEMS = 16;          // 4096 coefficients per block
+__global__ void __launch_bounds__(CMP_THREADS) compact_count_kernel(const double* __restrict__ coef, int64_t n, int* __restrict__ counts) {
+  __shared__ int warp_tot[CMP_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * CMP_THREADS * CMP_ITEMS;
+  int c = 0;
+  for (int k = 0; k < CMP_ITEMS; ++k) {
+    const int64_t e = base + (int64_t)k * CMP_THREADS + threadIdx.x;
+    c += (e < n && coef[e] != 0.0) ? 1 : 0;
+  }
+  for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
+  if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < CMP_THREADS / 32; ++w) t += warp_tot[w];
+    counts[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int* __restrict__ counts, int nblocks, int* __restrict__ total) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int start = 0; start < nblocks; start += 1024) {
+    const int k = start + threadIdx.x;
+    const int v = k < nblocks ? counts[k] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {          // inclusive Hillis-Steele scan
+      const int add = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (k < nblocks) counts[k] = carry + sh[threadIdx.x] - v;   // exclusive offset of block k
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(CMP_THREADS) compact_write_kernel(const double* __restrict__ coef, int64_t n, const int* __restrict__ offsets,
+                                                                    int* __restrict__ idx) {
+  __shared__ int warp_tot[CMP_THREADS / 32];
   __shared__ int base_sh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) base_sh = 0;
+  const int64_t base = (int64_t)blockIdx.x * CMP_THREADS * CMP_ITEMS;
+  if (threadIdx.x == 0) base_sh = offsets[blockIdx.x];
   __syncthreads();
-  for (int64_t start = 0; start < n; start += 1024) {
-    const int64_t e = start + threadIdx.x;
+  for (int k = 0; k < CMP_ITEMS; ++k) {                 // chunk of CMP_THREADS consecutive coefficients: order preserved
+    const int64_t e = base + (int64_t)k * CMP_THREADS + threadIdx.x;
     const bool nz = e < n && coef[e] != 0.0;
     const unsigned bal = __ballot_sync(0xffffffffu, nz);
     const int before = __popc(bal & ((1u << lane) - 1u));
@@ -34,12 +78,11 @@ __global__ void __launch_bounds__(1024) compact_nonzero_kernel(const double* __r
     __syncthreads();
     if (threadIdx.x == 0) {
       int t = 0;
-      for (int w = 0; w < 32; ++w) t += warp_tot[w];
+      for (int w = 0; w < CMP_THREADS / 32; ++w) t += warp_tot[w];
       base_sh += t;
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *count = base_sh;
 }
 
 // gather support rows into a dense [nsv][dp] block (zero padded), with norms and coefficients
@@ -148,9 +191,13 @@ static int matvec_T(cudaStream_t stream, const b2svm_kernel_desc& k, int d, cons
   int* idx = nullptr;
   int* count_dev = nullptr;
   keep_pool_memory();
+  const int cmp_blocks = (int)((na + CMP_THREADS * CMP_ITEMS - 1) / (CMP_THREADS * CMP_ITEMS));
   B2_CUDA(cudaMallocAsync(&idx, sizeof(int) * (size_t)na, stream));
-  B2_CUDA(cudaMallocAsync(&count_dev, sizeof(int), stream));
-  compact_nonzero_kernel<<<1, 1024, 0, stream>>>(coef, na, idx, count_dev);
+  B2_CUDA(cudaMallocAsync(&count_dev, sizeof(int) * (size_t)(cmp_blocks + 1), stream));
+  compact_count_kernel<<<cmp_blocks, CMP_THREADS, 0, stream>>>(coef, na, count_dev + 1);
+  compact_scan_kernel<<<1, 1024, 0, stream>>>(count_dev + 1, cmp_blocks, count_dev);
+  compact_write_kernel<<<cmp_blocks, CMP_THREADS, 0, stream>>>(coef, na, count_dev + 1, idx);
+  // (the count comes back to the host: the work buffers and the launch geometry of the mat-vec depend on it)
   int nsv = 0;
   B2_CUDA(cudaMemcpyAsync(&nsv, count_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
   B2_CUDA(cudaStreamSynchronize(stream));

@@ -28,7 +28,7 @@ if rank == 0:
     ref = BiKernelSVC(max_iter=10 ** 6).fit(X, y01)
     assert est.n_iter_ == ref.n_iter_, (est.n_iter_, ref.n_iter_)
     assert np.array_equal(est.alpha_, ref.alpha_)
-    assert est.rho_ == ref.rho_
+    assert abs(est.rho_ - ref.rho_) <= 1e-13 * max(1.0, abs(ref.rho_))     # a mean over the free SVs: summed per rank / per block
     np.testing.assert_allclose(dec, ref.decision_function(X[:300]), rtol=0, atol=1e-12)
     gold = O.fit_csvc(X, y01, max_iter=10 ** 6)
     assert abs(est.n_iter_ - gold.n_iter) <= max(1, 0.01 * gold.n_iter)
@@ -109,7 +109,7 @@ it_sh = sum(e.n_iter_ for e in ovo.multiclass_model.estimators_)
 it_ref = sum(e.n_iter_ for e in ref.multiclass_model.estimators_)
 assert it_sh == it_ref, (it_sh, it_ref)
 for a, b in zip(ovo.multiclass_model.estimators_, ref.multiclass_model.estimators_):
-    assert np.array_equal(a.alpha_, b.alpha_) and a.rho_ == b.rho_
+    assert np.array_equal(a.alpha_, b.alpha_) and abs(a.rho_ - b.rho_) <= 1e-13 * max(1.0, abs(b.rho_))
 assert np.array_equal(pred, ref.predict(Xd))
 if rank == 0:
     print("sharded worker ok: 45 one-vs-one sub-problems over", world, "GPUs,", it_sh, "iterations", flush=True)
