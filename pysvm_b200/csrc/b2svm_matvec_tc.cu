@@ -151,12 +151,34 @@ struct TcParams {
 // rbf: exp(-gamma (|a|^2 + |b|^2 - 2 a.b)) = 2^(c2 * a.b + na' + nb') with the norms pre-scaled by -gamma log2(e)
 // (split_rows_kernel) and c2 = 2 gamma log2(e): one add, one fma, one MUFU.EX2.  The rounding of the exponent
 // is |x| 2^-24 relative -- the same order as the float32 rounding of -gamma * dist in the reference (svc.py:230-232).
-template <int KIND>
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, 2^f by the Cephes
+// exp2f polynomial on [-0.5, 0.5] (relative error ~1e-7, the same order as MUFU.EX2's 2^-22), 2^n by an integer add
+// into the exponent field.  ~12 issue slots against 1 for ex2.approx -- used for ONE IN FOUR pairs of the rbf epilogue,
+// which looked bound by the MUFU pipe (XU 62 % busy, FMA 23 %: profiles/r2_matvec_tc_ncu_full.md).  MEASURED SLOWER
+// (1M x 500k, d = 32: 202.5 -> 226.3 ms): the epilogue is issue / latency bound (16 warps, 28 % warps active), so the
+// extra issue slots cost more than the MUFU slots they free.  Kept for the record, not used (POLY = false everywhere).
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = 1.535336188319500e-4f;
+  p = fmaf(p, f, 1.339887440266574e-3f);
+  p = fmaf(p, f, 9.618437357674640e-3f);
+  p = fmaf(p, f, 5.550332471162809e-2f);
+  p = fmaf(p, f, 2.402264791363012e-1f);
+  p = fmaf(p, f, 6.931472028550421e-1f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int KIND, bool POLY = false>
 __device__ __forceinline__ float epi_value(float c2, const KernelParams<float>& kp, uint32_t dot_bits, float norm_s, float norm_q) {
   const float dot = __uint_as_float(dot_bits);
   if constexpr (KIND == K_RBF) {
+    const float x = fmaf(c2, dot, norm_s + norm_q);
+    if constexpr (POLY) return exp2_fma(x);
     float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(c2, dot, norm_s + norm_q)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
   } else if constexpr (KIND == K_RFFCOS) {
     // cos(w_s . x_q + b_s): reduce to [-pi, pi] with a two-term 2 pi, then MUFU.COS (abs error ~5e-7)
