@@ -350,6 +350,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     L0.warm_cnt = L0.stored_cnt = L0.evict_cnt = 0;
     sh->leader = L0;
   }
+  // shared memory is not cleared between launches: an alpha unit parked by an earlier solve carries a valid-looking
+  // tag of the same epoch number, so the hand-over slots start out empty
+  for (int e = threadIdx.x; e < NW * NCAND; e += blockDim.x) (&sh->wa[0][0])[e] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
 
   // ============================== producer warp ==============================================
@@ -619,19 +622,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         if (P.timeline && threadIdx.x == 0 && epoch == 41u && cta < 160)   // when did every CTA publish (global ns timer)?
           P.timeline[TL_CTA_BASE + 2 * cta] = (long long)globaltimer_ns();
 #endif
-        // ---- the CTA winner's alpha, as soon as the warp that owns it has parked it
+        // ---- the CTA winner's alpha: forwarded as soon as the warp that owns it has parked it (its load may still be
+        // in flight: the check is repeated between the poll passes below instead of being waited for here)
         park_alpha();
         __syncwarp();
-        uint4 ua = ld_volatile_shared_v4(&sh->wa[from_warp][k]);
-        while (!unit_ok(ua, epoch)) ua = ld_volatile_shared_v4(&sh->wa[from_warp][k]);
-        if (world == 1) {   // ... pushed all-to-all like the record (world > 1: it travels with the level-2 push instead)
-          const uint4 au = make_unit(ua.x, ua.y, epoch);
+        uint4 ua = make_uint4(0u, 0u, 0u, 0u);
+        bool alpha_sent = false;
+        auto try_alpha = [&]() {
+          if (alpha_sent) return;
+          ua = ld_volatile_shared_v4(&sh->wa[from_warp][k]);      // (same address in every lane: one broadcast read)
+          if (!unit_ok(ua, epoch)) return;
+          alpha_sent = true;
+          if (world == 1) {   // pushed all-to-all like the record (world > 1: it travels with the level-2 push instead)
+            const uint4 au = make_unit(ua.x, ua.y, epoch);
 #pragma unroll
-          for (int mm = 0; mm < MAXM; ++mm) {
-            const int t = lane + 32 * mm;
-            if (t < ncta && t != cta) st_relaxed_v4(l1_slot(t) + l1_total, au);
+            for (int mm = 0; mm < MAXM; ++mm) {
+              const int t = lane + 32 * mm;
+              if (t < ncta && t != cta) st_relaxed_v4(l1_slot(t) + l1_total, au);
+            }
           }
-        }
+        };
+        try_alpha();
 
         // ---- poll the ncta level-1 records of this type (this read is the grid barrier)
         KCand gw;          // GPU-level winner
@@ -659,6 +670,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
               bsrc = take ? c : bsrc;
             }
             if (passes++ == 0) stamp(13);   // first pass back
+            try_alpha();
             if (__all_sync(0xffffffffu, all)) {
               gw = kc_redux(bk);
               const unsigned hold2 = __ballot_sync(0xffffffffu, gw.nik != 0u && bk.nik == gw.nik);
@@ -677,6 +689,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             }
             issue_poll();
           }
+          while (!alpha_sent) try_alpha();
           stamp(15);   // poll loop left
           stamp_val(14, (long long)passes);
 #ifdef B2SVM_TIMELINE
@@ -1168,6 +1181,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         }
 #ifdef B2SVM_TIMELINE
         const long long dbg_w0 = dbg ? clock64() : 0;
+        if (dbg && threadIdx.x == 0) P.timeline[TL_ITERS * TL_SLOTS + 12 * TL_WARP_SLOTS + 3] = clock64() - dbg_start;   // tile loop entered (sweep set-up done)
 #endif
         {
           uint32_t spins = 0;
@@ -1199,7 +1213,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             acc[2 * k + 1] = CK::dot(v, xj[q], acc[2 * k + 1]);
           }
         }
+#ifdef B2SVM_TIMELINE
+        if (dbg && threadIdx.x == 0) P.timeline[TL_ITERS * TL_SLOTS + 12 * TL_WARP_SLOTS + 0] = clock64() - dbg_start;   // dot products done
+#endif
         TransposeReduce<T, C::NV, C::LPR / 2>::run(acc, lig);
+#ifdef B2SVM_TIMELINE
+        if (dbg && threadIdx.x == 0) P.timeline[TL_ITERS * TL_SLOTS + 12 * TL_WARP_SLOTS + 1] = clock64() - dbg_start;   // transposed reduce done
+#endif
         if (C::FINAL == 2) {
           dti = acc[0];
           dtj = acc[1];
@@ -1245,6 +1265,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           cur.f1 = f;
         }
       }
+#ifdef B2SVM_TIMELINE
+      if (dbg && threadIdx.x == 0) P.timeline[TL_ITERS * TL_SLOTS + 12 * TL_WARP_SLOTS + 2] = clock64() - dbg_start;   // row epilogue done
+#endif
       if (one_tile) pf = cur;   // the warp's only tile: gradient, flags and norm stay in registers for the next sweep
       m = mn;
       sub = subn;

@@ -51,6 +51,8 @@ def run(n, d, iters, dtype=np.float32):
     sw = np.median(seg[1:, 0] - seg[:-1, 6])
     print(f"   {'sweep (6->next 0)':34s} {sw:9.0f}")
     print(f"   chain {tot:.0f} + sweep {sw:.0f} = {tot + sw:.0f} cycles -> {(tot + sw)/us:.0f} cycles/us")
+    print(f"   warp 0, first tile of the sweep at epoch 10 (cycles from sweep start): tile loop entered {wt[12, 3]}, dot products done {wt[12, 0]}, "
+          f"transposed reduce done {wt[12, 1]}, row epilogue done {wt[12, 2]}")
     base = wt[:11, 0].min()
     print("   per-warp sweep at epoch 10 (start, end rel. cycles; tiles; wait cycles):")
     for w in range(11):

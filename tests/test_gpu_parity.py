@@ -222,6 +222,26 @@ def test_g5_oneclass(golden):
     np.testing.assert_array_equal(est.predict(g["X"]), g["pred"])
 
 
+def test_back_to_back_solves_do_not_leak_state(golden, diabetes):
+    """A solve must not depend on what ran on the GPU before it: the persistent kernel's shared-memory hand-over
+    slots carry epoch tags, and a unit left by an EARLIER launch (same epoch number, other problem) once passed
+    for the current one -- the one-class fixture then took 47 instead of 51 iterations after the SVR tests."""
+    import hashlib
+    *_, svr, oc = _mods()
+    g = golden("g5_oneclass")
+    Xd, zd = diabetes
+
+    def fit():
+        est = oc.OneClassSVM(nu=.1, gamma=.1, max_iter=10 ** 5).fit(g["X"])
+        return est.n_iter_, hashlib.sha256(est.alpha_.tobytes()).hexdigest()
+
+    first = fit()
+    for kw in (dict(eps=10, C=100), dict(), dict(C=10.)):
+        svr.KernelSVR(max_iter=2000, **kw).fit(Xd, zd)          # another problem leaves its state behind
+        svr.NuSVR(max_iter=300).fit(Xd[:300], zd[:300])
+        assert fit() == first
+
+
 def test_linear_estimators(golden, breast_cancer, diabetes):
     *_, svc, svr, _ = _mods()
     X, y = breast_cancer
