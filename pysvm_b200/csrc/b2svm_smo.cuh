@@ -109,7 +109,7 @@ struct ProblemDev {
   int world, rank;
   long long row_offset, l_global, rows_per_rank;   // every rank's slice starts at rank * rows_per_rank
   double* dbg_steps;              // optional [DBG_EPOCHS][ncta][DBG_W]: si, sj, gi, gj, ai, aj, Kii, Kjj, Kij, ci, cj, row checksum | consumer view
-  int debug_flags;                // B2SVM_DEBUG_FLAGS: 1 = static tile assignment, 2 = L2 loads for G/flags
+  int debug_flags;                // B2SVM_DEBUG_FLAGS: 1 = static tile assignment
 };
 // level-2 box slot: {record, alpha unit, norm unit, K(x,x) unit, 2 half-chunk units per 16-byte chunk of the widest row (CH = 128)}
 constexpr int BOX_UNITS = 4 + 2 * 128;
@@ -261,6 +261,13 @@ __device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (
     }
   }
 }
+
+// compiler fence on one register value: nothing computed from v may be scheduled above this point
+__device__ __forceinline__ void opaque(float& v) { asm volatile("" : "+f"(v)); }
+__device__ __forceinline__ void opaque(double& v) { asm volatile("" : "+d"(v)); }
+__device__ __forceinline__ void opaque(int& v) { asm volatile("" : "+r"(v)); }
+
+constexpr int WARM_U = 4;   // tiles whose loads a warp keeps in flight in a warm (cached-column) sweep
 
 template <typename T>
 struct RowState {   // gradient-side state of one row (and its mirror variable), prefetched a tile ahead
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
   bool sweep_warm = false;
   const T* cache_i = nullptr;
   const T* cache_j = nullptr;
-  auto load_row_state = [&](int t) {
+  auto load_row_state = [&](int t, bool with_norm = true) {
     RowState<T> r;
     r.g0 = r.g1 = 0.0;
     r.f0 = r.f1 = 0;
@@ -473,16 +480,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     r.ki = r.kj = 0;
     const long long row = row0 + (long long)t * C::BR + rib;
     if (t < NT && lane_active && row < row1) {
-      if (P.debug_flags & 2) {
-        r.g0 = __ldcg(G + row);
-        r.f0 = __ldcg(flags + row);
-        if (mirror) { r.g1 = __ldcg(G + row + l); r.f1 = __ldcg(flags + row + l); }
-      } else {
-        r.g0 = G[row];
-        r.f0 = flags[row];
-        if (mirror) { r.g1 = G[row + l]; r.f1 = flags[row + l]; }
-      }
-      r.nt = norms[row];
+      r.g0 = G[row];
+      r.f0 = flags[row];
+      if (mirror) { r.g1 = G[row + l]; r.f1 = flags[row + l]; }
+      if (with_norm) r.nt = norms[row];
       if (CACHE && sweep_warm) {
         r.ki = cache_i[row];
         r.kj = cache_j[row];
@@ -558,6 +559,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       for (int q = 0; q < QL; ++q) row[q] = CK::zero();
       bool have_row = false, have_alpha = false;
       int status = 0;
+      int raw_slot = -1;   // the winner's entry in the (one sweep late) column-cache slot table
 
       if (!forced_now) {
         // ---- CTA-level winner (full-warp collectives only: two half-warp masks in one instruction compile to a
@@ -781,6 +783,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
 
         // ---- the winner's alpha, norm and row
         if (w.idx >= 0 && !status) {
+          if (CACHE && P.cache_slots > 0)   // (requested here so that it travels together with the row below)
+            raw_slot = __ldcg(P.slot_of + ((mirror && w.idx >= lg) ? w.idx - lg : w.idx));
           if (world > 1) {
             // from the box slot of the rank it came from; every unit is re-read until it carries this epoch
             const uint4* slot = box_base + (((size_t)par * BOX_RANKS + wsrc) * NCAND + k) * BOX_UNITS;
@@ -852,6 +856,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         w.flags = __ldcg(flags + w.idx);
         w_alpha = __ldcg(alpha + w.idx);
         have_alpha = true;
+        if (CACHE && P.cache_slots > 0) raw_slot = __ldcg(P.slot_of + ((mirror && w.idx >= lg) ? w.idx - lg : w.idx));
         if (k == 0 && lane == 0) sh->ticket = NW;
         if (P.kind != K_PRECOMPUTED) {
           const long long lrow = (mirror && w.idx >= lg) ? w.idx - lg : w.idx;
@@ -872,11 +877,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       {
         Selected<T> sv;
         sv.g = w.g; sv.alpha = w_alpha; sv.idx = w.idx; sv.flags = w.flags;
-        sv.raw_slot = -1; sv.pad = 0;
+        sv.raw_slot = raw_slot; sv.pad = 0;
         sv.norm = nrm; sv.kself = kself;
         if (w.idx >= 0) {
-          const long long grow = (mirror && w.idx >= lg) ? w.idx - lg : w.idx;
-          if (CACHE && P.cache_slots > 0 && lane == 0) sv.raw_slot = __ldcg(P.slot_of + grow);
+          if (CACHE && raw_slot >= 0 && !one_tile) {
+            // a cached column of a winner is most likely read by the coming sweep (a warm sweep reads nothing else from
+            // HBM): start pulling this CTA's rows of it into L2 now, a type barrier, a kernel value and a step ahead
+            const char* seg = reinterpret_cast<const char*>(reinterpret_cast<const T*>(P.cache) + (size_t)raw_slot * (size_t)l + row0);
+            const int bytes = (int)(row1 - row0) * (int)sizeof(T);
+            for (int o = lane * 128, n = 0; o < bytes && n < 8; o += 32 * 128, ++n)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(seg + o));
+          }
           if (have_row) {
 #pragma unroll
             for (int q = 0; q < QL; ++q) {
@@ -1092,7 +1103,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     const double nai = sh->ai, naj = sh->aj;
     const T ni = sh->ni, nj = sh->nj;
     V xi[C::CPL], xj[C::CPL];
-    {
+    if (!(CACHE && sh->warm != 0)) {   // (a warm sweep never touches the rows)
       const V* xri = xs + sh->ti * CH;
       const V* xrj = xs + sh->tj * CH;
 #pragma unroll
@@ -1137,7 +1148,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
       if (sh->p_sj >= 0) { P.slot_of[sh->p_rj] = sh->p_sj; if (P.row_of_slot) P.row_of_slot[sh->p_sj] = sh->p_rj; }
       __threadfence();
     }
-    if (warm) {   // the first tile's state was prefetched before this sweep's plan was known
+    // gradient update and candidate search of one row (and of its mirror variable), given its two kernel values
+    auto finish_row = [&](RowState<T>& cur, long long row, T kti, T ktj) {
+      // y_t * (delta_i Q_i[t] + delta_j Q_j[t]) = (y_i delta_i) K_ti + (y_j delta_j) K_tj   (solver.py:146)
+      const double c = ci * (double)kti + cj * (double)ktj;
+      {
+        const int v = (int)(row + goff);
+        const double g = cur.g0 - c;
+        G[row] = g;
+        int f = cur.f0;
+        if (v == wi) { f = nfi; flags[row] = (uint8_t)nfi; alpha[row] = nai; }
+        else if (v == wj) { f = nfj; flags[row] = (uint8_t)nfj; alpha[row] = naj; }
+        consider(nu, f, g, v, best, alpha + row);
+        cur.g0 = g;
+        cur.f0 = f;
+      }
+      if (mirror) {
+        const int v = (int)(row + goff + lg);
+        const double g = cur.g1 - c;
+        G[row + l] = g;
+        int f = cur.f1;
+        if (v == wi) { f = nfi; flags[row + l] = (uint8_t)nfi; alpha[row + l] = nai; }
+        else if (v == wj) { f = nfj; flags[row + l] = (uint8_t)nfj; alpha[row + l] = naj; }
+        consider(nu, f, g, v, best, alpha + row + l);
+        cur.g1 = g;
+        cur.f1 = f;
+      }
+    };
+    int m = warp, sub = 0;              // macro tile (first one static: its gradient state is already in pf), tile in it
+    if (CACHE && warm && !one_tile) {
+      // ---- warm sweep: two cached columns and the gradient, no arithmetic to hide a load behind.  One tile ahead
+      // (the prefetch depth of the recomputing path) makes every tile cost a full memory latency, so the loads of
+      // WARM_U tiles are in flight together; tiles are handed out statically (macro tiles warp, warp + NW, ...).
+      const int per_warp = warp < NM ? ((NM - 1 - warp) / NW + 1) * SUB : 0;
+#ifdef B2SVM_TIMELINE
+      const bool wdbg = P.timeline && cta == 0 && threadIdx.x == 0 && epoch == 10u;
+      long long* const wo = P.timeline + TL_ITERS * TL_SLOTS + 12 * TL_WARP_SLOTS;
+      if (wdbg) wo[3] = clock64();   // warm path entered (absolute)
+#endif
+      for (int j0 = 0; j0 < per_warp; j0 += WARM_U) {
+        RowState<T> rs[WARM_U];
+        int ts[WARM_U];
+#pragma unroll
+        for (int u = 0; u < WARM_U; ++u) {
+          const int j = j0 + u;
+          ts[u] = j >= per_warp ? NT : (SUB == 1 ? warp + j * NW : (warp + (j / SUB) * NW) * SUB + (j % SUB));
+          rs[u] = load_row_state(ts[u], false);
+        }
+#ifdef B2SVM_TIMELINE
+        if (wdbg && j0 == 0) wo[0] = clock64();   // loads of the first batch issued
+#endif
+        // (without the fences the float -> double conversion of a tile's kernel values is hoisted to right behind its
+        // loads, and the in-order issue then waits out one memory latency per tile instead of one per batch)
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int u = 0; u < WARM_U; ++u) {
+          opaque(rs[u].ki); opaque(rs[u].kj); opaque(rs[u].g0); opaque(rs[u].f0);
+          if (mirror) { opaque(rs[u].g1); opaque(rs[u].f1); }
+          const long long row = row0 + (long long)ts[u] * C::BR + rib;
+          if (ts[u] < NT && lane_active && row < row1) finish_row(rs[u], row, rs[u].ki, rs[u].kj);
+#ifdef B2SVM_TIMELINE
+          if (wdbg && j0 == 0 && u == 0) wo[1] = clock64();   // first tile done
+#endif
+        }
+      }
+#ifdef B2SVM_TIMELINE
+      if (wdbg) wo[2] = clock64();   // all tiles done
+#endif
+      m = NM;   // (the tile loop below is the recomputing path)
+    } else if (warm) {   // the first tile's state was prefetched before this sweep's plan was known
       const long long r0w = row0 + (long long)warp * SUB * C::BR + rib;
       if (warp < NM && lane_active && r0w < row1) { pf.ki = col_i[r0w]; pf.kj = col_j[r0w]; }
     }
@@ -1149,7 +1228,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
     long long dbg_wait = 0;
     int dbg_tiles = 0;
 #endif
-    int m = warp, sub = 0;              // macro tile (first one static: its gradient state is already in pf), tile in it
     while (m < NM) {
       const int t = m * SUB + sub;
       // next tile: the following one of this macro tile, else draw a new macro tile -- now, so that its
@@ -1240,30 +1318,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         const T ktj = warm ? cur.kj : kernel_value(kp, dtj, cur.nt, nj);
         if (store_i) col_i[row] = kti;
         if (store_j) col_j[row] = ktj;
-        // y_t * (delta_i Q_i[t] + delta_j Q_j[t]) = (y_i delta_i) K_ti + (y_j delta_j) K_tj   (solver.py:146)
-        const double c = ci * (double)kti + cj * (double)ktj;
-        {
-          const int v = (int)(row + goff);
-          const double g = cur.g0 - c;
-          G[row] = g;
-          int f = cur.f0;
-          if (v == wi) { f = nfi; flags[row] = (uint8_t)nfi; alpha[row] = nai; }
-          else if (v == wj) { f = nfj; flags[row] = (uint8_t)nfj; alpha[row] = naj; }
-          consider(nu, f, g, v, best, (P.debug_flags & 4) ? nullptr : alpha + row);
-          cur.g0 = g;
-          cur.f0 = f;
-        }
-        if (mirror) {
-          const int v = (int)(row + goff + lg);
-          const double g = cur.g1 - c;
-          G[row + l] = g;
-          int f = cur.f1;
-          if (v == wi) { f = nfi; flags[row + l] = (uint8_t)nfi; alpha[row + l] = nai; }
-          else if (v == wj) { f = nfj; flags[row + l] = (uint8_t)nfj; alpha[row + l] = naj; }
-          consider(nu, f, g, v, best, alpha + row + l);
-          cur.g1 = g;
-          cur.f1 = f;
-        }
+        finish_row(cur, row, kti, ktj);
       }
 #ifdef B2SVM_TIMELINE
       if (dbg && threadIdx.x == 0) P.timeline[TL_ITERS * TL_SLOTS + 12 * TL_WARP_SLOTS + 2] = clock64() - dbg_start;   // row epilogue done

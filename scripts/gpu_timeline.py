@@ -51,8 +51,17 @@ def run(n, d, iters, dtype=np.float32):
     sw = np.median(seg[1:, 0] - seg[:-1, 6])
     print(f"   {'sweep (6->next 0)':34s} {sw:9.0f}")
     print(f"   chain {tot:.0f} + sweep {sw:.0f} = {tot + sw:.0f} cycles -> {(tot + sw)/us:.0f} cycles/us")
+    if os.environ.get("PER_EPOCH"):
+        # a warm state mixes cached-column and recomputing sweeps: list them one by one
+        print("   epoch: chain(0->6) sweep(6->next 0) | join L1poll fetch select+K step plan")
+        for e in range(2, k - 1):
+            r = t[e]
+            print(f"     {e:3d}: {r[6]-r[0]:6d} {t[e+1][0]-r[6]:6d} | {r[1]-r[0]:5d} {r[3]-r[2]:5d} {r[8]-r[4]:5d} {r[10]-r[9]:5d} {r[11]-r[10]:5d} {r[5]-r[11]:5d}")
     print(f"   warp 0, first tile of the sweep at epoch 10 (cycles from sweep start): tile loop entered {wt[12, 3]}, dot products done {wt[12, 0]}, "
           f"transposed reduce done {wt[12, 1]}, row epilogue done {wt[12, 2]}")
+    if st.cold_sweeps == 0:
+        b6 = t[9, 6]
+        print(f"   warm sweep of warp 0 at epoch 10 (cycles from sweep start {b6}): path entered {wt[12,3]-b6}, loads issued {wt[12,0]-b6}, first tile done {wt[12,1]-b6}, all done {wt[12,2]-b6}, next epoch stamp 0 at {t[10,0]-b6}")
     base = wt[:11, 0].min()
     print("   per-warp sweep at epoch 10 (start, end rel. cycles; tiles; wait cycles):")
     for w in range(11):
