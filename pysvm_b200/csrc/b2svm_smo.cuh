@@ -245,20 +245,26 @@ __device__ __forceinline__ double ld_keep_f64(const double* p, uint64_t policy) 
   return v;
 }
 __device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (&b)[NCAND], const double* pa) {
+  // Branch-free (selects): almost every row leaves the running bests alone, and a branch per test would end the basic
+  // block there -- the rows of a batch of tiles could then not be interleaved by the scheduler.
   const bool second = nu && !(f & F_YPOS);
-  if (in_up(f)) {
-    if (!second) {
-      if (better_max(g, v, b[0].g, b[0].idx)) { b[0].g = g; b[0].idx = v; b[0].flags = f; touch_alpha(pa); }
-    } else {
-      if (better_max(g, v, b[2].g, b[2].idx)) { b[2].g = g; b[2].idx = v; b[2].flags = f; touch_alpha(pa); }
-    }
+  {
+    const double bg = second ? b[2].g : b[0].g;
+    const int bi = second ? b[2].idx : b[0].idx;
+    const bool take = in_up(f) && better_max(g, v, bg, bi);
+    const bool t0 = take && !second, t2 = take && second;
+    b[0].g = t0 ? g : b[0].g; b[0].idx = t0 ? v : b[0].idx; b[0].flags = t0 ? f : b[0].flags;
+    b[2].g = t2 ? g : b[2].g; b[2].idx = t2 ? v : b[2].idx; b[2].flags = t2 ? f : b[2].flags;
+    if (take) touch_alpha(pa);
   }
-  if (in_low(f)) {
-    if (!second) {
-      if (better_min(g, v, b[1].g, b[1].idx)) { b[1].g = g; b[1].idx = v; b[1].flags = f; touch_alpha(pa); }
-    } else {
-      if (better_min(g, v, b[3].g, b[3].idx)) { b[3].g = g; b[3].idx = v; b[3].flags = f; touch_alpha(pa); }
-    }
+  {
+    const double bg = second ? b[3].g : b[1].g;
+    const int bi = second ? b[3].idx : b[1].idx;
+    const bool take = in_low(f) && better_min(g, v, bg, bi);
+    const bool t1 = take && !second, t3 = take && second;
+    b[1].g = t1 ? g : b[1].g; b[1].idx = t1 ? v : b[1].idx; b[1].flags = t1 ? f : b[1].flags;
+    b[3].g = t3 ? g : b[3].g; b[3].idx = t3 ? v : b[3].idx; b[3].flags = t3 ? f : b[3].flags;
+    if (take) touch_alpha(pa);
   }
 }
 
