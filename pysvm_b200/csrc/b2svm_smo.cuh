@@ -110,6 +110,9 @@ struct ProblemDev {
   long long row_offset, l_global, rows_per_rank;   // every rank's slice starts at rank * rows_per_rank
   double* dbg_steps;              // optional [DBG_EPOCHS][ncta][DBG_W]: si, sj, gi, gj, ai, aj, Kii, Kjj, Kij, ci, cj, row checksum | consumer view
   int debug_flags;                // B2SVM_DEBUG_FLAGS: 1 = static tile assignment
+  // pacing of the exchange polls, in SM cycles (B2SVM_POLL_DELAY / _GAP / _DELAY2 / _GAP2): wait before the first poll of
+  // a level and between two polls.  Polling competes with the very records it waits for.
+  int poll_delay, poll_gap, poll_delay2, poll_gap2;
 };
 // level-2 box slot: {record, alpha unit, norm unit, K(x,x) unit, 2 half-chunk units per 16-byte chunk of the widest row (CH = 128)}
 constexpr int BOX_UNITS = 4 + 2 * 128;
@@ -265,6 +268,13 @@ __device__ __forceinline__ void consider(bool nu, int f, double g, int v, Cand (
     b[1].g = t1 ? g : b[1].g; b[1].idx = t1 ? v : b[1].idx; b[1].flags = t1 ? f : b[1].flags;
     b[3].g = t3 ? g : b[3].g; b[3].idx = t3 ? v : b[3].idx; b[3].flags = t3 ? f : b[3].flags;
     if (take) touch_alpha(pa);
+  }
+}
+
+__device__ __forceinline__ void spin_cycles(int n) {
+  if (n > 0) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < n) {}
   }
 }
 
@@ -594,15 +604,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
         // ---- poll loads of the first pass go out right away (they are looked at after the alpha hand-over below);
         // this CTA's own record never leaves its registers
         uint4 h[MAXM];
-        auto issue_poll = [&]() {
+#pragma unroll
+        for (int mm = 0; mm < MAXM; ++mm) h[mm] = make_uint4(0u, 0u, 0u, 0u);
+        auto issue_poll = [&]() {   // (only what is still missing: polling traffic competes with the records themselves)
 #pragma unroll
           for (int mm = 0; mm < MAXM; ++mm) {
             const int c = lane + 32 * mm;
-            h[mm] = make_uint4(0u, 0u, 0u, 0u);
-            if (c < ncta && c != cta) h[mm] = ld_relaxed_v4(l1_mine + c);
+            if (c < ncta && c != cta && h[mm].w != epoch) h[mm] = ld_relaxed_v4(l1_mine + c);
           }
         };
-        issue_poll();
         // the candidate's row, requested now and used after the poll: real loads when it may have to travel to the
         // other GPUs (world > 1), an L2 prefetch otherwise (the leaders' fetch of the winning row then hits)
         V myrow[QL];
@@ -659,6 +669,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           uint32_t rounds = 0;
           stamp(12);   // poll entry
           uint32_t passes = 0;
+          // The first poll goes out late: right behind the publish it can only fail (nobody else is there yet), and the
+          // loads of 148 pollers get in the way of the records still travelling (measured: polling from the publish on
+          // costs 4 % of the iteration rate, two polls in flight another 4 %)
+          if (ncta > 1) spin_cycles(P.poll_delay);
+          issue_poll();
           for (;;) {
             bool all = true;
             KCand bk = kc_empty();
@@ -695,6 +710,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
               }
               if (__any_sync(0xffffffffu, bad)) { status = 1; gw = kc_empty(); break; }
             }
+            spin_cycles(P.poll_gap);
             issue_poll();
           }
           while (!alpha_sent) try_alpha();
@@ -755,9 +771,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             const uint4* rbase = P.box + (((size_t)cta * 2 + par) * NCAND + k) * BOX_RANKS;
             uint64_t t_start = 0;
             uint32_t rounds = 0;
+            spin_cycles(P.poll_delay2);
             for (;;) {
               KCand bk = kc_empty();
               bool ok = true;
+              if (rounds) spin_cycles(P.poll_gap2);
               if (lane < world) {
                 const uint4 hh = ld_relaxed_sys_v4(rbase + lane);
                 ok = hh.w == epoch;
