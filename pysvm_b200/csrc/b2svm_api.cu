@@ -599,7 +599,7 @@ void fill_problem(const b2svm_handle* h, ProblemDev& P, long long max_iter, long
   P.dbg_steps = h->dbg_steps;
   P.debug_flags = getenv("B2SVM_DEBUG_FLAGS") ? atoi(getenv("B2SVM_DEBUG_FLAGS")) : 0;
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
-  P.poll_delay = env_int("B2SVM_POLL_DELAY", 300);
+  P.poll_delay = env_int("B2SVM_POLL_DELAY", 500);
   P.poll_gap = env_int("B2SVM_POLL_GAP", 0);
   P.poll_delay2 = env_int("B2SVM_POLL_DELAY2", 0);
   P.poll_gap2 = env_int("B2SVM_POLL_GAP2", 0);

@@ -813,20 +813,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             // from the box slot of the rank it came from; every unit is re-read until it carries this epoch
             const uint4* slot = box_base + (((size_t)par * BOX_RANKS + wsrc) * NCAND + k) * BOX_UNITS;
             uint32_t spins = 0;
+            const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+            uint4 a4 = none, n4 = none, k4 = none;
+            uint4 lo[QL], hi[QL];
+#pragma unroll
+            for (int q = 0; q < QL; ++q) lo[q] = hi[q] = none;
             for (;;) {
+              // (only what has not arrived yet is read again: re-reading all 2 CH + 3 units from every CTA of the GPU
+              // would compete with the very stores it waits for)
               bool ok = true;
-              const uint4 a4 = ld_relaxed_sys_v4(slot + 1);
-              const uint4 n4 = ld_relaxed_sys_v4(slot + 2);
-              const uint4 k4 = sizeof(T) == 8 ? ld_relaxed_sys_v4(slot + 3) : n4;
-              uint4 lo[QL], hi[QL];
+              if (!unit_ok(a4, epoch)) a4 = ld_relaxed_sys_v4(slot + 1);
+              if (!unit_ok(n4, epoch)) n4 = ld_relaxed_sys_v4(slot + 2);
+              if (sizeof(T) == 8) { if (!unit_ok(k4, epoch)) k4 = ld_relaxed_sys_v4(slot + 3); }
 #pragma unroll
               for (int q = 0; q < QL; ++q) {
                 const int c = lane + 32 * q;
                 if (c < CH && P.kind != K_PRECOMPUTED) {
-                  lo[q] = ld_relaxed_sys_v4(slot + 4 + 2 * c);
-                  hi[q] = ld_relaxed_sys_v4(slot + 4 + 2 * c + 1);
+                  if (!unit_ok(lo[q], epoch)) lo[q] = ld_relaxed_sys_v4(slot + 4 + 2 * c);
+                  if (!unit_ok(hi[q], epoch)) hi[q] = ld_relaxed_sys_v4(slot + 4 + 2 * c + 1);
                 }
               }
+              if (sizeof(T) != 8) k4 = n4;
               ok = unit_ok(a4, epoch) && unit_ok(n4, epoch) && unit_ok(k4, epoch);
               w_alpha = __hiloint2double((int)a4.y, (int)a4.x);
               if (sizeof(T) == 8) { nrm = (T)__hiloint2double((int)n4.y, (int)n4.x); kself = (T)__hiloint2double((int)k4.y, (int)k4.x); }
