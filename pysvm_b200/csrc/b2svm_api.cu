@@ -487,7 +487,10 @@ int plan_T(b2svm_handle* h) {
   // every rank of a sharded solve must launch the same number of CTAs (the mailbox is indexed rank * ncta + cta):
   // plan with the common slice size, not with this rank's (possibly shorter) last slice
   const long long plan_tiles = h->d.world > 1 ? (h->rows_per_rank + C::BR - 1) / C::BR : h->ntiles;
-  int min_tiles = NW;
+  // CTAs per problem: as many as leave every CTA at least five tiles.  (Measured on slices of 4k-25k rows, d = 128:
+  // spreading the sweep over more SMs wins 5-13 % over one tile per warp although every CTA then polls more records;
+  // `scripts/gpu_min_tiles.py`.)
+  int min_tiles = 5;
   if (const char* e = getenv("B2SVM_MIN_TILES_PER_CTA")) min_tiles = std::max(1, atoi(e));
   int max_ctas = h->d.max_ctas > 0 ? h->d.max_ctas : h->num_sms;
   if (const char* e = getenv("B2SVM_MAX_CTAS")) max_ctas = std::max(1, atoi(e));
