@@ -601,8 +601,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             if (t < ncta && t != cta) st_relaxed_v4(l1_slot(t), rec);
           }
         }
-        // ---- poll loads of the first pass go out right away (they are looked at after the alpha hand-over below);
-        // this CTA's own record never leaves its registers
+        // ---- the poll itself starts after the alpha hand-over below (see there why not earlier); this CTA's own
+        // record never leaves its registers
         uint4 h[MAXM];
 #pragma unroll
         for (int mm = 0; mm < MAXM; ++mm) h[mm] = make_uint4(0u, 0u, 0u, 0u);
