@@ -156,6 +156,12 @@ int b2svm_rho_b(b2svm_handle* h, double* rho, double* b);
  * whose ranks merge them before forming rho / (rho, b). */
 int b2svm_bias_partials(b2svm_handle* h, double* out);
 
+/* Frees the handle's Q-column cache (the reference's LRU of solver.py:207, here up to 70 % of the device memory) while
+ * keeping the handle usable: rho / rho_b, state access and further solves (then without a cache) still work.  The
+ * estimators call it at the end of fit(), where the reference keeps the solver alive inside the decision_function
+ * closure (svc.py:269-272).  No-op for precomputed kernels and cache-less handles. */
+int b2svm_release_cache(b2svm_handle* h);
+
 /* decision_function core (svc.py:269-272, :436-439; svr.py:191-194, :297-300; oc_svm.py:108-111):
  *   out[q] = sum_s coef[s] * K(Xa[s], Xb[q])      (no n_a x n_b matrix is materialised)
  * Xa: dev [na][lda], Xb: dev [nb][ldb] (dtype x_dtype), coef: dev float64 [na], out: dev float64 [nb].

@@ -18,7 +18,7 @@ EXPORTS = [
     "b2svm_abi_version", "b2svm_last_error", "b2svm_create", "b2svm_destroy", "b2svm_init_state",
     "b2svm_init_gradient", "b2svm_select", "b2svm_update", "b2svm_kernel_column", "b2svm_solve",
     "b2svm_rho", "b2svm_rho_b", "b2svm_kernel_matvec", "b2svm_rff_transform", "b2svm_rff_decision",
-    "b2svm_solve_batched", "b2svm_mailbox_export", "b2svm_mailbox_attach", "b2svm_prepare", "b2svm_bias_partials",
+    "b2svm_solve_batched", "b2svm_mailbox_export", "b2svm_mailbox_attach", "b2svm_prepare", "b2svm_bias_partials", "b2svm_release_cache",
     "b2svm_host_std", "b2svm_solve_ranks_on_one_gpu", "b2svm_rff_transform_f32", "b2svm_kernel_matrix", "b2svm_weighted_rows", "b2svm_select_wss3",
 ]
 
@@ -101,6 +101,7 @@ def load():
     lib.b2svm_mailbox_attach.argtypes = [vp, vp]
     lib.b2svm_prepare.argtypes = [vp]
     lib.b2svm_bias_partials.argtypes = [vp, P(dbl)]
+    lib.b2svm_release_cache.argtypes = [vp]
     lib.b2svm_host_std.argtypes = [vp, i64, i32, P(dbl)]
     for name in EXPORTS:
         fn = getattr(lib, name)          # AttributeError here = header / library mismatch

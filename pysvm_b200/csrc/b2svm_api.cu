@@ -1105,6 +1105,26 @@ static int bias_stats(b2svm_handle* h, BiasStats* host) {
  * out[0..5]  = sum_free, cnt_free, min_lb, cnt_lb, max_ub, cnt_ub            (solver.py:160-177)
  * out[6+6c..] = nsum, ncnt, nmax_hi, nhi, nmin_lo, nlo for class c = 0 (+1), 1 (-1)   (solver.py:378-419)
  * Empty extremes are reported as +inf (min) / -inf (max). */
+int b2svm_release_cache(b2svm_handle* h) {
+  // After a fit the solver object lives on (rho, state export, the reference keeps it inside its decision_function
+  // closure), but its Q-column cache -- up to 70 % of the device memory -- is dead weight: hand it back.  Later
+  // solves on the handle run without a cache.
+  if (!h) return fail(B2SVM_E_INVALID, "null handle");
+  if (h->precomputed || h->cache_slots == 0) return B2SVM_OK;
+  B2_CUDA(cudaSetDevice(h->d.device));
+  if (h->stream) B2_CUDA(cudaStreamSynchronize(h->stream)); else B2_CUDA(cudaDeviceSynchronize());
+  if (h->cache_pooled) pool_free(h->cache, h->stream); else cudaFree(h->cache);
+  pool_free(h->slot_of, h->stream);
+  pool_free(h->row_of_slot, h->stream);
+  h->cache = nullptr;
+  h->slot_of = nullptr;
+  h->row_of_slot = nullptr;
+  h->cache_slots = 0;
+  h->cache_used = 0;
+  h->cache_hand = 0;
+  return B2SVM_OK;
+}
+
 int b2svm_bias_partials(b2svm_handle* h, double* out /* host [18] */) {
   if (!h || !out) return fail(B2SVM_E_INVALID, "null argument");
   BiasStats s;

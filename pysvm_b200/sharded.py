@@ -365,6 +365,7 @@ class ShardedFit:
     def __init__(self, solver: "ShardedSolver", shard: Shard, coef_local: torch.Tensor, mirror: bool, group=None):
         self.solver, self.shard, self.coef_local, self.mirror, self.group = solver, shard, coef_local, mirror, group
         self.func = solver._engine.func
+        solver.release_cache()        # (as svc._Fitted: the fit is over, the column cache goes back to the device)
 
     def kernel_sum(self, x) -> np.ndarray:
         return decision_sharded(self.solver, self.coef_local, x, self.group)

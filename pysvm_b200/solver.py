@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -102,9 +103,10 @@ class QColumns:
         return self.X.shape[0]
 
     def __call__(self, i: int) -> torch.Tensor:
-        if self._engine is None:
-            raise RuntimeError("QColumns is not bound to a solver yet")
-        return self._engine.column(int(i))
+        eng = self._engine() if self._engine is not None else None
+        if eng is None:
+            raise RuntimeError("QColumns is not bound to a (live) solver")
+        return eng.column(int(i))
 
 
 class _Engine:
@@ -163,7 +165,8 @@ class _Engine:
         torch.cuda.synchronize(func.device)          # handle work runs on the legacy default stream
         N.check(self.lib.b2svm_create(C.byref(d), C.byref(h)))
         self.h = h
-        func._engine = self
+        func._engine = weakref.ref(self)        # (weak: solver -> engine -> func must not be a cycle, or the handle and its
+                                                #  cache -- tens of GB -- would outlive `del solver` until a gc pass)
 
     def close(self):
         if getattr(self, "h", None):
@@ -175,6 +178,11 @@ class _Engine:
             self.close()
         except Exception:
             pass
+
+    def release_cache(self):
+        """Hand the Q-column cache back to the device (b2svm_release_cache); the handle stays usable."""
+        if getattr(self, "h", None):
+            N.check(self.lib.b2svm_release_cache(self.h))
 
     # -- thin wrappers -----------------------------------------------------------------------
     def init_state(self, p: torch.Tensor):
@@ -358,6 +366,13 @@ class Solver:
     def get_Q(self, i: int, func=None) -> torch.Tensor:
         """solver.py:179-184 / 227-229."""
         return self._need(func).column(i)
+
+    def release_cache(self) -> None:
+        """Free the device-resident Q-column cache once no further solve is planned (the estimators do it at the end
+        of ``fit``: the reference keeps the solver alive inside its ``decision_function`` closure, svc.py:269-272, and
+        here that would pin up to 70 % of the device memory).  rho, alpha and further (cache-less) solves still work."""
+        if self._engine is not None:
+            self._engine.release_cache()
 
     # -- fused driver loop ----------------------------------------------------------------------------
     def solve(self, max_iter: int, func=None, wss: str = "mvp") -> N.SolveStats:

@@ -84,6 +84,7 @@ class _Fitted:
         self.Z = Z            # random Fourier features of the training rows (rff=True)
         self.X_train = X_train if X_train is not None else func.X     # (dense-Q mode: func.X is the kernel matrix)
         self._wz = None
+        solver.release_cache()        # the fit is over: the solver stays (rho, state), its column cache does not
 
     def kernel_sum(self, x) -> np.ndarray:
         """coef . K(X_train, x) as float64 NumPy (svc.py:269-272 without the n x m matrix)."""

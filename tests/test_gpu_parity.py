@@ -242,6 +242,41 @@ def test_back_to_back_solves_do_not_leak_state(golden, diabetes):
         assert fit() == first
 
 
+def test_fit_hands_the_column_cache_back():
+    """After fit() the estimator keeps its solver (the reference keeps it inside the decision_function closure), but not
+    the Q-column cache: device memory in use returns to (about) what X, alpha and the gradient take; rho and further
+    solves on the kept solver still work, and dropping a solver frees its handle at once (no reference cycle).
+    (Caches above 1 GB are plain device allocations; smaller ones live in the stream-ordered pool, which keeps them.)"""
+    import gc
+    import torch
+    _, P, S, svc, _, _ = _mods()
+    X, y01 = O.synth_classification(n=20000, d=16, seed=5)            # full kernel matrix: 1.6 GB of float32 columns
+    X = X.astype(np.float32)
+    gc.collect()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    est = svc.BiKernelSVC(max_iter=60000).fit(X, y01)
+    assert est.solve_stats_["cache_stores"] > 0                        # the cache was in use during the fit
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 256 << 20, (free0 - free1) >> 20           # X + vectors + pool / allocator slack, not 1.6 GB
+    s = est._fitted.solver
+    rel_close(s.calculate_rho(), est.rho_)
+    st = s.solve(50)                                                    # still usable, now on the cold path
+    assert st.cache_stores == 0
+    # no cycle: the handle goes when the last reference goes
+    yv = np.where(y01 == 1, 1.0, -1.0)
+    func = S.QColumns(X, yv, S.KernelSpec("rbf", 0.05), cache_bytes=1500 << 20)
+    sol = S.SolverWithCache(-np.ones(len(yv)), yv, 1.0, func=func)
+    sol.solve(10)
+    torch.cuda.synchronize()
+    held, _ = torch.cuda.mem_get_info()
+    del sol, func
+    torch.cuda.synchronize()
+    after, _ = torch.cuda.mem_get_info()
+    assert after - held > 1 << 30, (after - held) >> 20
+
+
 def test_linear_estimators(golden, breast_cancer, diabetes):
     *_, svc, svr, _ = _mods()
     X, y = breast_cancer
