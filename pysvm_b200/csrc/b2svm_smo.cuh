@@ -30,19 +30,31 @@
 //     and reduces them with REDUX.  No line is ever polled by two SMs: with one shared mailbox the 2 x 148 polling
 //     warps kept the L2 slices of those few lines so busy that the last record became visible only 3.6-4.9 us after
 //     its store (0.7-0.9 us with 12 CTAs), measured with the global timer.
-//   level 2 (row-sharded box, world > 1): the CTA that owns a GPU-level winner pushes its record into the private
-//     level-2 mailbox of EVERY CTA OF EVERY GPU over NVLink (CUDA-IPC peer mappings; 16 bytes each), and TOGETHER
-//     WITH IT alpha, norm, K(x,x) and the row x itself into the box slot [rank][type] of every GPU (SURVEY 8e:
-//     candidates travel with their rows); the type warps poll the `world` records of their private mailbox and then
-//     read the winning row from the local box.  Row units are {8 payload bytes, epoch, ~epoch}: self-validating like
-//     the records.  Each GPU holds ONLY ITS OWN rows of X; nothing but these pushes crosses the link.
+//     Polling is paced: the first poll goes out ~500 cycles after the alpha hand-over (~1000 after the publish), later
+//     polls re-read only the records still missing.  Polling from the publish on, or with two polls in flight, gets
+//     in the way of the records still travelling (measured: -4 % each).
+//   level 2 (row-sharded box, world > 1): every CTA forwards its GPU's winner to its counterpart -- the CTA with the
+//     same index -- on every GPU over NVLink (CUDA-IPC peer mappings): one 16-byte store per destination, one store
+//     instruction (lane = rank), into that CTA's private level-2 mailbox; the CTA that owns the GPU-level winner
+//     pushes, TOGETHER WITH IT, alpha, norm, K(x,x) and the row x itself into the box slot [rank][type] of every GPU
+//     (candidates travel with their rows); the type warps poll the `world` records of their private
+//     mailbox and then read the winning row from the local box (re-reading only the units that have not arrived).
+//     Row units are {8 payload bytes, epoch, ~epoch}: self-validating like the records.  Each GPU holds ONLY ITS OWN
+//     rows of X; nothing but these pushes crosses the link.
 // A polled 16-byte unit is {payload, payload, epoch, ~epoch} (records: {g, g, idx, epoch<<3 | flags}) and the reader
 // consumes ALL FOUR words: ptxas narrows a vector load whose components are partly dead into separate scalar loads
 // (observed: ld.relaxed.sys.v4 with .y/.w unused became two LDG.32), and then payload and tag are no longer read by
 // one memory transaction -- a stale payload can pass the tag check (found by comparing every leader's view per epoch).
+// The same tags guard the alpha hand-over through SHARED memory, which is not cleared between launches: the slots are
+// zeroed at kernel start (a unit parked by an earlier solve at the same epoch number once passed for the current one).
 // The owner's row loads (world > 1) / L2 prefetch (world == 1) are issued before the level-1 poll, so the row is on
 // hand (or L2-resident) by the time the winners are known.  G / flags / alpha of a row are only ever touched by the
 // CTA (= SM) that owns the row; when every consumer warp owns at most one tile they stay in registers across sweeps.
+//
+// With the Q-column cache (CACHE) a sweep whose two columns are both resident ("warm") reads nothing but those columns
+// and the gradient: it is pure memory latency, so it issues the loads of WARM_U tiles back to back before using the
+// first, the candidate update is branch-free so that those tiles interleave, and the type warps prefetch the winners'
+// cached columns into L2 as soon as the winners are known.
 #pragma once
 #include "b2svm_device.cuh"
 
