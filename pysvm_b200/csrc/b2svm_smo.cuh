@@ -24,7 +24,7 @@
 // cost 2-4 k cycles each on B200): every word that is polled carries the iteration ("epoch") it belongs to, so data
 // and flag travel together in single 16-byte relaxed stores, double-buffered by epoch parity.
 //   level 1 (inside a GPU): every CTA pushes, per candidate type, one record {key, key, ~(idx<<3|flags), epoch}
-//     (+ a 16-byte alpha unit) into the PRIVATE mailbox of every CTA of the GPU (all-to-all: ncta stores per record,
+//     into the PRIVATE mailbox of every CTA of the GPU (all-to-all: ncta stores per record,
 //     five per lane); ONE warp per candidate type ("type warp": warp k handles type k, so the arg-max and the
 //     arg-min chains run side by side) polls the ncta records of its own mailbox -- that read IS the grid barrier --
 //     and reduces them with REDUX.  No line is ever polled by two SMs: with one shared mailbox the 2 x 148 polling
@@ -131,7 +131,7 @@ constexpr int BOX_UNITS = 4 + 2 * 128;
 constexpr int BOX_RANKS = 8;
 constexpr int MAX_CTAS = 160;              // level-1 poll: 5 records per lane
 // sizes of the exchange buffers for a launch with `ncta` CTAs per problem
-__host__ __device__ inline size_t l1_units(int ncta) { return (size_t)ncta * 2 * NCAND * ((ncta + 7) & ~7); }   // records (alpha units: the same again)
+__host__ __device__ inline size_t l1_units(int ncta) { return (size_t)ncta * 2 * NCAND * ((ncta + 7) & ~7); }   // records; behind them one 128-byte outbox line per CTA for its alpha units
 __host__ __device__ inline size_t l2_record_units(int ncta) { return (size_t)ncta * 2 * NCAND * BOX_RANKS; }
 constexpr size_t BOX_BULK_UNITS = (size_t)2 * BOX_RANKS * NCAND * BOX_UNITS;
 constexpr size_t PROBLEM_SMEM_BYTES = (sizeof(ProblemDev) + 127) / 128 * 128;   // descriptor copy in front of the ring
@@ -663,14 +663,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
           ua = ld_volatile_shared_v4(&sh->wa[from_warp][k]);      // (same address in every lane: one broadcast read)
           if (!unit_ok(ua, epoch)) return;
           alpha_sent = true;
-          if (world == 1) {   // pushed all-to-all like the record (world > 1: it travels with the level-2 push instead)
-            const uint4 au = make_unit(ua.x, ua.y, epoch);
-#pragma unroll
-            for (int mm = 0; mm < MAXM; ++mm) {
-              const int t = lane + 32 * mm;
-              if (t < ncta && t != cta) st_relaxed_v4(l1_slot(t) + l1_total, au);
-            }
-          }
+          // world == 1: ONE store into this CTA's outbox (its own 128-byte line behind the mailboxes); only the winner's
+          // unit is ever read, once per CTA, after the poll -- pushing it all-to-all like the record doubled the store
+          // traffic of the exchange for a unit 147 of 148 CTAs never look at.  (world > 1: it travels with the level-2
+          // push instead.)  A snapshot, double-buffered by parity like the records: a fast CTA already storing the new
+          // alpha in its next sweep cannot race a slow leader.
+          if (world == 1 && ncta > 1 && lane == 0)
+            st_relaxed_v4(P.mbox + l1_total + ((size_t)cta * 2 + par) * NCAND + k, make_unit(ua.x, ua.y, epoch));
         };
         try_alpha();
 
@@ -867,8 +866,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) smo_persistent(const ProblemDev* 
             }
             have_row = have_alpha = true;
           } else {
-            // single GPU: the alpha unit its CTA published next to the record, the row straight from X
-            const uint4* unit = P.mbox + l1_total + (((size_t)cta * 2 + par) * NCAND + k) * nc8 + wsrc;
+            // single GPU: the alpha unit its CTA left in its outbox, the row straight from X
+            const uint4* unit = P.mbox + l1_total + ((size_t)wsrc * 2 + par) * NCAND + k;   // the winner's outbox
             uint4 u = wsrc == cta ? make_unit(0u, 0u, epoch) : ld_relaxed_v4(unit);
             if (P.kind != K_PRECOMPUTED) {
               const long long lrow = (mirror && w.idx >= lg) ? w.idx - lg : w.idx;
